@@ -1,0 +1,88 @@
+"""ctypes binding of libb200swin.so (the C-ABI declared in include/b200swin.h).
+
+There is no CPU fallback: if the library is missing or a call fails, the op raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libb200swin.so")
+
+F32, BF16 = 0, 1
+EPI_NONE, EPI_GELU, EPI_QKV, EPI_DGELU = 0, 1, 2, 3
+
+_lock = threading.Lock()
+_lib = None
+
+c_void_p, c_int, c_int64, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float,
+                                               ctypes.c_size_t)
+P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/b200swin.h (tests/test_cabi.py checks)
+SIGNATURES = {
+    "b200swin_version": (c_int, []),
+    "b200swin_last_error": (ctypes.c_char_p, []),
+    "b200swin_silog_workspace_bytes": (Z, [L]),
+    "b200swin_silog_fwd": (I, [P, I, P, L, F, P, P, P, Z, P]),
+    "b200swin_silog_bwd": (I, [P, I, P, L, F, P, P, P, P]),
+    "b200swin_window_gather": (I, [P, P, I, I, I, I, I, I, I, P]),
+    "b200swin_window_scatter": (I, [P, P, I, I, I, I, I, I, I, P]),
+    "b200swin_shift_mask": (I, [P, I, I, I, I, P]),
+    "b200swin_ln_fwd": (I, [P, P, P, P, P, L, P, P, P, L, I, F, I, P]),
+    "b200swin_ln_bwd_workspace_bytes": (Z, [L, I]),
+    "b200swin_ln_bwd": (I, [P, P, P, P, P, P, L, P, P, P, L, I, I, P, Z, P]),
+}
+
+
+def load() -> ctypes.CDLL:
+    """Load (once) and return the library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"b200swin: {LIB_PATH} is missing - build it with `python __graft_entry__.py build` "
+                    "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for these ops.")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().b200swin_last_error()
+        raise RuntimeError(f"b200swin {what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"b200swin supports float32 and bfloat16 tensors, got {t.dtype}")
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_of(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def require_cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("b200swin ops run on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
