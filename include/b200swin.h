@@ -86,6 +86,74 @@ int b200swin_ln_bwd(const void* dy, const void* x, const float* gamma, const flo
                     const float* row_scale, int64_t rows_per_scale, void* dx, float* dgamma, float* dbeta,
                     int64_t rows, int C, int dtype, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Attention core.  Replaces, for attn_type='cosine_mh', the body of WindowAttention.forward between
+ * the qkv projection and the output projection (models/swin_transformer_v2.py:292-328) TOGETHER with
+ * the block's pad / roll / window_partition / window_reverse / roll-back / crop (:429-463) and
+ * BasicLayer's shift mask (:874-892), all folded into the kernel's load/store addressing:
+ *
+ *   qkv  [B,H,W,3C]  natural token order, columns [q | k | v], head h = columns h*32..h*32+31 of each
+ *                    part; q and k ALREADY L2-normalised per head (EPI_QKV epilogue of b200swin_linear),
+ *   out  [B,H,W,C]   softmax(scale_h * q.k^T + table16[rel_idx(i,j),h] + mask) @ v, natural order,
+ *   lse  [B*nW,nH,N] float32 log-sum-exp per row (saved for backward), N = ws*ws.
+ *
+ * Pad tokens (zero rows added by F.pad) are not masked by the reference: their k is 0, their v is
+ * v_bias and their q is q_bias; the kernel synthesises them from qpad[C] (= normalised q_bias) and
+ * vpad[C] (= v_bias), both float32 and required only when H or W is not a multiple of ws.
+ * table16 [(2ws-1)^2, nH] float32 is the bias table AFTER 16*sigmoid (:304-313), scale [nH] float32 is
+ * exp(min(logit_scale, ln 100)) (:294).  The shift mask ({0,-100}) is computed on the fly from token
+ * coordinates when shift > 0; alternatively an explicit mask [nWm,N,N] float32 (window b uses
+ * mask[b % nWm], :319-322) can be given - this is the standalone WindowAttention.forward(x, mask)
+ * call, made with B = B_, H = W = ws, shift = 0.
+ *
+ * Backward: dout [B,H,W,C] -> dqkv [B,H,W,3C] holding dq, dk (gradients w.r.t. the UN-normalised q, k:
+ * the F.normalize backward is applied with inv_norm [B*H*W, 2, nH] float32 = 1/max(|q|,1e-12),
+ * 1/max(|k|,1e-12)) and dv; plus float32 accumulators that the caller zero-initialises:
+ * dtable16 [(2ws-1)^2, nH], dscale [nH] (= sum dS*cos), dvpad [C] (gradient reaching v_bias through
+ * pad tokens).  impl: 0 = fp32 CUDA-core kernel (any dtype, reference precision),
+ * 1 = tcgen05 tensor-core kernel (bf16 storage only).  head_dim must be 32 (every Swin-V2 variant).
+ * ------------------------------------------------------------------------------------------ */
+int b200swin_attn_fwd(const void* qkv, void* out, float* lse, const float* table16, const float* scale,
+                      const float* qpad, const float* vpad, const float* mask, int nWm, int B, int H, int W,
+                      int C, int nH, int ws, int shift, int dtype, int impl, void* stream);
+int b200swin_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
+                      const float* table16, const float* scale, const float* qpad, const float* vpad,
+                      const float* mask, int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, int B,
+                      int H, int W, int C, int nH, int ws, int shift, int dtype, int impl, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense contraction on tcgen05 tensor cores:  out[M,N] = epilogue( A[M,K] . B[N,K]^T ).
+ * Replaces F.linear / nn.Linear at models/swin_transformer_v2.py:286 (qkv), :334 (proj), :77 and :87
+ * (Mlp.fc1 / fc2) and their autograd (dgrad, wgrad).
+ *  - a_hi / b_hi: bf16 operands.  *_mn_major = 0: stored [M][K] / [N][K] (K contiguous, i.e. x and
+ *    nn.Linear.weight as they are); 1: stored [K][M] / [K][N].  dgrad (dX = dY.W) passes W with
+ *    b_mn_major = 1, wgrad (dW = dY^T.X) passes dY and X with both = 1: no transposed copy is made.
+ *  - a_lo / b_lo (both or neither): low bf16 halves from b200swin_split_bf16; the kernel then
+ *    accumulates hi.hi + hi.lo + lo.hi, which reproduces an fp32 GEMM to ~1e-5 relative.
+ *  - epilogue (B200SWIN_EPI_*): NONE: + bias[N] (nullable).  GELU: + bias, aux_out (nullable) receives
+ *    the pre-activation, out = erf-GELU.  DGELU: out = acc * gelu'(aux_in).  QKV: N = 3C; adds bias
+ *    (= q_bias[C]) to the q columns, nothing to k, bias2 (= v_bias[C]) to v; L2-normalises every
+ *    32-wide head slice of q and k in fp32 (F.normalize, eps 1e-12, :292-293) and writes
+ *    inv_norm[M,2,nH] = 1/max(|q|,eps), 1/max(|k|,eps) (nullable).
+ *  - out/aux dtype = out_dtype; accumulation is fp32.  splits > 1: split-K over blockIdx.z with fp32
+ *    partials in workspace and a fixed-order reduction (NONE epilogue only; used by wgrad).
+ * Shape rules: N % 4 == 0; the contiguous dimension of each operand % 8 == 0; base pointers 16-B aligned.
+ * ------------------------------------------------------------------------------------------ */
+int b200swin_gemm_splits(int64_t M, int64_t N, int64_t K);
+size_t b200swin_gemm_workspace_bytes(int64_t M, int64_t N, int splits);
+int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_major, const void* b_hi, const void* b_lo,
+                       int b_mn_major, int64_t M, int64_t N, int64_t K, int epilogue, const float* bias,
+                       const float* bias2, const void* aux_in, void* aux_out, float* inv_norm, int nH, void* out,
+                       int out_dtype, int splits, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Helpers around the GEMM (HBM-bound): fp32 -> bf16 hi (+ lo residual, nullable) split, and column sums
+ * out[n] = extra[n] + sum_m x[m, col0+n] over an [M, ld] matrix (bias gradients: q_bias/v_bias at
+ * :283-285, proj/fc biases). */
+int b200swin_split_bf16(const float* src, void* hi, void* lo, int64_t n, void* stream);
+size_t b200swin_colsum_workspace_bytes(int64_t M, int ncols);
+int b200swin_colsum(const void* x, int dtype, int64_t M, int64_t ld, int64_t col0, int ncols, const float* extra,
+                    float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

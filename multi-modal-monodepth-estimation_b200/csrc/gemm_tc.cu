@@ -1,0 +1,413 @@
+// tcgen05 GEMM for the dense contractions of the Swin-V2 block (qkv, proj, fc1, fc2; forward, dgrad, wgrad):
+//     D[M,N] = epilogue( A[M,K] . B[N,K]^T )      bf16 operands, fp32 accumulation in TMEM.
+// Replaces F.linear / nn.Linear at models/swin_transformer_v2.py:286 (qkv), :334 (proj), :77/:87 (Mlp) and
+// their autograd.
+//
+// * operands are staged by TMA (cp.async.bulk.tensor, 128 B swizzle) into a 3-stage mbarrier ring;
+// * one elected thread issues tcgen05.mma (M=128, N=128, K=16 per instruction) into a 128-column TMEM
+//   accumulator; tcgen05.commit releases smem stages and signals the epilogue;
+// * 4 epilogue warps read the accumulator with tcgen05.ld (one row per thread) and apply the fused epilogue:
+//     NONE  (+bias) | GELU (bias, erf GELU, optional pre-activation copy) | QKV (q_bias/0/v_bias, per-head
+//     L2-normalisation of q and k in fp32 + 1/|q|,1/|k| side output) | DGELU (multiply by gelu'(aux));
+// * either operand may be "MN-major" (stored [K][M] / [K][N]), which is how dgrad (B = W as stored) and wgrad
+//   (A = dY, B = X as stored) run WITHOUT any transposed copy in HBM;
+// * fp32-accurate mode: operands split as hi+lo bf16 pairs, 3 MMAs per k-step (hi.hi + hi.lo + lo.hi);
+// * split-K (blockIdx.z) with fp32 partials + a fixed-order reduce, used by wgrad where K = #tokens.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "../../include/b200swin.h"
+
+namespace b200swin {
+
+namespace {
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int kGemmThreads = 192;                       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
+constexpr uint32_t kStageBytes = kABytes + kBBytes;
+constexpr size_t kSmemBytes = (size_t)STAGES * kStageBytes + 1024;   // + alignment slack
+constexpr float kInvSqrt2 = 0.70710678118654752f;
+constexpr float kInvSqrt2Pi = 0.39894228040143268f;
+}  // namespace
+
+struct GemmParams {
+  CUtensorMap tmA[2], tmB[2];
+  int nseg;
+  int64_t M, N, K;
+  int num_kb, kb_per_split;
+  int epilogue, out_dtype;
+  void* out;
+  int64_t ldo;
+  const float* bias;
+  const float* bias2;
+  const void* aux_in;
+  void* aux_out;
+  float* inv_norm;
+  int nH, Cq;
+  float* partial;
+};
+
+__device__ __forceinline__ float gelu_erf(float z) { return 0.5f * z * (1.0f + erff(z * kInvSqrt2)); }
+__device__ __forceinline__ float gelu_grad(float z) {
+  return 0.5f * (1.0f + erff(z * kInvSqrt2)) + z * kInvSqrt2Pi * __expf(-0.5f * z * z);
+}
+
+template <typename T>
+__device__ __forceinline__ void store_chunk(T* p, const float (&v)[32], int nvalid) {
+  if (nvalid >= 32) {
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      float t[4] = {v[c], v[c + 1], v[c + 2], v[c + 3]};
+      st4(p + c, t);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < nvalid) Io<T>::st(p + c, v[c]);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void load_chunk32(const T* p, float (&v)[32], int nvalid) {
+  if (nvalid >= 32) {
+#pragma unroll
+    for (int c = 0; c < 32; c += 4) {
+      float t[4];
+      ld4(p + c, t);
+      v[c] = t[0]; v[c + 1] = t[1]; v[c + 2] = t[2]; v[c + 3] = t[3];
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = (c < nvalid) ? Io<T>::ld(p + c) : 0.f;
+  }
+}
+
+template <typename OutT>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[32], int64_t row, int64_t col0,
+                                               int nvalid) {
+  OutT* out = reinterpret_cast<OutT*>(p.out) + row * p.ldo + col0;
+  if (p.epilogue == B200SWIN_EPI_NONE) {
+    if (p.bias) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < nvalid) v[c] += p.bias[col0 + c];
+    }
+    store_chunk<OutT>(out, v, nvalid);
+  } else if (p.epilogue == B200SWIN_EPI_GELU) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < nvalid && p.bias) v[c] += p.bias[col0 + c];
+    if (p.aux_out) store_chunk<OutT>(reinterpret_cast<OutT*>(p.aux_out) + row * p.ldo + col0, v, nvalid);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = gelu_erf(v[c]);
+    store_chunk<OutT>(out, v, nvalid);
+  } else if (p.epilogue == B200SWIN_EPI_DGELU) {
+    float z[32];
+    load_chunk32<OutT>(reinterpret_cast<const OutT*>(p.aux_in) + row * p.ldo + col0, z, nvalid);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] *= gelu_grad(z[c]);
+    store_chunk<OutT>(out, v, nvalid);
+  } else {  // B200SWIN_EPI_QKV: one 32-column chunk == one head of q, k or v  (swin_transformer_v2.py:283-293)
+    const int part = (int)(col0 / p.Cq);
+    const int cin = (int)(col0 - (int64_t)part * p.Cq);
+    const float* b = part == 0 ? p.bias : (part == 2 ? p.bias2 : nullptr);
+    if (b) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] += b[cin + c];
+    }
+    if (part < 2) {
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) ss = fmaf(v[c], v[c], ss);
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);          // F.normalize(eps=1e-12)
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] *= inv;
+      if (p.inv_norm) p.inv_norm[(row * 2 + part) * p.nH + (cin >> 5)] = inv;
+    }
+    store_chunk<OutT>(out, v, nvalid);
+  }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const uint32_t smem_base = (ptx::smem_u32(smem_dyn) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024 B alignment
+  unsigned char* smem_al = smem_dyn + (smem_base - ptx::smem_u32(smem_dyn));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int64_t n0 = (int64_t)blockIdx.y * BN;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+  const int iters = (kb1 - kb0) * p.nseg;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    ptx::mbar_init(&accum_bar, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&p.tmA[0]);
+    ptx::prefetch_tmap(&p.tmB[0]);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_slot, BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+        const int seg = it / (kb1 - kb0);
+        const int kb = kb0 + it - seg * (kb1 - kb0);
+        const CUtensorMap* ta = &p.tmA[seg == 2 ? 1 : 0];           // segments: hi.hi, hi.lo, lo.hi
+        const CUtensorMap* tb = &p.tmB[seg == 1 ? 1 : 0];
+        unsigned char* sa = smem_al + (size_t)s * kStageBytes;
+        unsigned char* sb = sa + kABytes;
+        ptx::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+        const int k0 = kb * BK;
+        if (A_MN) {
+          ptx::tma_load_2d(sa, ta, &full_bar[s], (int)m0, k0);
+          ptx::tma_load_2d(sa + kABytes / 2, ta, &full_bar[s], (int)m0 + 64, k0);
+        } else {
+          ptx::tma_load_2d(sa, ta, &full_bar[s], k0, (int)m0);
+        }
+        if (B_MN) {
+          ptx::tma_load_2d(sb, tb, &full_bar[s], (int)n0, k0);
+          ptx::tma_load_2d(sb + kBBytes / 2, tb, &full_bar[s], (int)n0 + 64, k0);
+        } else {
+          ptx::tma_load_2d(sb, tb, &full_bar[s], k0, (int)n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        ptx::mbar_wait(&full_bar[s], ph);
+        ptx::tc_fence_after();
+        const uint32_t sa = smem_base + (uint32_t)s * kStageBytes;
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // K-major: 16 bf16 = 32 B along the swizzle row; MN-major: 16 k-rows = 2048 B
+          const uint64_t ad = A_MN ? ptx::make_smem_desc(sa + k * 2048, kABytes / 2, 1024)
+                                   : ptx::make_smem_desc(sa + k * 32, 16, 1024);
+          const uint64_t bd = B_MN ? ptx::make_smem_desc(sb + k * 2048, kBBytes / 2, 1024)
+                                   : ptx::make_smem_desc(sb + k * 32, 16, 1024);
+          ptx::mma_bf16_ss(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs retire
+      }
+      ptx::mma_commit(&accum_bar);               // accumulator complete
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue warps (TMEM -> HBM)
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int64_t row = m0 + q * 32 + lane;
+    if (iters > 0) {
+      ptx::mbar_wait(&accum_bar, 0);
+      ptx::tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int64_t col0 = n0 + c * 32;
+      if (col0 >= p.N) break;                    // warp-uniform
+      float v[32];
+      if (iters > 0) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+      }
+      if (row < p.M) {
+        const int nvalid = (int)min((int64_t)32, p.N - col0);
+        if (p.partial) {
+          store_chunk<float>(p.partial + ((int64_t)blockIdx.z * p.M + row) * p.N + col0, v, nvalid);
+        } else if (p.out_dtype == B200SWIN_BF16) {
+          epilogue_chunk<__nv_bfloat16>(p, v, row, col0, nvalid);
+        } else {
+          epilogue_chunk<float>(p, v, row, col0, nvalid);
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// fixed-order split-K reduction: out[m,n] = sum_z partial[z,m,n] (+ bias[n])
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t MN, int64_t N,
+                     const float* __restrict__ bias, OutT* __restrict__ out) {
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < MN;
+       i += (int64_t)gridDim.x * blockDim.x * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int z = 0; z < splits; ++z) {
+      float t[4];
+      ld4(partial + (int64_t)z * MN + i, t);
+      acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2]; acc[3] += t[3];
+    }
+    if (bias) {
+      int64_t n = i % N;
+      acc[0] += bias[n]; acc[1] += bias[n + 1]; acc[2] += bias[n + 2]; acc[3] += bias[n + 3];
+    }
+    st4(out + i, acc);
+  }
+}
+
+// --------------------------------------------------------------------------------------- host side
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn enc = get_encode_tiled();
+  BSW_REQUIRE(enc, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  BSW_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA: base pointer must be 16-byte aligned");
+  BSW_REQUIRE(outer_stride_bytes % 16 == 0, "TMA: row stride (%llu B) must be a multiple of 16",
+              (unsigned long long)outer_stride_bytes);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {outer_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BSW_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return B200SWIN_OK;
+}
+
+static int operand_map(CUtensorMap* m, const void* ptr, int mn_major, int64_t mn, int64_t k) {
+  // K-major: stored [mn][k] -> box {BK, 128 rows};  MN-major: stored [k][mn] -> box {64 mn, BK k-rows}
+  if (mn_major) return make_tmap_2d_bf16(m, ptr, (uint64_t)mn, (uint64_t)k, (uint64_t)mn * 2, 64, BK);
+  return make_tmap_2d_bf16(m, ptr, (uint64_t)k, (uint64_t)mn, (uint64_t)k * 2, BK, 128);
+}
+
+}  // namespace b200swin
+
+using namespace b200swin;
+
+extern "C" int b200swin_gemm_splits(int64_t M, int64_t N, int64_t K) {
+  // split-K factor the library would pick so that the grid covers the SMs about twice
+  int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int64_t num_kb = (K + BK - 1) / BK;
+  int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
+  if (want < 1) want = 1;
+  int64_t max_splits = num_kb / 8 > 0 ? num_kb / 8 : 1;      // keep >= 8 k-blocks per split
+  if (want > max_splits) want = max_splits;
+  if (want > 256) want = 256;
+  return (int)want;
+}
+
+extern "C" size_t b200swin_gemm_workspace_bytes(int64_t M, int64_t N, int splits) {
+  return splits > 1 ? (size_t)splits * (size_t)M * (size_t)N * sizeof(float) : 0;
+}
+
+extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_major, const void* b_hi,
+                                  const void* b_lo, int b_mn_major, int64_t M, int64_t N, int64_t K, int epilogue,
+                                  const float* bias, const float* bias2, const void* aux_in, void* aux_out,
+                                  float* inv_norm, int nH, void* out, int out_dtype, int splits, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  BSW_REQUIRE(a_hi && b_hi && out, "gemm: null pointer");
+  BSW_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: non-positive dimension");
+  BSW_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension exceeds 2^31");
+  BSW_REQUIRE((a_lo == nullptr) == (b_lo == nullptr), "gemm: a_lo and b_lo must be given together");
+  BSW_REQUIRE(out_dtype == B200SWIN_F32 || out_dtype == B200SWIN_BF16, "gemm: bad out dtype %d", out_dtype);
+  BSW_REQUIRE(epilogue >= B200SWIN_EPI_NONE && epilogue <= B200SWIN_EPI_DGELU, "gemm: bad epilogue %d", epilogue);
+  BSW_REQUIRE(N % 4 == 0, "gemm: N must be a multiple of 4");
+  BSW_REQUIRE((a_mn_major ? M : K) % 8 == 0 && (b_mn_major ? N : K) % 8 == 0,
+              "gemm: contiguous operand dimension must be a multiple of 8 (16-byte TMA rows)");
+  if (splits < 1) splits = 1;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  if (epilogue == B200SWIN_EPI_QKV) {
+    BSW_REQUIRE(N % 96 == 0 && nH > 0 && (N / 3) == (int64_t)nH * 32, "gemm: QKV epilogue needs N = 3*nH*32");
+    BSW_REQUIRE(splits == 1, "gemm: QKV epilogue cannot be split");
+    p.Cq = (int)(N / 3);
+  }
+  if (epilogue == B200SWIN_EPI_DGELU) BSW_REQUIRE(aux_in, "gemm: DGELU epilogue needs aux_in");
+  if (splits > 1) {
+    BSW_REQUIRE(epilogue == B200SWIN_EPI_NONE, "gemm: split-K supports only the plain epilogue");
+    BSW_REQUIRE(workspace && workspace_bytes >= b200swin_gemm_workspace_bytes(M, N, splits),
+                "gemm: split-K workspace too small");
+  }
+  int rc;
+  if ((rc = operand_map(&p.tmA[0], a_hi, a_mn_major, M, K))) return rc;
+  if ((rc = operand_map(&p.tmB[0], b_hi, b_mn_major, N, K))) return rc;
+  p.nseg = 1;
+  if (a_lo) {
+    if ((rc = operand_map(&p.tmA[1], a_lo, a_mn_major, M, K))) return rc;
+    if ((rc = operand_map(&p.tmB[1], b_lo, b_mn_major, N, K))) return rc;
+    p.nseg = 3;
+  }
+  p.M = M; p.N = N; p.K = K;
+  p.num_kb = (int)((K + BK - 1) / BK);
+  if (splits > p.num_kb) splits = p.num_kb;
+  p.kb_per_split = (p.num_kb + splits - 1) / splits;
+  splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.epilogue = epilogue; p.out_dtype = out_dtype;
+  p.out = out; p.ldo = N;
+  p.bias = bias; p.bias2 = bias2; p.aux_in = aux_in; p.aux_out = aux_out; p.inv_norm = inv_norm; p.nH = nH;
+  p.partial = splits > 1 ? (float*)workspace : nullptr;
+  if (splits > 1) p.bias = nullptr;
+
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)splits);
+  BSW_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm: grid too large");
+#define LAUNCH(AM, BMN)                                                                                       \
+  do {                                                                                                        \
+    BSW_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                  (int)kSmemBytes));                                                          \
+    gemm_tc_kernel<AM, BMN><<<grid, kGemmThreads, kSmemBytes, st>>>(p);                                       \
+  } while (0)
+  if (a_mn_major && b_mn_major) LAUNCH(true, true);
+  else if (a_mn_major) LAUNCH(true, false);
+  else if (b_mn_major) LAUNCH(false, true);
+  else LAUNCH(false, false);
+#undef LAUNCH
+  BSW_LAUNCH_CHECK();
+  if (splits > 1) {
+    int64_t MN = M * N;
+    int64_t blocks = (MN / 4 + 255) / 256;
+    int64_t cap = (int64_t)sm_count() * 8;
+    int g = (int)(blocks < cap ? blocks : cap);
+    if (out_dtype == B200SWIN_F32)
+      splitk_reduce_kernel<float><<<g, 256, 0, st>>>((const float*)workspace, splits, MN, N, bias, (float*)out);
+    else
+      splitk_reduce_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const float*)workspace, splits, MN, N, bias,
+                                                            (__nv_bfloat16*)out);
+    BSW_LAUNCH_CHECK();
+  }
+  return B200SWIN_OK;
+}

@@ -7,30 +7,10 @@
 // index-map parity tests.  Inside the attention block the same address math is folded into the
 // attention kernel's loads and stores, so no permuted copy touches HBM there.
 #include "common.cuh"
+#include "wingeom.cuh"
 #include "../../include/b200swin.h"
 
 namespace b200swin {
-
-struct WinGeom {
-  int B, H, W, Hp, Wp, ws, shift, nWh, nWw;
-  int64_t row_vecs;  // vectors per token row (C*elem_bytes / vec_bytes)
-};
-
-// Source token (b, i, j) on the unpadded grid for window-major slot (win, tok); returns false for a pad.
-__device__ __forceinline__ bool slot_to_token(const WinGeom& g, int64_t slot, int& b, int& i, int& j) {
-  const int N = g.ws * g.ws;
-  const int nW = g.nWh * g.nWw;
-  int64_t win = slot / N;
-  int tok = (int)(slot - win * N);
-  b = (int)(win / nW);
-  int w = (int)(win - (int64_t)b * nW);
-  int wh = w / g.nWw, ww = w - wh * g.nWw;
-  int r = tok / g.ws, c = tok - r * g.ws;
-  int si = wh * g.ws + r, sj = ww * g.ws + c;       // coordinates on the shifted padded grid
-  i = si + g.shift; if (i >= g.Hp) i -= g.Hp;       // shifted[si] = x[(si + shift) mod Hp]
-  j = sj + g.shift; if (j >= g.Wp) j -= g.Wp;
-  return i < g.H && j < g.W;
-}
 
 template <typename V, bool kGather>
 __global__ void __launch_bounds__(256)
@@ -79,10 +59,7 @@ static int check_geom(int B, int H, int W, int C, int ws, int shift, int elem_by
   BSW_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "window op: elem_bytes %d", elem_bytes);
   int64_t row_bytes = (int64_t)C * elem_bytes;
   BSW_REQUIRE(row_bytes % 4 == 0, "window op: C*elem_bytes must be a multiple of 4");
-  g->B = B; g->H = H; g->W = W; g->ws = ws; g->shift = shift;
-  g->Hp = (H + ws - 1) / ws * ws;
-  g->Wp = (W + ws - 1) / ws * ws;
-  g->nWh = g->Hp / ws; g->nWw = g->Wp / ws;
+  make_geom(g, B, H, W, ws, shift);
   bool al16 = ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
   *vec_bytes = (row_bytes % 16 == 0 && al16) ? 16 : 4;
   g->row_vecs = row_bytes / *vec_bytes;

@@ -176,3 +176,334 @@ class _LayerNormResidual(torch.autograd.Function):
 
 def layer_norm_residual(x, gamma, beta, eps, residual=None, row_scale=None, rows_per_scale=1):
     return _LayerNormResidual.apply(x, residual, gamma, beta, row_scale, int(rows_per_scale), float(eps))
+
+
+# ------------------------------------------------------------------------------ dense contractions
+def compute_dtype(x: torch.Tensor) -> torch.dtype:
+    """bf16 under torch.autocast('cuda', torch.bfloat16) (our definition of the reference's missing
+    bf16 mode) or for bf16 inputs; otherwise fp32 (reference precision)."""
+    if torch.is_autocast_enabled():
+        dt = torch.get_autocast_gpu_dtype()
+        if dt != torch.bfloat16:
+            raise TypeError("b200swin supports bfloat16 autocast only")
+        return dt
+    if x.dtype in (torch.float32, torch.bfloat16):
+        return x.dtype
+    raise TypeError(f"b200swin: unsupported activation dtype {x.dtype}")
+
+
+class Operand:
+    """A GEMM operand staged for the tensor cores: bf16 `hi` and, in fp32-accurate mode, the bf16
+    residual `lo` (x ~ hi + lo)."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo=None):
+        self.hi, self.lo = hi, lo
+
+
+def stage_operand(t: torch.Tensor, exact: bool) -> Operand:
+    """bf16 tensors pass through; fp32 tensors are cast (exact=False) or split hi/lo (exact=True)."""
+    t = t.contiguous()
+    if t.dtype == torch.bfloat16:
+        if exact:
+            raise TypeError("fp32-accurate GEMM mode needs float32 operands")
+        return Operand(t)
+    if t.dtype != torch.float32:
+        raise TypeError(f"unsupported operand dtype {t.dtype}")
+    lib = L.load()
+    with torch.cuda.device_of(t):
+        hi = torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+        lo = torch.empty_like(hi) if exact else None
+        L.check(lib.b200swin_split_bf16(t.data_ptr(), hi.data_ptr(), L.ptr(lo), t.numel(), L.stream_of(t)),
+                "split_bf16")
+    return Operand(hi, lo)
+
+
+_weight_cache: dict = {}
+
+
+def stage_weight(w: torch.Tensor, exact: bool) -> Operand:
+    """Stage a parameter once per value (keyed on the tensor's version counter, which optimizers bump)."""
+    key = (w.data_ptr(), exact)      # data_ptr is stable for a live parameter; version catches in-place updates
+    hit = _weight_cache.get(key)
+    if hit is not None and hit[0] == w._version and hit[1] == tuple(w.shape) and hit[3]() is w:
+        return hit[2]
+    import weakref
+    op = stage_operand(w.detach(), exact)
+    if len(_weight_cache) > 4096:
+        _weight_cache.clear()
+    _weight_cache[key] = (w._version, tuple(w.shape), op, weakref.ref(w))
+    return op
+
+
+def gemm(a: Operand, b: Operand, M: int, N: int, K: int, *, a_mn=False, b_mn=False, epilogue=L.EPI_NONE, bias=None,
+         bias2=None, aux_in=None, aux_out=None, inv_norm=None, nH=0, out_dtype=torch.bfloat16, splits=1):
+    """out[M,N] = epilogue(A . B^T) through b200swin_gemm_bf16 (see include/b200swin.h)."""
+    lib = L.load()
+    dev = a.hi.device
+    with torch.cuda.device(dev):
+        out = torch.empty((M, N), dtype=out_dtype, device=dev)
+        ws, ws_bytes = None, 0
+        if splits > 1:
+            ws_bytes = lib.b200swin_gemm_workspace_bytes(M, N, splits)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        L.check(lib.b200swin_gemm_bf16(a.hi.data_ptr(), L.ptr(a.lo), int(a_mn), b.hi.data_ptr(), L.ptr(b.lo), int(b_mn),
+                                       M, N, K, epilogue, L.ptr(bias), L.ptr(bias2), L.ptr(aux_in), L.ptr(aux_out),
+                                       L.ptr(inv_norm), nH, out.data_ptr(), L.dtype_code(out), splits, L.ptr(ws),
+                                       ws_bytes, L.stream_of(out)), "gemm_bf16")
+    return out
+
+
+def colsum(x: torch.Tensor, col0: int = 0, ncols: int | None = None, extra: torch.Tensor | None = None):
+    """fp32 column sums of a 2-D [M, ld] tensor over columns [col0, col0+ncols)."""
+    lib = L.load()
+    M, ld = x.shape
+    ncols = ld - col0 if ncols is None else ncols
+    with torch.cuda.device_of(x):
+        out = torch.empty(ncols, dtype=torch.float32, device=x.device)
+        ws_bytes = lib.b200swin_colsum_workspace_bytes(M, ncols)
+        ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=x.device)
+        L.check(lib.b200swin_colsum(x.data_ptr(), L.dtype_code(x), M, ld, col0, ncols, L.ptr(extra), out.data_ptr(),
+                                    ws.data_ptr(), ws_bytes, L.stream_of(x)), "colsum")
+    return out
+
+
+def _f32(t):
+    return None if t is None else t.detach().contiguous().float()
+
+
+def _wgrad(dy_op: Operand, x_op: Operand, M: int, N: int, K: int) -> torch.Tensor:
+    """dW[N,K] = dY^T . X with both operands read MN-major (as stored), split-K over the tokens."""
+    lib = L.load()
+    splits = lib.b200swin_gemm_splits(N, K, M)
+    return gemm(dy_op, x_op, N, K, M, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=splits)
+
+
+class _Linear(torch.autograd.Function):
+    """y = x @ W^T + b on tcgen05 (reference: nn.Linear at swin_transformer_v2.py:334 and others)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        L.require_cuda(x, weight, bias)
+        cd = compute_dtype(x)
+        exact = cd == torch.float32
+        N, K = weight.shape
+        x2 = x.reshape(-1, K)
+        M = x2.shape[0]
+        if cd == torch.bfloat16 and x2.dtype != torch.bfloat16:
+            x2 = x2.to(torch.bfloat16)
+        xo = stage_operand(x2, exact)
+        wo = stage_weight(weight, exact)
+        y = gemm(xo, wo, M, N, K, bias=_f32(bias), out_dtype=cd)
+        ctx.save_for_backward(xo.hi, xo.lo, weight)
+        ctx.has_bias = bias is not None
+        ctx.cd, ctx.xdtype, ctx.xshape = cd, x.dtype, x.shape
+        ctx.bdtype = bias.dtype if bias is not None else None
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xhi, xlo, weight = ctx.saved_tensors
+        exact = ctx.cd == torch.float32
+        N, K = weight.shape
+        dy2 = dy.reshape(-1, N)
+        M = dy2.shape[0]
+        if dy2.dtype != ctx.cd:
+            dy2 = dy2.to(ctx.cd)
+        dyo = stage_operand(dy2, exact)
+        wo = stage_weight(weight, exact)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dyo, wo, M, K, N, b_mn=True, out_dtype=ctx.cd).view(ctx.xshape)
+            if dx.dtype != ctx.xdtype:
+                dx = dx.to(ctx.xdtype)
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(dyo, Operand(xhi, xlo), M, N, K).to(weight.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2.contiguous()).to(ctx.bdtype)
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    return _Linear.apply(x, weight, bias)
+
+
+class _Mlp(torch.autograd.Function):
+    """fc2(GELU(fc1(x))) with the GELU fused into fc1's epilogue and gelu' fused into fc2's dgrad epilogue
+    (reference: Mlp.forward, swin_transformer_v2.py:76-89; exact-erf GELU)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        L.require_cuda(x, w1, b1, w2, b2)
+        cd = compute_dtype(x)
+        exact = cd == torch.float32
+        Hd, C = w1.shape
+        Co = w2.shape[0]
+        x2 = x.reshape(-1, C)
+        M = x2.shape[0]
+        if cd == torch.bfloat16 and x2.dtype != torch.bfloat16:
+            x2 = x2.to(torch.bfloat16)
+        xo = stage_operand(x2, exact)
+        z = torch.empty((M, Hd), dtype=cd, device=x.device)
+        h = gemm(xo, stage_weight(w1, exact), M, Hd, C, epilogue=L.EPI_GELU, bias=_f32(b1), aux_out=z, out_dtype=cd)
+        ho = stage_operand(h, exact)
+        y = gemm(ho, stage_weight(w2, exact), M, Co, Hd, bias=_f32(b2), out_dtype=cd)
+        ctx.save_for_backward(xo.hi, xo.lo, z, ho.hi, ho.lo, w1, w2)
+        ctx.cd, ctx.xdtype, ctx.xshape = cd, x.dtype, x.shape
+        ctx.bd = (b1.dtype if b1 is not None else None, b2.dtype if b2 is not None else None)
+        return y.view(*x.shape[:-1], Co)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xhi, xlo, z, hhi, hlo, w1, w2 = ctx.saved_tensors
+        exact = ctx.cd == torch.float32
+        Hd, C = w1.shape
+        Co = w2.shape[0]
+        dy2 = dy.reshape(-1, Co)
+        M = dy2.shape[0]
+        if dy2.dtype != ctx.cd:
+            dy2 = dy2.to(ctx.cd)
+        dy2 = dy2.contiguous()
+        dyo = stage_operand(dy2, exact)
+        dw2 = _wgrad(dyo, Operand(hhi, hlo), M, Co, Hd).to(w2.dtype)
+        db2 = colsum(dy2).to(ctx.bd[1]) if ctx.bd[1] is not None else None
+        dz = gemm(dyo, stage_weight(w2, exact), M, Hd, Co, b_mn=True, epilogue=L.EPI_DGELU, aux_in=z, out_dtype=ctx.cd)
+        dzo = stage_operand(dz, exact)
+        dw1 = _wgrad(dzo, Operand(xhi, xlo), M, Hd, C).to(w1.dtype)
+        db1 = colsum(dz).to(ctx.bd[0]) if ctx.bd[0] is not None else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dzo, stage_weight(w1, exact), M, C, Hd, b_mn=True, out_dtype=ctx.cd).view(ctx.xshape)
+            if dx.dtype != ctx.xdtype:
+                dx = dx.to(ctx.xdtype)
+        return dx, dw1, db1, dw2, db2
+
+
+def mlp(x, w1, b1, w2, b2):
+    return _Mlp.apply(x, w1, b1, w2, b2)
+
+
+class _QKV(torch.autograd.Function):
+    """qkv = x @ Wqkv^T + (q_bias, 0, v_bias) with q and k L2-normalised per head in the GEMM epilogue
+    (reference: swin_transformer_v2.py:283-293).  Returns (qkv_hat [T,3C], inv_norm [T,2,nH]).
+    PRIVATE CONTRACT with _AttnCore: the gradient arriving for qkv_hat is already the gradient w.r.t. the
+    UN-normalised q, k (the attention backward applies the F.normalize backward with inv_norm)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, q_bias, v_bias, nH):
+        L.require_cuda(x, weight, q_bias, v_bias)
+        cd = compute_dtype(x)
+        exact = cd == torch.float32
+        N, K = weight.shape
+        x2 = x.reshape(-1, K)
+        M = x2.shape[0]
+        if cd == torch.bfloat16 and x2.dtype != torch.bfloat16:
+            x2 = x2.to(torch.bfloat16)
+        xo = stage_operand(x2, exact)
+        inv_norm = torch.empty((M, 2, nH), dtype=torch.float32, device=x.device)
+        qkv = gemm(xo, stage_weight(weight, exact), M, N, K, epilogue=L.EPI_QKV, bias=_f32(q_bias), bias2=_f32(v_bias),
+                   inv_norm=inv_norm, nH=nH, out_dtype=cd)
+        ctx.save_for_backward(xo.hi, xo.lo, weight)
+        ctx.cd, ctx.xdtype, ctx.xshape = cd, x.dtype, x.shape
+        ctx.has_bias = q_bias is not None
+        ctx.bdtype = q_bias.dtype if q_bias is not None else None
+        ctx.mark_non_differentiable(inv_norm)
+        return qkv, inv_norm
+
+    @staticmethod
+    def backward(ctx, dqkv, _):
+        xhi, xlo, weight = ctx.saved_tensors
+        exact = ctx.cd == torch.float32
+        N, K = weight.shape
+        C = N // 3
+        d2 = dqkv.reshape(-1, N)
+        M = d2.shape[0]
+        if d2.dtype != ctx.cd:
+            d2 = d2.to(ctx.cd)
+        d2 = d2.contiguous()
+        do = stage_operand(d2, exact)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(do, stage_weight(weight, exact), M, K, N, b_mn=True, out_dtype=ctx.cd).view(ctx.xshape)
+            if dx.dtype != ctx.xdtype:
+                dx = dx.to(ctx.xdtype)
+        dw = _wgrad(do, Operand(xhi, xlo), M, N, K).to(weight.dtype)
+        dqb = dvb = None
+        if ctx.has_bias:
+            dqb = colsum(d2, 0, C).to(ctx.bdtype)
+            dvb = colsum(d2, 2 * C, C).to(ctx.bdtype)
+        return dx, dw, dqb, dvb, None
+
+
+def qkv_project(x, weight, q_bias, v_bias, nH):
+    return _QKV.apply(x, weight, q_bias, v_bias, int(nH))
+
+
+# ------------------------------------------------------------------------------ attention core
+ATTN_IMPL = {"mode": "auto"}     # "auto" | "simt" | "tc"
+
+
+def _pick_impl(dtype, ws):
+    mode = ATTN_IMPL["mode"]
+    if mode == "simt":
+        return 0
+    if mode == "tc":
+        return 1
+    return 0
+
+
+class _AttnCore(torch.autograd.Function):
+    """softmax(scale * q_hat k_hat^T + table16[rel] + mask) @ v over shifted windows, reading and writing the
+    natural [B,H,W,*] layout (pad/roll/partition/reverse/crop and the shift mask are address math).
+    Reference: swin_transformer_v2.py:295-328 + :429-463 + :874-892."""
+
+    @staticmethod
+    def forward(ctx, qkv, inv_norm, table16, scale, qpad, vpad, mask, geom):
+        B, H, W, C, nH, ws, shift = geom
+        L.require_cuda(qkv, inv_norm, table16, scale, qpad, vpad, mask)
+        lib = L.load()
+        qkv = qkv.contiguous()
+        t16 = table16.contiguous().float()
+        sc = scale.contiguous().float()
+        qp, vp, mk = _f32(qpad), _f32(vpad), _f32(mask)
+        Hp, Wp = (H + ws - 1) // ws * ws, (W + ws - 1) // ws * ws
+        nwin = B * (Hp // ws) * (Wp // ws)
+        impl = _pick_impl(qkv.dtype, ws)
+        nWm = mask.shape[0] if mask is not None else 0
+        with torch.cuda.device_of(qkv):
+            out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
+            lse = torch.empty((nwin, nH, ws * ws), dtype=torch.float32, device=qkv.device)
+            L.check(lib.b200swin_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), t16.data_ptr(), sc.data_ptr(),
+                                          L.ptr(qp), L.ptr(vp), L.ptr(mk), nWm, B, H, W, C, nH, ws, shift,
+                                          L.dtype_code(qkv), impl, L.stream_of(qkv)), "attn_fwd")
+        ctx.save_for_backward(qkv, out, lse, inv_norm, t16, sc, qp, vp, mk)
+        ctx.geom, ctx.impl, ctx.nWm = geom, impl, nWm
+        ctx.dtypes = (table16.dtype, scale.dtype, vpad.dtype if vpad is not None else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse, inv_norm, t16, sc, qp, vp, mk = ctx.saved_tensors
+        B, H, W, C, nH, ws, shift = ctx.geom
+        lib = L.load()
+        dout = dout.contiguous()
+        if dout.dtype != qkv.dtype:
+            dout = dout.to(qkv.dtype)
+        with torch.cuda.device_of(qkv):
+            dqkv = torch.empty_like(qkv)
+            acc = torch.zeros(t16.numel() + nH + C, dtype=torch.float32, device=qkv.device)
+            dt16 = acc[:t16.numel()].view_as(t16)
+            dsc = acc[t16.numel():t16.numel() + nH]
+            dvp = acc[t16.numel() + nH:]
+            L.check(lib.b200swin_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                          inv_norm.data_ptr(), t16.data_ptr(), sc.data_ptr(), L.ptr(qp), L.ptr(vp),
+                                          L.ptr(mk), ctx.nWm, dqkv.data_ptr(), dt16.data_ptr(), dsc.data_ptr(),
+                                          dvp.data_ptr(), B, H, W, C, nH, ws, shift, L.dtype_code(qkv), ctx.impl,
+                                          L.stream_of(qkv)), "attn_bwd")
+        tdt, sdt, vdt = ctx.dtypes
+        return (dqkv, None, dt16.to(tdt), dsc.view(sc.shape).to(sdt), None,
+                dvp.to(vdt) if vdt is not None else None, None, None)
+
+
+def attention_core(qkv, inv_norm, table16, scale, qpad, vpad, mask, B, H, W, C, nH, ws, shift):
+    return _AttnCore.apply(qkv, inv_norm, table16, scale, qpad, vpad, mask, (B, H, W, C, nH, ws, shift))

@@ -52,7 +52,7 @@ def test_ln_residual(rows, C, dtype, with_res, with_scale):
     tol = 1e-4 if dtype == torch.float32 else 2e-2
 
     def close(a, ref, name):
-        a = a.double().cpu()
+        a = a.detach().double().cpu()
         err = (a - ref).norm() / ref.norm().clamp_min(1e-30)
         assert err <= tol, f"{name}: rel-L2 {err:.3e}"
         if dtype == torch.float32:
