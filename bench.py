@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py - train images/sec of the Swin-V2 hot path on B200 (BASELINE.json metric, configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--pairs P] [--dtype bf16|fp32]
+
+A "step" is one pass of the hot path over one batch of synthetic NYUv2-shaped input:
+Swin-V2-B encoder (embed 128, depths [2,2,18,2], heads [4,8,16,32], windows [12,12,12,6], 24 blocks) forward
+and backward on 24 frame pairs (= 48 RGB frames of 480x480) per GPU under bf16 autocast with fp32 master
+weights, a pixel-shuffle depth read-out (one more b200swin GEMM; the reference's decoder_v2 is a cuDNN conv
+stack OUTSIDE the hot path and is not part of the step), the SiLog loss on both frames (forward + backward),
+the NCCL gradient all-reduce (N > 1) and a fused AdamW step.  images/sec = frames through the encoder / s.
+
+`value` times K steps with inputs resident in HBM (CUDA events, barrier + synchronize on both sides, max over
+ranks).  `e2e` repeats the measurement through the public module API with HOST inputs: every step copies the
+batch from pinned host memory and reads the loss back.  `roofline` is the aggregate of every tcgen05 GEMM
+launch inside the timed region (CUDA events around each launch) against the measured sustained bf16 peak.
+`cpu_baseline` / `--impl reference`: the CPU oracle (oracle/swin_ref.py, a restatement of the reference's PyTorch
+path pinned by golden vectors; the reference itself is not on the GPU box) on a bounded sample of the same
+workload with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32], window_size=[12, 12, 12, 6],
+           pretrain_window_size=[12, 12, 12, 6], use_shift=[True, True, False, False], drop_path_rate=0.3)
+IMG = 480
+MAX_DEPTH = 10.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=24, help="frame pairs per GPU (BASELINE: 24)")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--attn", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--cpu-sample-pairs", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def encoder_flops_per_frame():
+    """Algorithmic forward FLOPs per frame (SURVEY.md section 8d formula), GEMM part and attention-core part."""
+    gemm = attn = 0.0
+    T = (IMG // 4) ** 2
+    side = IMG // 4
+    for i, depth in enumerate(CFG["depths"]):
+        C = CFG["embed_dim"] * 2 ** i
+        ws = CFG["window_size"][i]
+        sp = (side + ws - 1) // ws * ws
+        Tp, N = sp * sp, ws * ws
+        gemm += depth * (2 * T * C * 3 * C + 2 * T * C * C + 16 * T * C * C)
+        attn += depth * (4 * Tp * N * C)
+        if i < len(CFG["depths"]) - 1:
+            gemm += 2 * (T // 4) * 4 * C * 2 * C
+            side = (side + 1) // 2
+            T = side * side
+    return gemm, attn
+
+
+# ------------------------------------------------------------------------------------------ synthetic data
+def make_batch(pairs, seed, device="cpu", pin=False):
+    g = torch.Generator().manual_seed(seed)
+    img1 = torch.rand(pairs, 3, IMG, IMG, generator=g)
+    img2 = torch.rand(pairs, 3, IMG, IMG, generator=g)
+    d = []
+    for _ in range(2):
+        t = 0.5 + (MAX_DEPTH - 0.5) * torch.rand(pairs, IMG, IMG, generator=g)
+        t = torch.where(torch.rand(pairs, IMG, IMG, generator=g) < 0.05, torch.zeros(()), t)
+        d.append(t)
+    out = [img1, img2, d[0], d[1]]
+    if pin:
+        out = [t.pin_memory() for t in out]
+    if device != "cpu":
+        out = [t.to(device) for t in out]
+    return out
+
+
+# ------------------------------------------------------------------------------------------ b200 arm
+class DepthModel(torch.nn.Module):
+    """Swin-V2-B encoder (b200swin drop-in) + pixel-shuffle depth read-out: Linear(1024 -> 32*32) per stride-32
+    token through the b200swin GEMM, sigmoid * max_depth (the reference decoders end the same way,
+    models/decoder_v2.py:119)."""
+
+    def __init__(self):
+        super().__init__()
+        from b200swin.swin_transformer_v2 import SwinTransformerV2
+        self.encoder = SwinTransformerV2(**CFG)
+        self.encoder.init_weights(None)
+        self.readout = torch.nn.Linear(CFG["embed_dim"] * 8, 32 * 32)
+        torch.nn.init.normal_(self.readout.weight, std=0.02)
+        torch.nn.init.zeros_(self.readout.bias)
+
+    def forward(self, frame1, frame2):
+        from b200swin import ops
+        frames = torch.cat([frame1, frame2])                     # models/model.py:116
+        feat = self.encoder(frames)[0]                           # [2P, 1024, 15, 15] fp32 NCHW
+        B, C, h, w = feat.shape
+        tok = feat.permute(0, 2, 3, 1).reshape(B, h * w, C)
+        d = ops.linear(tok, self.readout.weight, self.readout.bias)        # [2P, 225, 1024]
+        d = d.view(B, h, w, 32, 32).permute(0, 1, 3, 2, 4).reshape(B, h * 32, w * 32)
+        d = torch.sigmoid(d.float()) * MAX_DEPTH
+        return d.chunk(2, dim=0)
+
+
+def clocks_sampler(path):
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    try:
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                stdout=open(path, "w"), stderr=subprocess.DEVNULL)
+    except Exception:
+        return None
+
+
+def clocks_summary(path, gpu_index):
+    sm, mx, reasons = [], 0, set()
+    try:
+        for line in open(path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or f[0] != str(gpu_index):
+                continue
+            sm.append(float(f[1]))
+            mx = max(mx, float(f[2]))
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+    except Exception:
+        pass
+    # the first samples may precede the load: median over the upper half
+    sm.sort()
+    load = sm[len(sm) // 2:] if sm else []
+    return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx or None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1404.8), d.get("hbm_gbs", 6449.4), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from b200swin import SiLogLoss, _lib, ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.ATTN_IMPL["mode"] = args.attn
+    torch.manual_seed(0)                                   # identical weights on every rank
+    model = DepthModel().to(dev)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    net.train()
+    crit = SiLogLoss()
+    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=0.05, fused=True)
+    P = args.pairs
+    host = make_batch(P, 1234 + rank, pin=True)
+    resident = [t.to(dev) for t in host]
+    use_amp = args.dtype == "bf16"
+
+    def step(batch):
+        img1, img2, d1, d2 = batch
+        with torch.autocast("cuda", torch.bfloat16, enabled=use_amp):
+            p1, p2 = net(img1, img2)
+        loss = (crit(p1, d1) + crit(p2, d2)) / 2                 # train.py:215-217
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        loss = step(resident)
+    torch.cuda.synchronize(dev)
+    assert torch.isfinite(loss).item(), "non-finite loss in warm-up"
+
+    # ---- device-resident timing, with live per-launch timing of the GEMM for the roofline
+    clk_path = os.path.join(tempfile.gettempdir(), f"b200swin_clocks_{rank}.csv")
+    sampler = clocks_sampler(clk_path) if rank == 0 else None
+    _lib.reset_counters()
+    _lib.TIMING.update(name="b200swin_gemm_bf16", events=[],
+                       work=lambda a: 2.0 * a[6] * a[7] * a[8] * (3 if a[1] else 1))
+    ms = timed(lambda: step(resident), args.steps)
+    _lib.TIMING["name"] = None
+    launches = _lib.COUNTERS["launches"]
+    calls = dict(_lib.COUNTERS["calls"])
+    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in _lib.TIMING["events"])
+    gemm_flops = sum(w for _, _, w in _lib.TIMING["events"])
+    n_gemm = len(_lib.TIMING["events"])
+
+    # ---- end to end through the public API with host buffers
+    def e2e_step():
+        batch = [t.to(dev, non_blocking=True) for t in host]
+        return step(batch).item()
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    if sampler is not None:
+        sampler.terminate()
+    frames = 2 * P * world
+    value = frames * args.steps / (ms / 1e3)
+    e2e = frames * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        tf_peak, hbm_peak, how = peaks()
+        gemm_f, attn_f = encoder_flops_per_frame()
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        line = {
+            "metric": "train images/sec, Swin-V2-B depth @480^2 (hot path: encoder fwd+bwd + SiLog + AdamW)",
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if use_amp else "f32(split-bf16 x3)", "data": "synthetic",
+            "config": {"workload": "swin_v2_base_480x480_ws12_24pairs_per_gpu_train_step(encoder+pixelshuffle_readout"
+                                   "+silog_x2+adamw; decoder_v2 outside hot path, not included)",
+                       "pairs_per_gpu": P, "frames_per_gpu": 2 * P, "windows": CFG["window_size"],
+                       "attn_impl": args.attn, "parallelism": f"dp{world}",
+                       "l2": "inputs+activations >> 126 MB L2 (48x3x480x480 fp32 = 133 MB images alone)"},
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host),
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "launch_calls": calls,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tf_peak, "traffic": None, "kernel": "gemm_tc_kernel (all launches)",
+                         "launches": n_gemm, "kernel_ms_per_step": gemm_ms / args.steps, "peak_source": how},
+            "model_flops": {"encoder_fwd_gflop_per_frame": (gemm_f + attn_f) / 1e9,
+                            "step_tflops_achieved": 3 * (gemm_f + attn_f) * 2 * P / (ms / args.steps / 1e3) / 1e12},
+            "clocks": clocks_summary(clk_path, local),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_reference(args.cpu_sample_pairs, steps=1, warmup=0)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_reference(pairs, steps, warmup):
+    """The CPU oracle (port of the reference's PyTorch path) on a bounded sample: `pairs` frame pairs of the same
+    workload, forward + backward + SiLog, fp32, all host threads."""
+    from oracle import silog_ref, swin_ref
+    from b200swin.swin_transformer_v2 import SwinTransformerV2
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    enc = SwinTransformerV2(**CFG)          # parameter container only (never executed on the CPU)
+    enc.init_weights(None)
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "relative_coords" not in k)
+          for k, v in enc.state_dict().items()}
+    readout_w = (torch.randn(1024, CFG["embed_dim"] * 8) * 0.02).requires_grad_(True)
+    readout_b = torch.zeros(1024, requires_grad=True)
+    img1, img2, d1, d2 = make_batch(pairs, 1234)
+
+    def one():
+        feat = swin_ref.swin_v2(torch.cat([img1, img2]), sd, CFG["embed_dim"], CFG["depths"], CFG["num_heads"],
+                                CFG["window_size"], CFG["use_shift"], (3,))[0]
+        B, C, h, w = feat.shape
+        d = torch.nn.functional.linear(feat.permute(0, 2, 3, 1).reshape(B, h * w, C), readout_w, readout_b)
+        d = torch.sigmoid(d.view(B, h, w, 32, 32).permute(0, 1, 3, 2, 4).reshape(B, h * 32, w * 32)) * MAX_DEPTH
+        p1, p2 = d.chunk(2)
+        loss = (silog_ref.silog_torch(p1, d1) + silog_ref.silog_torch(p2, d2)) / 2
+        loss.backward()
+        return loss.item()
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    return {"value": 2 * pairs * steps / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} step(s) of {pairs} pair(s) ({2 * pairs} frames) 480x480, Swin-V2-B ws12 fwd+bwd+SiLog, "
+                      f"fp32 torch CPU, {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pairs = args.cpu_sample_pairs
+    steps, warmup = max(1, min(args.steps, 2)), min(args.warmup, 1)
+    t0 = time.perf_counter()
+    base = cpu_reference(pairs, steps, warmup)
+    line = {
+        "impl": "reference",
+        "metric": "train images/sec, Swin-V2-B depth @480^2 (hot path: encoder fwd+bwd + SiLog + AdamW)",
+        "value": base["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": (time.perf_counter() - t0) * 1e3 / (steps + warmup), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "swin_v2_base_480x480_ws12 train step, bounded CPU sample", "pairs_per_step": pairs,
+                   "note": "CPU oracle port of the reference PyTorch path on the host cores; requested steps/warmup "
+                           f"({args.steps}/{args.warmup}) clamped to ({steps}/{warmup}) to bound the run"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

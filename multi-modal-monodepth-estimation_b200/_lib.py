@@ -58,13 +58,61 @@ def load() -> ctypes.CDLL:
                 raise RuntimeError(
                     f"b200swin: {LIB_PATH} is missing - build it with `python __graft_entry__.py build` "
                     "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for these ops.")
-            lib = ctypes.CDLL(LIB_PATH)
+            cdll = ctypes.CDLL(LIB_PATH)
+            lib = _Instrumented()
             for name, (res, args) in SIGNATURES.items():
-                fn = getattr(lib, name)
+                fn = getattr(cdll, name)
                 fn.restype = res
                 fn.argtypes = args
+                setattr(lib, name, _wrap(name, fn) if name in KERNELS_PER_CALL else fn)
             _lib = lib
     return _lib
+
+
+class _Instrumented:
+    """Namespace of the bound entry points (launching ones wrapped by the counters below)."""
+
+
+# kernels launched per C-ABI call (for the bench's gpu_launches claim); split-K gemm adds its reduce
+KERNELS_PER_CALL = {
+    "b200swin_silog_fwd": 2, "b200swin_silog_bwd": 1, "b200swin_window_gather": 1, "b200swin_window_scatter": 1,
+    "b200swin_shift_mask": 1, "b200swin_ln_fwd": 1, "b200swin_ln_bwd": 2, "b200swin_attn_fwd": 1,
+    "b200swin_attn_bwd": 2, "b200swin_gemm_bf16": 1, "b200swin_split_bf16": 1, "b200swin_colsum": 2,
+}
+
+COUNTERS = {"launches": 0, "calls": {}}
+# optional live timing of one entry point with CUDA events on the launching stream (bench.py roofline):
+# TIMING = {"name": <symbol>, "events": [(start, end, work)], "work": callable(args) -> float}
+TIMING = {"name": None, "events": [], "work": None}
+
+
+def _wrap(name, fn):
+    per_call = KERNELS_PER_CALL[name]
+
+    def call(*args):
+        n = per_call
+        if name == "b200swin_gemm_bf16" and args[18] > 1:
+            n += 1
+        COUNTERS["launches"] += n
+        COUNTERS["calls"][name] = COUNTERS["calls"].get(name, 0) + 1
+        if TIMING["name"] == name:
+            st = torch.cuda.current_stream()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            rc = fn(*args)
+            e1.record(st)
+            TIMING["events"].append((e0, e1, TIMING["work"](args) if TIMING["work"] else 0.0))
+            return rc
+        return fn(*args)
+
+    return call
+
+
+def reset_counters():
+    COUNTERS["launches"] = 0
+    COUNTERS["calls"] = {}
+    TIMING["events"] = []
 
 
 def check(rc: int, what: str) -> None:

@@ -182,8 +182,8 @@ def layer_norm_residual(x, gamma, beta, eps, residual=None, row_scale=None, rows
 def compute_dtype(x: torch.Tensor) -> torch.dtype:
     """bf16 under torch.autocast('cuda', torch.bfloat16) (our definition of the reference's missing
     bf16 mode) or for bf16 inputs; otherwise fp32 (reference precision)."""
-    if torch.is_autocast_enabled():
-        dt = torch.get_autocast_gpu_dtype()
+    if torch.is_autocast_enabled('cuda'):
+        dt = torch.get_autocast_dtype('cuda')
         if dt != torch.bfloat16:
             raise TypeError("b200swin supports bfloat16 autocast only")
         return dt

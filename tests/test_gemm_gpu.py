@@ -29,7 +29,7 @@ def test_nt_bf16(M, N, K):
     b = torch.randn(N, K, generator=g).bfloat16().cuda()
     ref = a.double() @ b.double().t()
     out32 = ops.gemm(ops.Operand(a), ops.Operand(b), M, N, K, out_dtype=torch.float32)
-    assert _relerr(out32, ref) < 2e-6
+    assert _relerr(out32, ref) < 5e-6          # fp32 accumulation over K
     out16 = ops.gemm(ops.Operand(a), ops.Operand(b), M, N, K, out_dtype=torch.bfloat16)
     assert _relerr(out16, ref) < 4e-3
 
