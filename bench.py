@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--attn", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--cpu-sample-pairs", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print per-entry-point CUDA-event times to stderr")
     return ap.parse_args()
 
 
@@ -228,9 +229,23 @@ def run_b200(args):
     _lib.TIMING["name"] = None
     launches = _lib.COUNTERS["launches"]
     calls = dict(_lib.COUNTERS["calls"])
-    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in _lib.TIMING["events"])
-    gemm_flops = sum(w for _, _, w in _lib.TIMING["events"])
+    gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _, _ in _lib.TIMING["events"])
+    gemm_flops = sum(w for _, _, w, _ in _lib.TIMING["events"])
     n_gemm = len(_lib.TIMING["events"])
+
+    if args.breakdown:
+        # diagnostic: CUDA-event time of every C-ABI entry point over one more step (not part of the JSON contract)
+        _lib.reset_counters()
+        _lib.TIMING.update(name="*", events=[])
+        ms1 = timed(lambda: step(resident), 1)
+        _lib.TIMING["name"] = None
+        agg = {}
+        for e0, e1, _, nm in _lib.TIMING["events"]:
+            agg[nm] = agg.get(nm, 0.0) + e0.elapsed_time(e1)
+        if rank == 0:
+            tot = sum(agg.values())
+            print("breakdown (ms/step):", json.dumps({k: round(v, 2) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}),
+                  f"sum={tot:.1f} step={ms1:.1f} other(torch ops, gaps)={ms1 - tot:.1f}", file=sys.stderr)
 
     # ---- end to end through the public API with host buffers
     def e2e_step():

@@ -95,14 +95,15 @@ def _wrap(name, fn):
             n += 1
         COUNTERS["launches"] += n
         COUNTERS["calls"][name] = COUNTERS["calls"].get(name, 0) + 1
-        if TIMING["name"] == name:
+        if TIMING["name"] == name or TIMING["name"] == "*":
             st = torch.cuda.current_stream()
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(st)
             rc = fn(*args)
             e1.record(st)
-            TIMING["events"].append((e0, e1, TIMING["work"](args) if TIMING["work"] else 0.0))
+            TIMING["events"].append((e0, e1, TIMING["work"](args) if (TIMING["work"] and name == "b200swin_gemm_bf16")
+                                     else 0.0, name))
             return rc
         return fn(*args)
 

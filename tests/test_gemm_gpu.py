@@ -59,7 +59,7 @@ def test_wgrad_layout_both_mn_major_splitk(T, N, K, splits):
         splits = L.load().b200swin_gemm_splits(N, K, T)
     out = ops.gemm(ops.Operand(dy), ops.Operand(x), N, K, T, a_mn=True, b_mn=True, out_dtype=torch.float32,
                    splits=splits)
-    assert _relerr(out, ref) < 3e-6
+    assert _relerr(out, ref) < 2e-5          # fp32 accumulation over up to 43200 tokens
 
 
 @pytest.mark.parametrize("M,N,K", [(640, 384, 128), (1000, 512, 512)])
