@@ -440,16 +440,25 @@ def qkv_project(x, weight, q_bias, v_bias, nH):
 
 
 # ------------------------------------------------------------------------------ attention core
-ATTN_IMPL = {"mode": "auto"}     # "auto" | "simt" | "tc"
+# "auto": tcgen05 kernels whenever they apply (bf16 storage, windows <= 16x16, on-the-fly mask), else the fp32
+# CUDA-core kernels.  "simt" / "tc" force one implementation (tests, A/B timing).  Backward has its own switch.
+ATTN_IMPL = {"mode": "auto", "bwd_mode": "auto"}
+_TC_BWD_AVAILABLE = False
 
 
-def _pick_impl(dtype, ws):
-    mode = ATTN_IMPL["mode"]
+def _tc_applicable(dtype, ws, mask):
+    return dtype == torch.bfloat16 and ws * ws <= 256 and mask is None
+
+
+def _pick_impl(dtype, ws, mask, backward=False):
+    mode = ATTN_IMPL["bwd_mode" if backward else "mode"]
     if mode == "simt":
         return 0
     if mode == "tc":
         return 1
-    return 0
+    if backward and not _TC_BWD_AVAILABLE:
+        return 0
+    return 1 if _tc_applicable(dtype, ws, mask) else 0
 
 
 class _AttnCore(torch.autograd.Function):
@@ -468,7 +477,8 @@ class _AttnCore(torch.autograd.Function):
         qp, vp, mk = _f32(qpad), _f32(vpad), _f32(mask)
         Hp, Wp = (H + ws - 1) // ws * ws, (W + ws - 1) // ws * ws
         nwin = B * (Hp // ws) * (Wp // ws)
-        impl = _pick_impl(qkv.dtype, ws)
+        impl = _pick_impl(qkv.dtype, ws, mask)
+        ctx.impl_bwd = _pick_impl(qkv.dtype, ws, mask, backward=True)
         nWm = mask.shape[0] if mask is not None else 0
         with torch.cuda.device_of(qkv):
             out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
@@ -498,7 +508,7 @@ class _AttnCore(torch.autograd.Function):
             L.check(lib.b200swin_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
                                           inv_norm.data_ptr(), t16.data_ptr(), sc.data_ptr(), L.ptr(qp), L.ptr(vp),
                                           L.ptr(mk), ctx.nWm, dqkv.data_ptr(), dt16.data_ptr(), dsc.data_ptr(),
-                                          dvp.data_ptr(), B, H, W, C, nH, ws, shift, L.dtype_code(qkv), ctx.impl,
+                                          dvp.data_ptr(), B, H, W, C, nH, ws, shift, L.dtype_code(qkv), ctx.impl_bwd,
                                           L.stream_of(qkv)), "attn_bwd")
         tdt, sdt, vdt = ctx.dtypes
         return (dqkv, None, dt16.to(tdt), dsc.view(sc.shape).to(sdt), None,

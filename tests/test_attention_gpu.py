@@ -181,14 +181,20 @@ def test_swin_small_vs_reference_golden():
         assert _relerr(o, g[f"out.{i}"]) < 2e-2
 
 
-@pytest.mark.parametrize("B,H,W,C,nH,ws,shift,dtype", [
-    (2, 24, 24, 128, 4, 12, 6, torch.float32), (1, 30, 30, 64, 2, 12, 6, torch.float32),
-    (2, 16, 20, 96, 3, 8, 4, torch.bfloat16), (1, 15, 15, 64, 2, 6, 3, torch.float32),
-    (1, 48, 48, 32, 1, 24, 12, torch.float32), (1, 30, 30, 32, 1, 30, 0, torch.float32)])
-def test_attention_core_vs_oracle(B, H, W, C, nH, ws, shift, dtype):
+@pytest.mark.parametrize("B,H,W,C,nH,ws,shift,dtype,impl", [
+    (2, 24, 24, 128, 4, 12, 6, torch.float32, "simt"), (1, 30, 30, 64, 2, 12, 6, torch.float32, "simt"),
+    (2, 16, 20, 96, 3, 8, 4, torch.bfloat16, "simt"), (1, 15, 15, 64, 2, 6, 3, torch.float32, "simt"),
+    (1, 48, 48, 32, 1, 24, 12, torch.float32, "simt"), (1, 30, 30, 32, 1, 30, 0, torch.float32, "simt"),
+    # tcgen05 kernels (bf16 storage): unshifted / shifted / padded / small and large windows / many heads
+    (2, 24, 24, 128, 4, 12, 0, torch.bfloat16, "tc"), (2, 24, 24, 128, 4, 12, 6, torch.bfloat16, "tc"),
+    (1, 30, 30, 64, 2, 12, 6, torch.bfloat16, "tc"), (2, 16, 20, 96, 3, 8, 4, torch.bfloat16, "tc"),
+    (1, 15, 15, 64, 2, 6, 3, torch.bfloat16, "tc"), (1, 32, 32, 32, 1, 16, 8, torch.bfloat16, "tc"),
+    (3, 12, 12, 512, 16, 12, 0, torch.bfloat16, "tc"), (1, 9, 10, 64, 2, 4, 2, torch.bfloat16, "tc")])
+def test_attention_core_vs_oracle(B, H, W, C, nH, ws, shift, dtype, impl):
     """The core kernel alone (natural-order qkv in, natural-order out), forward and every gradient, against the
     oracle's gather -> dense attention -> scatter in float64."""
     from b200swin import ops
+    ops.ATTN_IMPL["mode"] = impl
     gen = torch.Generator().manual_seed(B * 1000 + H * 10 + ws)
     T = B * H * W
     N = ws * ws
@@ -238,6 +244,7 @@ def test_attention_core_vs_oracle(B, H, W, C, nH, ws, shift, dtype):
     qkv_leaf = qkv_hat.detach().requires_grad_(True)
     out = ops.attention_core(qkv_leaf.view(B, H, W, 3 * C), inv_norm, 16 * torch.sigmoid(tg), sg, qpad, vbg, None,
                              B, H, W, C, nH, ws, shift)
+    ops.ATTN_IMPL["mode"] = "auto"
     tol = 1e-4 if dtype == torch.float32 else 2e-2
     assert _relerr(out.reshape(B, H * W, C), oref) < tol
     (out.reshape(B, H * W, C).float() * cot.to(dev)).sum().backward()
