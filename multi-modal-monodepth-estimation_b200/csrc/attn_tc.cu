@@ -351,10 +351,485 @@ int attn_fwd_tc(const void* qkv, void* out, float* lse, const float* table16, co
   return B200SWIN_EINVAL;
 }
 
-int attn_bwd_tc(const void*, const void*, const void*, const float*, const float*, const float*, const float*,
-                const float*, const float*, const float*, int, void*, float*, float*, float*, int, int, int, int, int,
-                int, int, cudaStream_t) {
-  set_error("attn_bwd: tensor-core backward not available in this build");
+// ================================================================================================ backward
+// Per (window, head), with S and dP recomputed on the tensor cores (never in HBM):
+//   S  = Q K^T,  dP = dO V^T                 (tcgen05, fp32 in TMEM)
+//   P  = exp2(S' - lse),  dS = P * (dP - D)  (one thread per row and column half; D = <dO, O>)
+//   P, dS -> bf16 panels [128 query rows][64 keys] in smem (128 B swizzle).  The SAME bytes are a K-major
+//   A operand (dQ = dS K) and an MN-major A operand (dV = P^T dO, dK = dS^T Q): no transpose is ever made.
+//   dQ, dK (through the F.normalize backward) and dV go to the natural-layout dqkv tensor.
+// The gradient of the 16*sigmoid bias table is a sum of dS over ALL windows: each CTA works on ONE head
+// (persistent, head-major) and keeps its dS sums in REGISTERS across windows, flushing once at the end
+// (tail rows of >128-token windows use shared-memory atomics).
+}  // namespace b200swin
+namespace b200swin {
+namespace {
+constexpr int kBwdThreads = 256;
+
+struct TcBwdArgs {
+  const __nv_bfloat16* qkv;
+  const __nv_bfloat16* out;
+  const __nv_bfloat16* dout;
+  const float* lse;
+  const float* inv_norm;
+  const float* table16;
+  const float* scale;
+  const float* qpad;
+  const float* vpad;
+  __nv_bfloat16* dqkv;
+  float* dtable16;
+  float* dscale;
+  float* dvpad;
+  WinGeom g;
+  int C, nH;
+  int64_t nwin;
+};
+
+template <int NPAD>
+struct BwdLayout {
+  static constexpr int MT = (NPAD + 127) / 128;
+  static constexpr int NP = (NPAD + 63) / 64;                        // 64-key panels of P / dS
+  static constexpr uint32_t kRow = NPAD * 64;                        // one [NPAD][64 B] operand tile
+  static constexpr uint32_t kBufBytes = 5 * kRow;                    // Q | dO | K | V | O
+  static constexpr uint32_t kPanel = 128 * 128;                      // [128 rows][128 B]
+  static constexpr uint32_t kPBytes = NP * kPanel;
+  static constexpr uint32_t kTmemCols = 512;
+  static constexpr uint32_t S_COL = 0, DP_COL = NPAD, DQ_COL = 2 * NPAD, DV_COL = DQ_COL + 32, DK_COL = DQ_COL + 64,
+                            DVT_COL = DQ_COL + 96, DKT_COL = DQ_COL + 128;
+  static_assert(2 * NPAD + 160 <= 512, "TMEM budget: S + dP + dQ + dV + dK (+ tails)");
+  static constexpr int NH = NPAD / 2;                                // columns per thread (two warps share a lane quarter)
+  static_assert(NH % 8 == 0, "column halves are processed in chunks of 8");
+};
+
+template <int NPAD>
+__device__ __forceinline__ void load_item_bwd(const TcBwdArgs& a, int64_t win, int h, unsigned char* buf, int* tok,
+                                              int N) {
+  using LY = BwdLayout<NPAD>;
+  const uint32_t q_s = ptx::smem_u32(buf), g_s = q_s + LY::kRow, k_s = g_s + LY::kRow, v_s = k_s + LY::kRow,
+                 o_s = v_s + LY::kRow;
+  const int C3 = 3 * a.C;
+  for (int r = threadIdx.x; r < NPAD; r += kBwdThreads) {
+    int t = -2;
+    if (r < N) {
+      int b, i, j, si, sj;
+      bool real = win_token(a.g, win, r, b, i, j, si, sj);
+      t = real ? ((b * a.g.H + i) * a.g.W + j) : -1;
+    }
+    tok[r] = t;
+    if (t >= 0) {
+      const __nv_bfloat16* src = a.qkv + (int64_t)t * C3 + h * HD;
+      const __nv_bfloat16* gsrc = a.dout + (int64_t)t * a.C + h * HD;
+      const __nv_bfloat16* osrc = a.out + (int64_t)t * a.C + h * HD;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t off = sw64_off(r, c);
+        ptx::cp_async_16(q_s + off, src + c * 8);
+        ptx::cp_async_16(k_s + off, src + a.C + c * 8);
+        ptx::cp_async_16(v_s + off, src + 2 * a.C + c * 8);
+        ptx::cp_async_16(g_s + off, gsrc + c * 8);
+        ptx::cp_async_16(o_s + off, osrc + c * 8);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 qv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (t == -1) {
+          if (a.qpad) {
+            const float* p = a.qpad + h * HD + c * 8;
+            qv = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+          }
+          if (a.vpad) {
+            const float* p = a.vpad + h * HD + c * 8;
+            vv = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+          }
+        }
+        const uint32_t off = sw64_off(r, c);
+        *reinterpret_cast<uint4*>(buf + off) = qv;
+        *reinterpret_cast<uint4*>(buf + LY::kRow + off) = make_uint4(0, 0, 0, 0);          // dO of a cropped row
+        *reinterpret_cast<uint4*>(buf + 2 * LY::kRow + off) = make_uint4(0, 0, 0, 0);      // k of a pad token
+        *reinterpret_cast<uint4*>(buf + 3 * LY::kRow + off) = vv;
+        *reinterpret_cast<uint4*>(buf + 4 * LY::kRow + off) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+}
+
+// 32 bf16 of row r of a [rows][64 B] swizzled tile -> fp32
+__device__ __forceinline__ void read_row_sw64(const unsigned char* tile, int r, float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 w = *reinterpret_cast<const uint4*>(tile + sw64_off(r, c));
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&ww[e]);
+      float2 f = __bfloat1622float2(t);
+      v[c * 8 + 2 * e] = f.x;
+      v[c * 8 + 2 * e + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, const float (&v)[32]) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    d[c] = make_uint4(pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]),
+                      pack_bf16(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ TcBwdArgs a) {
+  using LY = BwdLayout<NPAD>;
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t bar_a, bar_b;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float dvpad_s[HD];
+  __shared__ float red_s[kBwdThreads / 32];
+
+  const WinGeom& g = a.g;
+  const int ws = g.ws, N = ws * ws, tw = 2 * ws - 1, ntab = tw * tw;
+  const uint32_t base_u32 = (ptx::smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* sm = smem_dyn + (base_u32 - ptx::smem_u32(smem_dyn));
+  unsigned char* bufs[2] = {sm, sm + LY::kBufBytes};
+  unsigned char* Pp = sm + 2 * LY::kBufBytes;
+  unsigned char* dSp = Pp + LY::kPBytes;
+  float* tab = reinterpret_cast<float*>(dSp + LY::kPBytes);
+  float* dtab = tab + ntab;
+  float* D_s = dtab + ntab;                    // [NPAD] <dO_r, O_r>
+  float* lse_s = D_s + NPAD;                   // [NPAD] lse in log2 units
+  int* toks[2] = {reinterpret_cast<int*>(lse_s + NPAD), reinterpret_cast<int*>(lse_s + NPAD) + NPAD};
+  int* meta = toks[1] + NPAD;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, half = warp >> 2;
+  const int row_local = q * 32 + lane;
+  const int h = blockIdx.x % a.nH;
+  const int64_t wstep = gridDim.x / a.nH;
+
+  for (int i = threadIdx.x; i < (int)(2 * LY::kBufBytes + 2 * LY::kPBytes) / 16; i += kBwdThreads)
+    reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  for (int r = threadIdx.x; r < ntab; r += kBwdThreads) { tab[r] = a.table16[r * a.nH + h] * kLog2e; dtab[r] = 0.f; }
+  if (threadIdx.x < HD) dvpad_s[threadIdx.x] = 0.f;
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(&bar_a, 1);
+    ptx::mbar_init(&bar_b, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(&tmem_slot, LY::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+
+  constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, NPAD, 0, 0);
+  constexpr uint32_t idesc_dq = ptx::make_idesc_bf16(128, HD, 0, 1);     // A = dS (K-major), B = K MN-major
+  constexpr uint32_t idesc_t = ptx::make_idesc_bf16(128, HD, 1, 1);      // A = P^T / dS^T (MN-major), B MN-major
+  constexpr uint32_t idesc_t64 = ptx::make_idesc_bf16(64, HD, 1, 1);     // tail keys 128.. (M = 64)
+
+  const float sc = a.scale[h], scale2 = sc * kLog2e;
+  float acc[LY::NH];                       // register-resident sum over windows of dS[row_local, my columns]
+#pragma unroll
+  for (int c = 0; c < LY::NH; ++c) acc[c] = 0.f;
+  float dsc = 0.f;
+  uint32_t ph_a = 0, ph_b = 0;
+
+  int64_t win = blockIdx.x / a.nH;
+  int it = 0;
+  if (win < a.nwin) load_item_bwd<NPAD>(a, win, h, bufs[0], toks[0], N);
+  ptx::cp_async_commit();
+
+  for (; win < a.nwin; win += wstep, ++it) {
+    const int b = it & 1;
+    if (win + wstep < a.nwin) load_item_bwd<NPAD>(a, win + wstep, h, bufs[b ^ 1], toks[b ^ 1], N);
+    ptx::cp_async_commit();
+    for (int r = threadIdx.x; r < NPAD; r += kBwdThreads) {
+      int region = 0;
+      if (g.shift > 0 && r < N) {
+        int bb, i, j, si, sj;
+        win_token(g, win, r, bb, i, j, si, sj);
+        region = 3 * region_1d(si, g.Hp, ws, g.shift) + region_1d(sj, g.Wp, ws, g.shift);
+      }
+      meta[r] = (r < N ? ((r / ws) * tw + (r % ws)) : 0) | (region << 16);
+    }
+    ptx::cp_async_wait<1>();
+    __syncthreads();                                   // everybody's gather of this item is visible
+    unsigned char* buf = bufs[b];
+    const int* tok = toks[b];
+    // D_r = <dO_r, O_r>, lse in log2 units (pad / padding rows: dO = 0 -> D = 0; lse = +inf -> P = 0)
+    for (int r = threadIdx.x; r < NPAD; r += kBwdThreads) {
+      float gv[32], ov[32];
+      read_row_sw64(buf + LY::kRow, r, gv);
+      read_row_sw64(buf + 4 * LY::kRow, r, ov);
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) d = fmaf(gv[c], ov[c], d);
+      D_s[r] = d;
+      lse_s[r] = (r < N) ? a.lse[(win * a.nH + h) * N + r] * kLog2e : INFINITY;
+    }
+    ptx::fence_proxy_async_smem();
+    __syncthreads();
+
+    const uint32_t q_s = ptx::smem_u32(buf), g_s = q_s + LY::kRow, k_s = g_s + LY::kRow, v_s = k_s + LY::kRow;
+    const uint32_t p_s = ptx::smem_u32(Pp), ds_s = ptx::smem_u32(dSp);
+
+#pragma unroll 1
+    for (int tile = 0; tile < LY::MT; ++tile) {
+      const int rows_valid = min(128, N - tile * 128);
+      if (rows_valid <= 0) break;
+      // ---- S = Q_t K^T, dP = dO_t V^T
+      if (threadIdx.x == 0) {
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t bk = ptx::make_smem_desc(k_s + ks * 32, 16, 512, kSw64);
+          const uint64_t bv = ptx::make_smem_desc(v_s + ks * 32, 16, 512, kSw64);
+          ptx::mma_bf16_ss(tmem_base + LY::S_COL, ptx::make_smem_desc(q_s + tile * 8192 + ks * 32, 16, 512, kSw64), bk,
+                           idesc_s, ks);
+          ptx::mma_bf16_ss(tmem_base + LY::DP_COL, ptx::make_smem_desc(g_s + tile * 8192 + ks * 32, 16, 512, kSw64), bv,
+                           idesc_s, ks);
+        }
+        ptx::mma_commit(&bar_a);
+      }
+      ptx::mbar_wait(&bar_a, ph_a);
+      ph_a ^= 1;
+      ptx::tc_fence_after();
+
+      // ---- P, dS for (row, my half of the columns)
+      {
+        const int r = tile * 128 + row_local;
+        const bool rvalid = r < N;
+        const int rr = rvalid ? r : 0;
+        const int base_i = (meta[rr] & 0xffff) + (ws - 1) * (tw + 1);
+        const int reg_i = meta[rr] >> 16;
+        const float lse2 = rvalid ? lse_s[rr] : INFINITY;
+        const float Dr = D_s[rr];
+#pragma unroll
+        for (int cc = 0; cc < LY::NH / 8; ++cc) {
+          const int j0 = half * LY::NH + cc * 8;
+          uint32_t sv[8], dv[8];
+          ptx::tmem_ld_32x32b_x8(t_row + LY::S_COL + j0, sv);
+          ptx::tmem_ld_32x32b_x8(t_row + LY::DP_COL + j0, dv);
+          ptx::tmem_ld_wait();
+          float p[8], ds[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u;
+            const int mj = meta[j];
+            const int rel = base_i - (mj & 0xffff);
+            const float cosv = __uint_as_float(sv[u]);
+            float s2 = fmaf(cosv, scale2, tab[rel]);
+            if ((mj >> 16) != reg_i) s2 += kMaskLog2;
+            float pv = exp2f(s2 - lse2);
+            float dsv = pv * (__uint_as_float(dv[u]) - Dr);
+            if (!rvalid || (NPAD != N && j >= N)) { pv = 0.f; dsv = 0.f; }
+            p[u] = pv;
+            ds[u] = dsv;
+            dsc = fmaf(dsv, cosv, dsc);
+            if (tile == 0) acc[cc * 8 + u] += dsv;
+            else if (dsv != 0.f) atomicAdd(dtab + rel, dsv);
+          }
+          const uint32_t off = (uint32_t)((j0 >> 6) * LY::kPanel + row_local * 128 + ((((j0 & 63) >> 3) ^ (row_local & 7)) << 4));
+          *reinterpret_cast<uint4*>(Pp + off) =
+              make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+          *reinterpret_cast<uint4*>(dSp + off) =
+              make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      __syncthreads();
+
+      // ---- dQ_t = dS K ;  dV += P^T dO_t ;  dK += dS^T Q_t
+      if (threadIdx.x == 0) {
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int ks = 0; ks < NPAD / 16; ++ks) {
+          const uint64_t ad = ptx::make_smem_desc(ds_s + (ks >> 2) * LY::kPanel + (ks & 3) * 32, 16, 1024, 2);
+          const uint64_t bd = ptx::make_smem_desc(k_s + ks * 1024, 512, 512, kSw64);
+          ptx::mma_bf16_ss(tmem_base + LY::DQ_COL, ad, bd, idesc_dq, ks);
+        }
+        const int ksteps = (rows_valid + 15) / 16;
+#pragma unroll 1
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t accf = (tile | ks) != 0 ? 1u : 0u;
+          const uint64_t bg = ptx::make_smem_desc(g_s + (tile * 128 + ks * 16) * 64, 512, 512, kSw64);
+          const uint64_t bq = ptx::make_smem_desc(q_s + (tile * 128 + ks * 16) * 64, 512, 512, kSw64);
+          ptx::mma_bf16_ss(tmem_base + LY::DV_COL, ptx::make_smem_desc(p_s + ks * 2048, LY::kPanel, 1024, 2), bg, idesc_t, accf);
+          ptx::mma_bf16_ss(tmem_base + LY::DK_COL, ptx::make_smem_desc(ds_s + ks * 2048, LY::kPanel, 1024, 2), bq, idesc_t, accf);
+          if (NPAD > 128) {
+            ptx::mma_bf16_ss(tmem_base + LY::DVT_COL, ptx::make_smem_desc(p_s + 2 * LY::kPanel + ks * 2048, LY::kPanel, 1024, 2),
+                             bg, idesc_t64, accf);
+            ptx::mma_bf16_ss(tmem_base + LY::DKT_COL, ptx::make_smem_desc(ds_s + 2 * LY::kPanel + ks * 2048, LY::kPanel, 1024, 2),
+                             bq, idesc_t64, accf);
+          }
+        }
+        ptx::mma_commit(&bar_b);
+      }
+      ptx::mbar_wait(&bar_b, ph_b);
+      ph_b ^= 1;
+      ptx::tc_fence_after();
+      if (half == 0) {
+        // dq = (scale * dS K  -  q_hat <.,q_hat>) / max(|q|, eps)
+        const int r = tile * 128 + row_local;
+        uint32_t o[32];
+        ptx::tmem_ld_32x32b_x32(t_row + LY::DQ_COL, o);
+        ptx::tmem_ld_wait();
+        if (r < N && tok[r] >= 0) {
+          const int t = tok[r];
+          float qh[32], dq[32];
+          read_row_sw64(buf, r, qh);
+          float dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { dq[c] = __uint_as_float(o[c]) * sc; dot = fmaf(dq[c], qh[c], dot); }
+          const float invn = a.inv_norm[((int64_t)t * 2 + 0) * a.nH + h];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) dq[c] = (dq[c] - qh[c] * dot) * invn;
+          store_row_bf16(a.dqkv + (int64_t)t * 3 * a.C + h * HD, dq);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncthreads();          // S/dP/dQ columns and the P/dS panels are free for the next tile
+    }
+
+    // ---- dK, dV rows: keys 0..127 from the M=128 accumulators (warps 0-3), keys 128.. from the M=64 ones (warp 4)
+    {
+      const bool main_rows = half == 0;
+      const bool tail_rows = NPAD > 128 && warp == 4;
+      if (main_rows || tail_rows) {
+        const int j = main_rows ? row_local : 128 + lane;
+        uint32_t ov[32], ok[32];
+        ptx::tmem_ld_32x32b_x32(t_row + (main_rows ? LY::DV_COL : LY::DVT_COL), ov);
+        ptx::tmem_ld_32x32b_x32(t_row + (main_rows ? LY::DK_COL : LY::DKT_COL), ok);
+        ptx::tmem_ld_wait();
+        const bool jvalid = j < N && (main_rows || lane < 16);
+        const int t = jvalid ? tok[j] : -2;
+        if (t >= 0) {
+          float kh[32], dk[32], dvv[32];
+          read_row_sw64(buf + 2 * LY::kRow, j, kh);
+          float dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            dk[c] = __uint_as_float(ok[c]) * sc;
+            dot = fmaf(dk[c], kh[c], dot);
+            dvv[c] = __uint_as_float(ov[c]);
+          }
+          const float invn = a.inv_norm[((int64_t)t * 2 + 1) * a.nH + h];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) dk[c] = (dk[c] - kh[c] * dot) * invn;
+          __nv_bfloat16* dst = a.dqkv + (int64_t)t * 3 * a.C + h * HD;
+          store_row_bf16(dst + a.C, dk);
+          store_row_bf16(dst + 2 * a.C, dvv);
+        }
+        // pad tokens carry v = v_bias: their dV rows belong to v_bias (reduced over the warp, then smem)
+        const bool is_pad = t == -1;
+        if (__any_sync(0xffffffffu, is_pad)) {
+#pragma unroll 1
+          for (int c = 0; c < 32; ++c) {
+            float v = is_pad ? __uint_as_float(ov[c]) : 0.f;
+            v = warp_sum(v);
+            if (lane == 0) atomicAdd(&dvpad_s[c], v);
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+  }
+  ptx::cp_async_wait<0>();
+
+  // ---- flush the per-CTA accumulators: register dS sums -> smem table -> global (one atomic per entry)
+  {
+    const int r = row_local;
+    if (r < N) {
+      const int base_i = ((r / ws) * tw + (r % ws)) + (ws - 1) * (tw + 1);
+#pragma unroll
+      for (int c = 0; c < LY::NH; ++c) {
+        const int j = half * LY::NH + c;
+        if (j < N) atomicAdd(dtab + base_i - ((j / ws) * tw + (j % ws)), acc[c]);
+      }
+    }
+  }
+  dsc = warp_sum(dsc);
+  if (lane == 0) red_s[warp] = dsc;
+  __syncthreads();
+  for (int r = threadIdx.x; r < ntab; r += kBwdThreads) {
+    const float v = dtab[r];
+    if (v != 0.f) atomicAdd(a.dtable16 + r * a.nH + h, v);
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < kBwdThreads / 32; ++w) s += red_s[w];
+    atomicAdd(a.dscale + h, s);
+  }
+  if (threadIdx.x < HD && a.dvpad) {
+    const float v = dvpad_s[threadIdx.x];
+    if (v != 0.f) atomicAdd(a.dvpad + h * HD + threadIdx.x, v);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, LY::kTmemCols);
+  }
+}
+
+template <int NPAD>
+static int launch_bwd(const TcBwdArgs& a, cudaStream_t st) {
+  using LY = BwdLayout<NPAD>;
+  const int ws = a.g.ws, ntab = (2 * ws - 1) * (2 * ws - 1);
+  size_t smem = 1024 + 2 * (size_t)LY::kBufBytes + 2 * (size_t)LY::kPBytes + 2 * (size_t)ntab * 4 + 5 * (size_t)NPAD * 4;
+  BSW_REQUIRE(smem <= 227 * 1024, "attn_bwd(tc): shared memory budget exceeded (%zu B)", smem);
+  BSW_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t groups = sm_count() / a.nH;                 // one CTA per SM, every CTA pinned to one head
+  if (groups < 1) groups = 1;
+  if (groups > a.nwin) groups = a.nwin;
+  attn_bwd_tc_kernel<NPAD><<<(unsigned)(groups * a.nH), kBwdThreads, smem, st>>>(a);
+  BSW_LAUNCH_CHECK();
+  return B200SWIN_OK;
+}
+}  // namespace
+
+bool attn_tc_bwd_supported(int ws, int C, int nH, const void* mask) {
+  const int npad = (ws * ws + 15) / 16 * 16;
+  return mask == nullptr && C == nH * HD && npad <= 176 && ws >= 2;
+}
+
+int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
+                const float* table16, const float* scale, const float* qpad, const float* vpad, const float* mask,
+                int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, int B, int H, int W, int C, int nH,
+                int ws, int shift, cudaStream_t st) {
+  (void)nWm;
+  BSW_REQUIRE(attn_tc_bwd_supported(ws, C, nH, mask),
+              "attn_bwd(tc): needs head_dim 32, window <= 13x13 and the on-the-fly mask");
+  BSW_REQUIRE(shift >= 0 && shift < ws, "attn_bwd(tc): bad shift");
+  BSW_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout) |
+                reinterpret_cast<uintptr_t>(dqkv)) & 15) == 0 && C % 8 == 0,
+              "attn_bwd(tc): tensors must be 16-byte aligned");
+  BSW_REQUIRE((int64_t)B * H * W < (1ll << 29), "attn_bwd(tc): too many tokens");
+  TcBwdArgs a;
+  a.qkv = (const __nv_bfloat16*)qkv; a.out = (const __nv_bfloat16*)out; a.dout = (const __nv_bfloat16*)dout;
+  a.lse = lse; a.inv_norm = inv_norm; a.table16 = table16; a.scale = scale; a.qpad = qpad; a.vpad = vpad;
+  a.dqkv = (__nv_bfloat16*)dqkv; a.dtable16 = dtable16; a.dscale = dscale; a.dvpad = dvpad;
+  make_geom(&a.g, B, H, W, ws, shift);
+  a.C = C; a.nH = nH;
+  a.nwin = (int64_t)B * a.g.nWh * a.g.nWw;
+  const int npad = (ws * ws + 15) / 16 * 16;
+  switch (npad) {
+    case 16: return launch_bwd<16>(a, st);
+    case 32: return launch_bwd<32>(a, st);
+    case 48: return launch_bwd<48>(a, st);
+    case 64: return launch_bwd<64>(a, st);
+    case 112: return launch_bwd<112>(a, st);
+    case 128: return launch_bwd<128>(a, st);
+    case 144: return launch_bwd<144>(a, st);
+    case 176: return launch_bwd<176>(a, st);
+    default: break;
+  }
+  set_error("attn_bwd(tc): window %dx%d not instantiated", ws, ws);
   return B200SWIN_EINVAL;
 }
 

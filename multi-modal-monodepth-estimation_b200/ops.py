@@ -443,11 +443,12 @@ def qkv_project(x, weight, q_bias, v_bias, nH):
 # "auto": tcgen05 kernels whenever they apply (bf16 storage, windows <= 16x16, on-the-fly mask), else the fp32
 # CUDA-core kernels.  "simt" / "tc" force one implementation (tests, A/B timing).  Backward has its own switch.
 ATTN_IMPL = {"mode": "auto", "bwd_mode": "auto"}
-_TC_BWD_AVAILABLE = False
 
 
-def _tc_applicable(dtype, ws, mask):
-    return dtype == torch.bfloat16 and ws * ws <= 256 and mask is None
+def _tc_applicable(dtype, ws, mask, backward=False):
+    npad = (ws * ws + 15) // 16 * 16
+    # TMEM budget: forward holds S + O (N <= 256); backward holds S + dP + dQ/dK/dV (N <= 176, i.e. ws <= 13)
+    return dtype == torch.bfloat16 and mask is None and npad <= (176 if backward else 256)
 
 
 def _pick_impl(dtype, ws, mask, backward=False):
@@ -456,9 +457,7 @@ def _pick_impl(dtype, ws, mask, backward=False):
         return 0
     if mode == "tc":
         return 1
-    if backward and not _TC_BWD_AVAILABLE:
-        return 0
-    return 1 if _tc_applicable(dtype, ws, mask) else 0
+    return 1 if _tc_applicable(dtype, ws, mask, backward) else 0
 
 
 class _AttnCore(torch.autograd.Function):

@@ -195,6 +195,7 @@ def test_attention_core_vs_oracle(B, H, W, C, nH, ws, shift, dtype, impl):
     oracle's gather -> dense attention -> scatter in float64."""
     from b200swin import ops
     ops.ATTN_IMPL["mode"] = impl
+    ops.ATTN_IMPL["bwd_mode"] = "simt" if impl == "simt" else "auto"
     gen = torch.Generator().manual_seed(B * 1000 + H * 10 + ws)
     T = B * H * W
     N = ws * ws
@@ -244,10 +245,10 @@ def test_attention_core_vs_oracle(B, H, W, C, nH, ws, shift, dtype, impl):
     qkv_leaf = qkv_hat.detach().requires_grad_(True)
     out = ops.attention_core(qkv_leaf.view(B, H, W, 3 * C), inv_norm, 16 * torch.sigmoid(tg), sg, qpad, vbg, None,
                              B, H, W, C, nH, ws, shift)
-    ops.ATTN_IMPL["mode"] = "auto"
     tol = 1e-4 if dtype == torch.float32 else 2e-2
     assert _relerr(out.reshape(B, H * W, C), oref) < tol
     (out.reshape(B, H * W, C).float() * cot.to(dev)).sum().backward()
+    ops.ATTN_IMPL["mode"] = ops.ATTN_IMPL["bwd_mode"] = "auto"
     dq, dk, dv = qkv_leaf.grad.float().view(T, 3, nH, 32).unbind(1)
     gtol = 2e-4 if dtype == torch.float32 else 3e-2
     assert _relerr(dq, gref[0]) < gtol, "dq"
