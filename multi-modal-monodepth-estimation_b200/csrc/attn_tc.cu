@@ -388,7 +388,9 @@ struct TcBwdArgs {
 template <int NPAD>
 struct BwdLayout {
   static constexpr int MT = (NPAD + 127) / 128;
-  static constexpr int NP = (NPAD + 63) / 64;                        // 64-key panels of P / dS
+  // 64-key panels of P / dS.  The M=128 transposed MMAs always address two panels (keys 0..127), so at least two
+  // are allocated (unused ones stay zero); windows with more than 128 tokens add a third for the M=64 tail.
+  static constexpr int NP = NPAD > 128 ? 3 : 2;
   static constexpr uint32_t kRow = NPAD * 64;                        // one [NPAD][64 B] operand tile
   static constexpr uint32_t kBufBytes = 5 * kRow;                    // Q | dO | K | V | O
   static constexpr uint32_t kPanel = 128 * 128;                      // [128 rows][128 B]
