@@ -3,9 +3,12 @@
 // Replaces F.linear / nn.Linear at models/swin_transformer_v2.py:286 (qkv), :334 (proj), :77/:87 (Mlp) and
 // their autograd.
 //
-// * operands are staged by TMA (cp.async.bulk.tensor, 128 B swizzle) into a 3-stage mbarrier ring;
-// * one elected thread issues tcgen05.mma (M=128, N=128, K=16 per instruction) into a 128-column TMEM
-//   accumulator; tcgen05.commit releases smem stages and signals the epilogue;
+// * PERSISTENT: one CTA per SM walks a static tile schedule (consecutive CTAs share the A tile -> L2 reuse);
+// * operands are staged by TMA (cp.async.bulk.tensor, 128 B swizzle) into a 4/6-stage mbarrier ring that
+//   runs ahead across tile boundaries (no pipeline drain between tiles);
+// * one elected thread issues tcgen05.mma (M=128, N=128|256, K=16 per instruction) into one of TWO TMEM
+//   accumulators; tcgen05.commit releases smem stages and signals the epilogue, which drains accumulator i
+//   while the tensor pipe fills accumulator i^1;
 // * 4 epilogue warps read the accumulator with tcgen05.ld (one row per thread) and apply the fused epilogue:
 //     NONE  (+bias) | GELU (bias, erf GELU, optional pre-activation copy) | QKV (q_bias/0/v_bias, per-head
 //     L2-normalisation of q and k in fp32 + 1/|q|,1/|k| side output) | DGELU (multiply by gelu'(aux));
@@ -20,11 +23,17 @@
 namespace b200swin {
 
 namespace {
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr int BM = 128, BK = 64;
 constexpr int kGemmThreads = 192;                       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
-constexpr uint32_t kABytes = BM * BK * 2, kBBytes = BN * BK * 2;
-constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr size_t kSmemBytes = (size_t)STAGES * kStageBytes + 1024;   // + alignment slack
+constexpr uint32_t kABytes = BM * BK * 2;
+template <int BN>
+struct Tile {
+  static constexpr uint32_t kBBytes = BN * BK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BN == 256 ? 4 : 6;                  // 4 x 48 KB or 6 x 32 KB = 192 KB
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024;
+  static constexpr uint32_t kTmemCols = 2 * BN;                      // double-buffered accumulator
+};
 constexpr float kInvSqrt2 = 0.70710678118654752f;
 constexpr float kInvSqrt2Pi = 0.39894228040143268f;
 }  // namespace
@@ -33,7 +42,9 @@ struct GemmParams {
   CUtensorMap tmA[2], tmB[2];
   int nseg;
   int64_t M, N, K;
-  int num_kb, kb_per_split;
+  int num_kb, kb_per_split, splits;
+  int m_tiles, n_tiles;
+  int64_t num_tiles;
   int epilogue, out_dtype;
   void* out;
   int64_t ldo;
@@ -126,33 +137,31 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
   }
 }
 
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kGemmThreads)
+template <bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  using TL = Tile<BN>;
+  constexpr int STAGES = TL::kStages;
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = (ptx::smem_u32(smem_dyn) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024 B alignment
   unsigned char* smem_al = smem_dyn + (smem_base - ptx::smem_u32(smem_dyn));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * BM;
-  const int64_t n0 = (int64_t)blockIdx.y * BN;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int kb1 = min(p.num_kb, kb0 + p.kb_per_split);
-  const int iters = (kb1 - kb0) * p.nseg;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    ptx::mbar_init(&accum_bar, 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&p.tmA[0]);
     ptx::prefetch_tmap(&p.tmB[0]);
   }
   if (warp == 1) {
-    ptx::tmem_alloc(&tmem_slot, BN);
+    ptx::tmem_alloc(&tmem_slot, TL::kTmemCols);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -160,32 +169,48 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
+  // static persistent schedule: tile t -> (split z, m block, n block); n fastest so that CTAs running at the
+  // same time share the streamed A tile in L2 (the weight-side B operand is small and stays resident)
+  auto decode = [&](int64_t t, int& mb, int& nb, int& z) {
+    nb = (int)(t % p.n_tiles);
+    int64_t r = t / p.n_tiles;
+    mb = (int)(r % p.m_tiles);
+    z = (int)(r / p.m_tiles);
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        const int seg = it / (kb1 - kb0);
-        const int kb = kb0 + it - seg * (kb1 - kb0);
-        const CUtensorMap* ta = &p.tmA[seg == 2 ? 1 : 0];           // segments: hi.hi, hi.lo, lo.hi
-        const CUtensorMap* tb = &p.tmB[seg == 1 ? 1 : 0];
-        unsigned char* sa = smem_al + (size_t)s * kStageBytes;
-        unsigned char* sb = sa + kABytes;
-        ptx::mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-        const int k0 = kb * BK;
-        if (A_MN) {
-          ptx::tma_load_2d(sa, ta, &full_bar[s], (int)m0, k0);
-          ptx::tma_load_2d(sa + kABytes / 2, ta, &full_bar[s], (int)m0 + 64, k0);
-        } else {
-          ptx::tma_load_2d(sa, ta, &full_bar[s], k0, (int)m0);
-        }
-        if (B_MN) {
-          ptx::tma_load_2d(sb, tb, &full_bar[s], (int)n0, k0);
-          ptx::tma_load_2d(sb + kBBytes / 2, tb, &full_bar[s], (int)n0 + 64, k0);
-        } else {
-          ptx::tma_load_2d(sb, tb, &full_bar[s], k0, (int)n0);
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        int mb, nb, z;
+        decode(t, mb, nb, z);
+        const int m0 = mb * BM, n0 = nb * BN;
+        const int kb0 = z * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          const CUtensorMap* ta = &p.tmA[seg == 2 ? 1 : 0];           // segments: hi.hi, hi.lo, lo.hi
+          const CUtensorMap* tb = &p.tmB[seg == 1 ? 1 : 0];
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+            unsigned char* sa = smem_al + (size_t)s * TL::kStageBytes;
+            unsigned char* sb = sa + kABytes;
+            ptx::mbar_arrive_expect_tx(&full_bar[s], TL::kStageBytes);
+            const int k0 = kb * BK;
+            if (A_MN) {
+              ptx::tma_load_2d(sa, ta, &full_bar[s], m0, k0);
+              ptx::tma_load_2d(sa + kABytes / 2, ta, &full_bar[s], m0 + 64, k0);
+            } else {
+              ptx::tma_load_2d(sa, ta, &full_bar[s], k0, m0);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d(sb + j * 8192, tb, &full_bar[s], n0 + 64 * j, k0);
+            } else {
+              ptx::tma_load_2d(sb, tb, &full_bar[s], k0, n0);
+            }
+          }
         }
       }
     }
@@ -193,66 +218,79 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       // ------------------------------------------------------------------ MMA issuer
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
+      // descriptors differ between k-steps only in the start-address field (low 14 bits, 16 B units)
+      const uint64_t adesc0 = A_MN ? ptx::make_smem_desc(0, kABytes / 2, 1024) : ptx::make_smem_desc(0, 16, 1024);
+      const uint64_t bdesc0 = B_MN ? ptx::make_smem_desc(0, 8192, 1024) : ptx::make_smem_desc(0, 16, 1024);
+      constexpr uint32_t a_step = (A_MN ? 2048 : 32) >> 4, b_step = (B_MN ? 2048 : 32) >> 4;
+      uint32_t it = 0, tcount = 0;
+      for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+        int mb, nb, z;
+        decode(t, mb, nb, z);
+        const int kb0 = z * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+        const int iters = (kb1 - kb0) * p.nseg;
+        const uint32_t acc = tcount & 1;
+        ptx::mbar_wait(&acc_empty[acc], ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         ptx::tc_fence_after();
-        const uint32_t sa = smem_base + (uint32_t)s * kStageBytes;
-        const uint32_t sb = sa + kABytes;
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + (uint32_t)s * TL::kStageBytes;
+          const uint64_t ad = adesc0 + (sa >> 4), bd = bdesc0 + ((sa + kABytes) >> 4);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // K-major: 16 bf16 = 32 B along the swizzle row; MN-major: 16 k-rows = 2048 B
-          const uint64_t ad = A_MN ? ptx::make_smem_desc(sa + k * 2048, kABytes / 2, 1024)
-                                   : ptx::make_smem_desc(sa + k * 32, 16, 1024);
-          const uint64_t bd = B_MN ? ptx::make_smem_desc(sb + k * 2048, kBBytes / 2, 1024)
-                                   : ptx::make_smem_desc(sb + k * 32, 16, 1024);
-          ptx::mma_bf16_ss(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k)
+            ptx::mma_bf16_ss(d_tmem, ad + k * a_step, bd + k * b_step, idesc, (i | k) != 0 ? 1u : 0u);
+          ptx::mma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs retire
         }
-        ptx::mma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs retire
+        ptx::mma_commit(&acc_full[acc]);           // accumulator complete -> epilogue
       }
-      ptx::mma_commit(&accum_bar);               // accumulator complete
     }
   } else {
     // -------------------------------------------------------------------- epilogue warps (TMEM -> HBM)
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
-    const int64_t row = m0 + q * 32 + lane;
-    if (iters > 0) {
-      ptx::mbar_wait(&accum_bar, 0);
+    uint32_t tcount = 0;
+    for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+      int mb, nb, z;
+      decode(t, mb, nb, z);
+      const int64_t m0 = (int64_t)mb * BM, n0 = (int64_t)nb * BN;
+      const int64_t row = m0 + q * 32 + lane;
+      const uint32_t acc = tcount & 1;
+      ptx::mbar_wait(&acc_full[acc], (tcount >> 1) & 1);
       ptx::tc_fence_after();
-    }
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int64_t col0 = n0 + c * 32;
-      if (col0 >= p.N) break;                    // warp-uniform
-      float v[32];
-      if (iters > 0) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-        ptx::tmem_ld_wait();
+      for (int c = 0; c < BN / 32; ++c) {
+        const int64_t col0 = n0 + c * 32;
+        if (col0 >= p.N) break;                    // warp-uniform
+        float v[32];
+        {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0.f;
-      }
-      if (row < p.M) {
-        const int nvalid = (int)min((int64_t)32, p.N - col0);
-        if (p.partial) {
-          store_chunk<float>(p.partial + ((int64_t)blockIdx.z * p.M + row) * p.N + col0, v, nvalid);
-        } else if (p.out_dtype == B200SWIN_BF16) {
-          epilogue_chunk<__nv_bfloat16>(p, v, row, col0, nvalid);
-        } else {
-          epilogue_chunk<float>(p, v, row, col0, nvalid);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        }
+        if (row < p.M) {
+          const int nvalid = (int)min((int64_t)32, p.N - col0);
+          if (p.partial) {
+            store_chunk<float>(p.partial + ((int64_t)z * p.M + row) * p.N + col0, v, nvalid);
+          } else if (p.out_dtype == B200SWIN_BF16) {
+            epilogue_chunk<__nv_bfloat16>(p, v, row, col0, nvalid);
+          } else {
+            epilogue_chunk<float>(p, v, row, col0, nvalid);
+          }
         }
       }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);    // 4 arrivals (one per epilogue warp) free the accumulator
     }
-    ptx::tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, BN);
+    ptx::tmem_dealloc(tmem_base, TL::kTmemCols);
   }
 }
 
@@ -308,10 +346,10 @@ int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t
   return B200SWIN_OK;
 }
 
-static int operand_map(CUtensorMap* m, const void* ptr, int mn_major, int64_t mn, int64_t k) {
-  // K-major: stored [mn][k] -> box {BK, 128 rows};  MN-major: stored [k][mn] -> box {64 mn, BK k-rows}
+static int operand_map(CUtensorMap* m, const void* ptr, int mn_major, int64_t mn, int64_t k, int rows) {
+  // K-major: stored [mn][k] -> box {BK, rows};  MN-major: stored [k][mn] -> box {64 mn, BK k-rows}
   if (mn_major) return make_tmap_2d_bf16(m, ptr, (uint64_t)mn, (uint64_t)k, (uint64_t)mn * 2, 64, BK);
-  return make_tmap_2d_bf16(m, ptr, (uint64_t)k, (uint64_t)mn, (uint64_t)k * 2, BK, 128);
+  return make_tmap_2d_bf16(m, ptr, (uint64_t)k, (uint64_t)mn, (uint64_t)k * 2, BK, (uint32_t)rows);
 }
 
 }  // namespace b200swin
@@ -320,7 +358,7 @@ using namespace b200swin;
 
 extern "C" int b200swin_gemm_splits(int64_t M, int64_t N, int64_t K) {
   // split-K factor the library would pick so that the grid covers the SMs about twice
-  int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int64_t tiles = ((M + BM - 1) / BM) * ((N + 127) / 128);
   int64_t num_kb = (K + BK - 1) / BK;
   int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
   if (want < 1) want = 1;
@@ -362,13 +400,15 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
     BSW_REQUIRE(workspace && workspace_bytes >= b200swin_gemm_workspace_bytes(M, N, splits),
                 "gemm: split-K workspace too small");
   }
+  // 128x256 tiles halve the A re-reads and the smem bandwidth per MMA; 128x128 when N does not fill them
+  const int bn = (N % 256 == 0 || N >= 1024) ? 256 : 128;
   int rc;
-  if ((rc = operand_map(&p.tmA[0], a_hi, a_mn_major, M, K))) return rc;
-  if ((rc = operand_map(&p.tmB[0], b_hi, b_mn_major, N, K))) return rc;
+  if ((rc = operand_map(&p.tmA[0], a_hi, a_mn_major, M, K, BM))) return rc;
+  if ((rc = operand_map(&p.tmB[0], b_hi, b_mn_major, N, K, bn))) return rc;
   p.nseg = 1;
   if (a_lo) {
-    if ((rc = operand_map(&p.tmA[1], a_lo, a_mn_major, M, K))) return rc;
-    if ((rc = operand_map(&p.tmB[1], b_lo, b_mn_major, N, K))) return rc;
+    if ((rc = operand_map(&p.tmA[1], a_lo, a_mn_major, M, K, BM))) return rc;
+    if ((rc = operand_map(&p.tmB[1], b_lo, b_mn_major, N, K, bn))) return rc;
     p.nseg = 3;
   }
   p.M = M; p.N = N; p.K = K;
@@ -381,20 +421,25 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   p.bias = bias; p.bias2 = bias2; p.aux_in = aux_in; p.aux_out = aux_out; p.inv_norm = inv_norm; p.nH = nH;
   p.partial = splits > 1 ? (float*)workspace : nullptr;
   if (splits > 1) p.bias = nullptr;
+  p.splits = splits;
 
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)splits);
-  BSW_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm: grid too large");
-#define LAUNCH(AM, BMN)                                                                                       \
+  p.m_tiles = (int)((M + BM - 1) / BM);
+  p.n_tiles = (int)((N + bn - 1) / bn);
+  p.num_tiles = (int64_t)p.m_tiles * p.n_tiles * splits;
+  const unsigned grid = (unsigned)(p.num_tiles < sm_count() ? p.num_tiles : sm_count());
+#define LAUNCH(AM, BMN, BNV)                                                                                  \
   do {                                                                                                        \
-    BSW_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                  (int)kSmemBytes));                                                          \
-    gemm_tc_kernel<AM, BMN><<<grid, kGemmThreads, kSmemBytes, st>>>(p);                                       \
+    BSW_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AM, BMN, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  (int)Tile<BNV>::kSmemBytes));                                               \
+    gemm_tc_kernel<AM, BMN, BNV><<<grid, kGemmThreads, Tile<BNV>::kSmemBytes, st>>>(p);                       \
   } while (0)
-  if (a_mn_major && b_mn_major) LAUNCH(true, true);
-  else if (a_mn_major) LAUNCH(true, false);
-  else if (b_mn_major) LAUNCH(false, true);
-  else LAUNCH(false, false);
+#define LAUNCH_BN(AM, BMN) do { if (bn == 256) LAUNCH(AM, BMN, 256); else LAUNCH(AM, BMN, 128); } while (0)
+  if (a_mn_major && b_mn_major) LAUNCH_BN(true, true);
+  else if (a_mn_major) LAUNCH_BN(true, false);
+  else if (b_mn_major) LAUNCH_BN(false, true);
+  else LAUNCH_BN(false, false);
+#undef LAUNCH_BN
 #undef LAUNCH
   BSW_LAUNCH_CHECK();
   if (splits > 1) {
