@@ -9,7 +9,10 @@
 // * one elected thread issues tcgen05.mma (M=128, N=128|256, K=16 per instruction) into one of TWO TMEM
 //   accumulators; tcgen05.commit releases smem stages and signals the epilogue, which drains accumulator i
 //   while the tensor pipe fills accumulator i^1;
-// * 4 epilogue warps read the accumulator with tcgen05.ld (one row per thread) and apply the fused epilogue:
+// * 4 epilogue warps read the accumulator with tcgen05.ld (one row per thread), apply the fused epilogue in
+//   registers, stage 32-row x 64-byte units in shared memory (64 B swizzle, conflict-free) and hand them to
+//   TMA stores (cp.async.bulk.tensor ... bulk_group), so HBM sees full-sector row writes and the M/N edges are
+//   clipped by the tensor map:
 //     NONE  (+bias) | GELU (bias, erf GELU, optional pre-activation copy) | QKV (q_bias/0/v_bias, per-head
 //     L2-normalisation of q and k in fp32 + 1/|q|,1/|k| side output) | DGELU (multiply by gelu'(aux));
 // * either operand may be "MN-major" (stored [K][M] / [K][N]), which is how dgrad (B = W as stored) and wgrad
@@ -26,12 +29,16 @@ namespace {
 constexpr int BM = 128, BK = 64;
 constexpr int kGemmThreads = 192;                       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr uint32_t kABytes = BM * BK * 2;
+// epilogue staging: per epilogue warp a ring of kEpiBufs units of 32 rows x 64 B (SWIZZLE_64B)
+constexpr int kEpiBufs = 4;
+constexpr uint32_t kEpiUnitBytes = 32 * 64;
+constexpr uint32_t kEpiSmemBytes = 4 * kEpiBufs * kEpiUnitBytes;    // 32 KB
 template <int BN>
 struct Tile {
   static constexpr uint32_t kBBytes = BN * BK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BN == 256 ? 4 : 6;                  // 4 x 48 KB or 6 x 32 KB = 192 KB
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kEpiSmemBytes + 1024;
   static constexpr uint32_t kTmemCols = 2 * BN;                      // double-buffered accumulator
 };
 constexpr float kInvSqrt2 = 0.70710678118654752f;
@@ -40,6 +47,7 @@ constexpr float kInvSqrt2Pi = 0.39894228040143268f;
 
 struct GemmParams {
   CUtensorMap tmA[2], tmB[2];
+  CUtensorMap tmOut, tmAux;                 // store maps: box {64 B of columns, 32 rows}, SWIZZLE_64B
   int nseg;
   int64_t M, N, K;
   int num_kb, kb_per_split, splits;
@@ -54,7 +62,8 @@ struct GemmParams {
   void* aux_out;
   float* inv_norm;
   int nH, Cq;
-  float* partial;
+  int partial;                              // split-K: tmOut covers the fp32 workspace [splits * m_pad, N]
+  int64_t m_pad;
 };
 
 __device__ __forceinline__ float gelu_erf(float z) { return 0.5f * z * (1.0f + erff(z * kInvSqrt2)); }
@@ -62,20 +71,65 @@ __device__ __forceinline__ float gelu_grad(float z) {
   return 0.5f * (1.0f + erff(z * kInvSqrt2)) + z * kInvSqrt2Pi * __expf(-0.5f * z * z);
 }
 
-template <typename T>
-__device__ __forceinline__ void store_chunk(T* p, const float (&v)[32], int nvalid) {
-  if (nvalid >= 32) {
-#pragma unroll
-    for (int c = 0; c < 32; c += 4) {
-      float t[4] = {v[c], v[c + 1], v[c + 2], v[c + 3]};
-      st4(p + c, t);
+// Per-warp staging ring for the TMA-store epilogue.  A unit is 32 rows x 64 B with the 64-byte swizzle
+// (16-byte piece j of row r sits at r*64 + ((j ^ ((r >> 1) & 3)) << 4)): eight consecutive rows hit eight distinct
+// 16-byte bank groups, so the st.shared.v4 of a warp is conflict-free.
+struct Stager {
+  uint32_t base;       // shared address of this warp's kEpiBufs units
+  uint32_t slot;       // units issued so far
+  int lane;
+
+  __device__ __forceinline__ uint32_t acquire() {
+    if (lane == 0) ptx::bulk_wait_read<kEpiBufs - 1>();    // the store that last used this unit has read it
+    __syncwarp();
+    return base + (slot % kEpiBufs) * kEpiUnitBytes;
+  }
+  __device__ __forceinline__ void piece(uint32_t unit, int j, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const uint32_t addr = unit + (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+  }
+  __device__ __forceinline__ void release(const CUtensorMap* tm, uint32_t unit, int c0, int c1) {
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(tm, unit, c0, c1);
+      ptx::bulk_commit();
     }
+    ++slot;
+  }
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// 32 consecutive columns of one row per thread -> global through the staging ring (col0 / row0: tile coordinates of
+// the warp's 32 x 32 chunk; the tensor map clips everything beyond M and N)
+template <typename OutT>
+__device__ __forceinline__ void store_chunk(Stager& st, const CUtensorMap* tm, const float (&v)[32], int col0, int row0,
+                                            int64_t N) {
+  if constexpr (sizeof(OutT) == 2) {
+    const uint32_t u = st.acquire();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      st.piece(u, j, pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+               pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    st.release(tm, u, col0, row0);
   } else {
 #pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (c < nvalid) Io<T>::st(p + c, v[c]);
+    for (int h = 0; h < 2; ++h) {
+      if (col0 + 16 * h >= N) break;                     // warp-uniform
+      const uint32_t u = st.acquire();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        st.piece(u, j, __float_as_uint(v[16 * h + 4 * j]), __float_as_uint(v[16 * h + 4 * j + 1]),
+                 __float_as_uint(v[16 * h + 4 * j + 2]), __float_as_uint(v[16 * h + 4 * j + 3]));
+      st.release(tm, u, col0 + 16 * h, row0);
+    }
   }
 }
+
 template <typename T>
 __device__ __forceinline__ void load_chunk32(const T* p, float (&v)[32], int nvalid) {
   if (nvalid >= 32) {
@@ -91,39 +145,46 @@ __device__ __forceinline__ void load_chunk32(const T* p, float (&v)[32], int nva
   }
 }
 
-template <typename OutT>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[32], int64_t row, int64_t col0,
-                                               int nvalid) {
-  OutT* out = reinterpret_cast<OutT*>(p.out) + row * p.ldo + col0;
-  if (p.epilogue == B200SWIN_EPI_NONE) {
-    if (p.bias) {
+// v[c] += bias[c0 + c] for the columns that exist (N is a multiple of 4, so float4 granularity is exact)
+__device__ __forceinline__ void add_bias32(float (&v)[32], const float* __restrict__ bias, int nvalid) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c < nvalid) v[c] += p.bias[col0 + c];
+  for (int c = 0; c < 32; c += 4) {
+    if (c < nvalid) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c));
+      v[c] += b.x; v[c + 1] += b.y; v[c + 2] += b.z; v[c + 3] += b.w;
     }
-    store_chunk<OutT>(out, v, nvalid);
+  }
+}
+
+// `valid_row`: this thread's row exists (row < M); rows beyond M still take part in the staging (the store clips).
+template <typename OutT>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, Stager& st, float (&v)[32], int64_t row, int row0,
+                                               int col0, int nvalid, bool valid_row) {
+  if (p.epilogue == B200SWIN_EPI_NONE) {
+    if (p.bias) add_bias32(v, p.bias + col0, nvalid);
+    store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
   } else if (p.epilogue == B200SWIN_EPI_GELU) {
-#pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (c < nvalid && p.bias) v[c] += p.bias[col0 + c];
-    if (p.aux_out) store_chunk<OutT>(reinterpret_cast<OutT*>(p.aux_out) + row * p.ldo + col0, v, nvalid);
+    if (p.bias) add_bias32(v, p.bias + col0, nvalid);
+    if (p.aux_out) store_chunk<OutT>(st, &p.tmAux, v, col0, row0, p.N);
 #pragma unroll
     for (int c = 0; c < 32; ++c) v[c] = gelu_erf(v[c]);
-    store_chunk<OutT>(out, v, nvalid);
+    store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
   } else if (p.epilogue == B200SWIN_EPI_DGELU) {
     float z[32];
-    load_chunk32<OutT>(reinterpret_cast<const OutT*>(p.aux_in) + row * p.ldo + col0, z, nvalid);
+    if (valid_row) {
+      load_chunk32<OutT>(reinterpret_cast<const OutT*>(p.aux_in) + row * p.ldo + col0, z, nvalid);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) z[c] = 0.f;
+    }
 #pragma unroll
     for (int c = 0; c < 32; ++c) v[c] *= gelu_grad(z[c]);
-    store_chunk<OutT>(out, v, nvalid);
+    store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
   } else {  // B200SWIN_EPI_QKV: one 32-column chunk == one head of q, k or v  (swin_transformer_v2.py:283-293)
-    const int part = (int)(col0 / p.Cq);
-    const int cin = (int)(col0 - (int64_t)part * p.Cq);
+    const int part = col0 / p.Cq;
+    const int cin = col0 - part * p.Cq;
     const float* b = part == 0 ? p.bias : (part == 2 ? p.bias2 : nullptr);
-    if (b) {
-#pragma unroll
-      for (int c = 0; c < 32; ++c) v[c] += b[cin + c];
-    }
+    if (b) add_bias32(v, b + cin, 32);
     if (part < 2) {
       float ss = 0.f;
 #pragma unroll
@@ -131,9 +192,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
       const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);          // F.normalize(eps=1e-12)
 #pragma unroll
       for (int c = 0; c < 32; ++c) v[c] *= inv;
-      if (p.inv_norm) p.inv_norm[(row * 2 + part) * p.nH + (cin >> 5)] = inv;
+      if (p.inv_norm && valid_row) p.inv_norm[(row * 2 + part) * p.nH + (cin >> 5)] = inv;
     }
-    store_chunk<OutT>(out, v, nvalid);
+    store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
   }
 }
 
@@ -159,6 +220,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&p.tmA[0]);
     ptx::prefetch_tmap(&p.tmB[0]);
+    ptx::prefetch_tmap(&p.tmOut);
   }
   if (warp == 1) {
     ptx::tmem_alloc(&tmem_slot, TL::kTmemCols);
@@ -248,37 +310,41 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       }
     }
   } else {
-    // -------------------------------------------------------------------- epilogue warps (TMEM -> HBM)
+    // -------------------------------------------------------------------- epilogue warps (TMEM -> smem -> TMA store)
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    Stager st;
+    st.base = smem_base + (uint32_t)STAGES * TL::kStageBytes + (uint32_t)q * (kEpiBufs * kEpiUnitBytes);
+    st.slot = 0;
+    st.lane = lane;
     uint32_t tcount = 0;
     for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
       int mb, nb, z;
       decode(t, mb, nb, z);
-      const int64_t m0 = (int64_t)mb * BM, n0 = (int64_t)nb * BN;
-      const int64_t row = m0 + q * 32 + lane;
+      const int m0 = mb * BM + q * 32, n0 = nb * BN;
+      const int64_t row = (int64_t)m0 + lane;
       const uint32_t acc = tcount & 1;
       ptx::mbar_wait(&acc_full[acc], (tcount >> 1) & 1);
       ptx::tc_fence_after();
+      if (m0 < p.M) {                              // warp-uniform: this 32-row slab exists
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int64_t col0 = n0 + c * 32;
-        if (col0 >= p.N) break;                    // warp-uniform
-        float v[32];
-        {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
-          ptx::tmem_ld_wait();
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= p.N) break;                  // warp-uniform
+          float v[32];
+          {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        }
-        if (row < p.M) {
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          }
           const int nvalid = (int)min((int64_t)32, p.N - col0);
           if (p.partial) {
-            store_chunk<float>(p.partial + ((int64_t)z * p.M + row) * p.N + col0, v, nvalid);
+            store_chunk<float>(st, &p.tmOut, v, col0, (int)((int64_t)z * p.m_pad) + m0, p.N);
           } else if (p.out_dtype == B200SWIN_BF16) {
-            epilogue_chunk<__nv_bfloat16>(p, v, row, col0, nvalid);
+            epilogue_chunk<__nv_bfloat16>(p, st, v, row, m0, col0, nvalid, row < p.M);
           } else {
-            epilogue_chunk<float>(p, v, row, col0, nvalid);
+            epilogue_chunk<float>(p, st, v, row, m0, col0, nvalid, row < p.M);
           }
         }
       }
@@ -286,6 +352,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);    // 4 arrivals (one per epilogue warp) free the accumulator
     }
+    if (lane == 0) ptx::bulk_wait<0>();            // all stores of this warp have landed before the CTA retires
   }
   __syncthreads();
   if (warp == 1) {
@@ -297,14 +364,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 // fixed-order split-K reduction: out[m,n] = sum_z partial[z,m,n] (+ bias[n])
 template <typename OutT>
 __global__ void __launch_bounds__(256)
-splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t MN, int64_t N,
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, int64_t MN, int64_t N, int64_t split_stride,
                      const float* __restrict__ bias, OutT* __restrict__ out) {
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < MN;
        i += (int64_t)gridDim.x * blockDim.x * 4) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int z = 0; z < splits; ++z) {
       float t[4];
-      ld4(partial + (int64_t)z * MN + i, t);
+      ld4(partial + (int64_t)z * split_stride + i, t);
       acc[0] += t[0]; acc[1] += t[1]; acc[2] += t[2]; acc[3] += t[3];
     }
     if (bias) {
@@ -346,6 +413,34 @@ int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t
   return B200SWIN_OK;
 }
 
+int make_tmap_2d(CUtensorMap* m, const void* base, int dtype, uint64_t inner, uint64_t outer,
+                 uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode_tiled();
+  BSW_REQUIRE(enc, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  BSW_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA: base pointer must be 16-byte aligned");
+  BSW_REQUIRE(outer_stride_bytes % 16 == 0, "TMA: row stride (%llu B) must be a multiple of 16",
+              (unsigned long long)outer_stride_bytes);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {outer_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                              : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                     : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(m, dtype == B200SWIN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BSW_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return B200SWIN_OK;
+}
+
+// store map of a row-major [rows][N] output: box = 64 bytes of columns x 32 rows, 64 B swizzle
+static int store_map(CUtensorMap* m, const void* ptr, int dtype, int64_t rows, int64_t N) {
+  const uint32_t es = dtype == B200SWIN_BF16 ? 2 : 4;
+  return make_tmap_2d(m, ptr, dtype, (uint64_t)N, (uint64_t)rows, (uint64_t)N * es, 64 / es, 32, 64);
+}
+
 static int operand_map(CUtensorMap* m, const void* ptr, int mn_major, int64_t mn, int64_t k, int rows) {
   // K-major: stored [mn][k] -> box {BK, rows};  MN-major: stored [k][mn] -> box {64 mn, BK k-rows}
   if (mn_major) return make_tmap_2d_bf16(m, ptr, (uint64_t)mn, (uint64_t)k, (uint64_t)mn * 2, 64, BK);
@@ -369,7 +464,9 @@ extern "C" int b200swin_gemm_splits(int64_t M, int64_t N, int64_t K) {
 }
 
 extern "C" size_t b200swin_gemm_workspace_bytes(int64_t M, int64_t N, int splits) {
-  return splits > 1 ? (size_t)splits * (size_t)M * (size_t)N * sizeof(float) : 0;
+  // fp32 partials [splits][M rounded up to the 128-row tile][N]
+  const int64_t m_pad = (M + BM - 1) / BM * BM;
+  return splits > 1 ? (size_t)splits * (size_t)m_pad * (size_t)N * sizeof(float) : 0;
 }
 
 extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_major, const void* b_hi,
@@ -383,7 +480,7 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   BSW_REQUIRE((a_lo == nullptr) == (b_lo == nullptr), "gemm: a_lo and b_lo must be given together");
   BSW_REQUIRE(out_dtype == B200SWIN_F32 || out_dtype == B200SWIN_BF16, "gemm: bad out dtype %d", out_dtype);
   BSW_REQUIRE(epilogue >= B200SWIN_EPI_NONE && epilogue <= B200SWIN_EPI_DGELU, "gemm: bad epilogue %d", epilogue);
-  BSW_REQUIRE(N % 4 == 0, "gemm: N must be a multiple of 4");
+  BSW_REQUIRE(N % 8 == 0, "gemm: N must be a multiple of 8 (16-byte rows for the TMA stores)");
   BSW_REQUIRE((a_mn_major ? M : K) % 8 == 0 && (b_mn_major ? N : K) % 8 == 0,
               "gemm: contiguous operand dimension must be a multiple of 8 (16-byte TMA rows)");
   if (splits < 1) splits = 1;
@@ -419,9 +516,16 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   p.epilogue = epilogue; p.out_dtype = out_dtype;
   p.out = out; p.ldo = N;
   p.bias = bias; p.bias2 = bias2; p.aux_in = aux_in; p.aux_out = aux_out; p.inv_norm = inv_norm; p.nH = nH;
-  p.partial = splits > 1 ? (float*)workspace : nullptr;
+  p.partial = splits > 1 ? 1 : 0;
+  p.m_pad = (M + BM - 1) / BM * BM;
   if (splits > 1) p.bias = nullptr;
   p.splits = splits;
+  if (splits > 1) {
+    if ((rc = store_map(&p.tmOut, workspace, B200SWIN_F32, (int64_t)splits * p.m_pad, N))) return rc;
+  } else {
+    if ((rc = store_map(&p.tmOut, out, out_dtype, M, N))) return rc;
+    if (aux_out && (rc = store_map(&p.tmAux, aux_out, out_dtype, M, N))) return rc;
+  }
 
   cudaStream_t st = (cudaStream_t)stream;
   p.m_tiles = (int)((M + BM - 1) / BM);
@@ -448,9 +552,10 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
     int64_t cap = (int64_t)sm_count() * 8;
     int g = (int)(blocks < cap ? blocks : cap);
     if (out_dtype == B200SWIN_F32)
-      splitk_reduce_kernel<float><<<g, 256, 0, st>>>((const float*)workspace, splits, MN, N, bias, (float*)out);
+      splitk_reduce_kernel<float><<<g, 256, 0, st>>>((const float*)workspace, splits, MN, N, p.m_pad * N, bias,
+                                                     (float*)out);
     else
-      splitk_reduce_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const float*)workspace, splits, MN, N, bias,
+      splitk_reduce_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const float*)workspace, splits, MN, N, p.m_pad * N, bias,
                                                             (__nv_bfloat16*)out);
     BSW_LAUNCH_CHECK();
   }

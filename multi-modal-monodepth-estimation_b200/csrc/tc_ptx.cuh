@@ -64,6 +64,22 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "r"(c3)
       : "memory");
 }
+// shared -> global tile store (bulk async group); rows/columns outside the tensor map are clipped by the hardware
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
 // Ampere-style 16-byte async copy global -> shared (LDGSTS); src_bytes = 0 zero-fills the destination
 __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes = 16) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
@@ -202,5 +218,8 @@ EncodeTiledFn get_encode_tiled();
 // 2-D bf16 tensor [outer][inner] (inner contiguous), box [box_outer][box_inner], 128 B swizzle, zero OOB fill.
 int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
                       uint32_t box_inner, uint32_t box_outer);
+// general form: dtype = B200SWIN_F32 | B200SWIN_BF16, swizzle_bytes = 0 | 32 | 64 | 128
+int make_tmap_2d(CUtensorMap* m, const void* base, int dtype, uint64_t inner, uint64_t outer,
+                 uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 
 }  // namespace b200swin
