@@ -14,6 +14,7 @@
 //           math), log-sum-exp per row for the backward.
 //
 // Windows with more than 128 tokens (ws=12 -> 144) run a second 128-row tile for the remaining rows.
+#include <stdlib.h>
 #include "common.cuh"
 #include "wingeom.cuh"
 #include "tc_ptx.cuh"
@@ -309,6 +310,16 @@ static int launch_fwd(const TcArgs& a, cudaStream_t st) {
 }
 }  // namespace
 
+// warp-specialised forward (attn_fwd_ws.cu)
+bool attn_fwd_ws_supported(int ws);
+int attn_fwd_ws(const void* qkv, void* out, float* lse, const float* table16, const float* scale, const float* qpad,
+                const float* vpad, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st);
+static bool use_legacy_fwd() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200SWIN_ATTN_FWD_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 bool attn_tc_supported(int ws, int C, int nH, const void* mask) {
   const int N = ws * ws;
   return mask == nullptr && C == nH * HD && N <= 256 && N >= 4;
@@ -324,6 +335,8 @@ int attn_fwd_tc(const void* qkv, void* out, float* lse, const float* table16, co
   BSW_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && C % 8 == 0,
               "attn_fwd(tc): qkv/out must be 16-byte aligned");
   BSW_REQUIRE((int64_t)B * H * W < (1ll << 29), "attn_fwd(tc): too many tokens");
+  if (attn_fwd_ws_supported(ws) && !use_legacy_fwd())
+    return attn_fwd_ws(qkv, out, lse, table16, scale, qpad, vpad, B, H, W, C, nH, ws, shift, st);
   TcArgs a;
   a.qkv = (const __nv_bfloat16*)qkv; a.out = (__nv_bfloat16*)out; a.lse = lse;
   a.table16 = table16; a.scale = scale; a.qpad = qpad; a.vpad = vpad;
