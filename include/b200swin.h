@@ -116,10 +116,13 @@ int b200swin_ln_bwd(const void* dy, const void* x, const float* gamma, const flo
 int b200swin_attn_fwd(const void* qkv, void* out, float* lse, const float* table16, const float* scale,
                       const float* qpad, const float* vpad, const float* mask, int nWm, int B, int H, int W,
                       int C, int nH, int ws, int shift, int dtype, int impl, void* stream);
+/* bytes of caller-owned scratch the backward needs for this shape / implementation (0: none) */
+size_t b200swin_attn_bwd_workspace_bytes(int B, int H, int W, int nH, int ws, int dtype, int impl);
 int b200swin_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
                       const float* table16, const float* scale, const float* qpad, const float* vpad,
                       const float* mask, int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, int B,
-                      int H, int W, int C, int nH, int ws, int shift, int dtype, int impl, void* stream);
+                      int H, int W, int C, int nH, int ws, int shift, int dtype, int impl, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense contraction on tcgen05 tensor cores:  out[M,N] = epilogue( A[M,K] . B[N,K]^T ).

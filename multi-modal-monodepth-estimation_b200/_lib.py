@@ -37,7 +37,8 @@ SIGNATURES = {
     "b200swin_ln_bwd_workspace_bytes": (Z, [L, I]),
     "b200swin_ln_bwd": (I, [P, P, P, P, P, P, L, P, P, P, L, I, I, P, Z, P]),
     "b200swin_attn_fwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P]),
-    "b200swin_attn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, I, I, P]),
+    "b200swin_attn_bwd_workspace_bytes": (Z, [I, I, I, I, I, I, I]),
+    "b200swin_attn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, I, I, P, Z, P]),
     "b200swin_gemm_splits": (I, [L, L, L]),
     "b200swin_gemm_workspace_bytes": (Z, [L, L, I]),
     "b200swin_gemm_bf16": (I, [P, P, I, P, P, I, L, L, L, I, P, P, P, P, P, I, P, I, I, P, Z, P]),

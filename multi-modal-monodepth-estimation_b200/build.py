@@ -60,7 +60,8 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool =
         src, obj = pair
         if not force and _newer(obj, [src] + headers):
             return None
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", src, "-o", obj]
+        extra = os.environ.get("B200SWIN_EXTRA_NVCC", "").split()          # e.g. -DB200SWIN_TRACE for debug builds
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

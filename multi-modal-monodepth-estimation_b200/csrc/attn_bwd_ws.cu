@@ -1,0 +1,913 @@
+// Warp-specialised attention-core backward on tcgen05 (bf16 storage, windows up to 12x12 = 144 tokens).
+//
+// Same math as the backward half of attn_tc.cu (reference autograd of
+// models/swin_transformer_v2.py:295-328 with :429-463 and :874-892 as address math), per (window, head) item:
+//   S = Q K^T, dP = dO V^T            tcgen05, fp32 in TMEM, never in HBM
+//   P = exp2(S' - lse), dS = P (dP - D)   CUDA cores, D = <dO, O> precomputed per (token, head) by a tiny pre-kernel
+//   dQ = dS K, dV = P^T dO, dK = dS^T Q   tcgen05; P / dS are bf16 panels in shared memory whose bytes serve both as
+//                                         the K-major A operand (dQ) and the MN-major A operand (dV, dK)
+// restructured as a dataflow pipeline:
+//   warps 12-14  gather: cp.async of q_hat / k_hat / v / dO rows (+ lse, D) into a ring of swizzled UMMA tiles;
+//   warp  15     one thread issues every tcgen05.mma, software-pipelined: S, dP of unit u+1 go out before
+//                dQ, dK, dV of unit u, so the tensor pipe works on the previous unit while the 12 compute warps
+//                are busy with the current one;
+//   warps 0-11   compute: TMEM lane quarter q = warp % 4 (= SM sub-partition), key third kq = warp / 4.  A thread
+//                owns one query row x one third of the keys; the sum over windows of dS (the gradient of the
+//                relative position bias) stays in its REGISTERS across all items of a head and is flushed once.
+// A 12x12 window has 144 = 128 + 16 query rows.  The 16-row tail is a second unit whose S / dP rows sit in lanes
+// 0-15 of quarter 0; they are read with the 16x256b TMEM shape, which spreads 16 rows x 8 columns over all 32
+// lanes, so the tail costs a fraction of a full pass (its bias-gradient sums live in shared memory).
+// Items are head-major, every CTA owns a contiguous range (accumulators are flushed when the head changes).
+#include <stdlib.h>
+#include <vector>
+#include "common.cuh"
+#include "wingeom.cuh"
+#include "tc_ptx.cuh"
+#include "../../include/b200swin.h"
+
+namespace b200swin {
+
+namespace {
+constexpr int HD = 32;
+// 12 compute warps (3 key thirds x 4 TMEM lane quarters), 3 gather warps, 1 MMA issuer warp.  The service warps have
+// the HIGHEST warp ids: the scheduler favours them, and they are nearly always asleep.
+constexpr int kThreads = 512;
+constexpr int kComputeWarps = 12;
+constexpr int kCompute = kComputeWarps * 32;
+constexpr int kIssuerWarp = 15;
+constexpr int kLoaders = 96;
+constexpr int LAG = 1;
+// register budget: 512 threads x 128 at launch = 65536 = 128 x kRegService + 384 x kRegCompute.  The compute threads
+// keep up to 48 bias-gradient sums live across the whole kernel; NOTHING may spill: with ~225 KB of the unified
+// L1 carved out as shared memory there is no L1 left, and a local-memory access costs an L2 round trip.
+constexpr int kRegService = 56, kRegCompute = 152;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kMaskLog2 = -100.0f * 1.4426950408889634f;
+constexpr uint32_t kSw64 = 4;       // UMMA layout type SWIZZLE_64B
+constexpr uint32_t kPanel = 128 * 128;   // one 64-key panel of P or dS: [128 query rows][128 B], 128 B swizzle
+
+struct BwArgs {
+  const __nv_bfloat16* qkv;
+  const __nv_bfloat16* dout;
+  const float* lse;
+  const float* dvec;        // [B*H*W, nH]  D = <dO, O>
+  const float* inv_norm;
+  const float* table16;
+  const float* scale;
+  const float* qpad;
+  const float* vpad;
+  __nv_bfloat16* dqkv;
+  float* dtable16;
+  float* dscale;
+  float* dvpad;
+  WinGeom g;
+  int C, nH;
+  int64_t nwin, nitems;
+  long long* trace;   // debug builds (-DB200SWIN_TRACE)
+};
+
+#ifdef B200SWIN_TRACE
+#define TR(ev, idx)                                                                           \
+  do {                                                                                        \
+    if (a.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trc_ < 3000) {               \
+      long long* e_ = a.trace + 1 + 4 * ((threadIdx.x >> 5) * 3000 + trc_);                   \
+      e_[0] = (ev); e_[1] = threadIdx.x >> 5; e_[2] = (idx); e_[3] = clock64();               \
+      ++trc_;                                                                                 \
+    }                                                                                         \
+  } while (0)
+#else
+#define TR(ev, idx) do {} while (0)
+#endif
+
+constexpr int ceil8(int x) { return (x + 7) / 8 * 8; }
+
+template <int WS>
+struct Cfg {
+  static constexpr int N = WS * WS;
+  static constexpr int NPAD = (N + 15) / 16 * 16;
+  static constexpr int MT = (NPAD + 127) / 128;
+  static constexpr int TAIL = N - 128 * (MT - 1);                 // valid query rows of the last tile
+  static_assert(MT == 1 || TAIL <= 16, "the tail unit handles at most 16 rows");
+  static constexpr int NP = NPAD > 128 ? 3 : 2;                   // 64-key panels (the M=128 transposed MMAs span two)
+  static constexpr int K0 = 0, K1 = ceil8((NPAD + 2) / 3), K2 = ceil8((2 * NPAD + 2) / 3) < NPAD ? ceil8((2 * NPAD + 2) / 3) : NPAD,
+                       K3 = NPAD;                                  // key thirds (multiples of 8)
+  static constexpr int NCMAX = (K1 - K0 > K2 - K1 ? K1 - K0 : K2 - K1) > K3 - K2 ? (K1 - K0 > K2 - K1 ? K1 - K0 : K2 - K1) : K3 - K2;
+  // equal thirds that start on a window row -> the unrolled compute code is shared by all key thirds
+  static constexpr bool UNIFIED = (K1 - K0 == K2 - K1) && (K2 - K1 == K3 - K2) && (K1 % WS == 0) && (NPAD == N);
+  static constexpr uint32_t kRow = NPAD * 64;                     // one [NPAD][64 B] operand tile
+  // Q | dO | K | V | lse[NPAD] | D[NPAD], padded to 1 KB so that every tile keeps the swizzle phase of its address
+  static constexpr uint32_t kStage = (4 * kRow + 2 * NPAD * 4 + 1023) / 1024 * 1024;
+  static constexpr uint32_t kPBytes = NP * kPanel;
+  static constexpr int TW = 2 * WS - 1, NTAB = TW * TW;
+  // TMEM columns
+  static constexpr uint32_t S_COL = 0, DP_COL = NPAD, DQ_COL = 2 * NPAD /* two buffers */, DV_COL = DQ_COL + 64,
+                            DK_COL = DV_COL + 32, DVT_COL = DK_COL + 32, DKT_COL = DVT_COL + 32;
+  static_assert(2 * NPAD + 192 <= 512, "TMEM budget");
+  static constexpr size_t kFixed = 2 * (size_t)kPBytes + 2 * (size_t)NTAB * 4 + (size_t)NPAD * 4 /* meta */ +
+                                   (MT > 1 ? 16 * (size_t)NPAD * 4 : 0) /* tail bias-gradient sums */ + 1024 + 64;
+  static constexpr int NSTAGE_RAW = (int)((227 * 1024 - kFixed) / kStage);
+  static constexpr int NSTAGE = NSTAGE_RAW > 6 ? 6 : NSTAGE_RAW;
+  static_assert(NSTAGE >= 2, "shared memory budget");
+  static constexpr size_t kSmem = kFixed + (size_t)NSTAGE * kStage;
+};
+
+__device__ __forceinline__ uint32_t sw64_off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+// 16 lanes x 8 columns spread over the warp: thread t gets rows t/4 and t/4 + 8, columns 2 (t % 4) and + 1
+// (r0, r1: first row; r2, r3: second row) -- layout verified on hardware by tools/probe/tmem_shapes.cu
+__device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+template <int R>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+__device__ __forceinline__ void cp_async_4(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+__device__ __forceinline__ int src_token(const WinGeom& g, int b, int wh, int ww, int y, int x) {
+  int i = wh * g.ws + y + g.shift; if (i >= g.Hp) i -= g.Hp;
+  int j = ww * g.ws + x + g.shift; if (j >= g.Wp) j -= g.Wp;
+  return (i < g.H && j < g.W) ? (b * g.H + i) * g.W + j : -1;
+}
+
+// F.normalize backward + store of one gradient row straight from a 32-column TMEM accumulator:
+//   d = (g*sc - x_hat <g*sc, x_hat>) * inv_norm,   x_hat read from the swizzled operand tile.
+// Two passes over the accumulator in 8-column pieces (dot product, then the row) keep the register peak far below the
+// long-lived bias-gradient sums -- a peak here would make the allocator spill THOSE for their whole life.
+// Warp-collective (tcgen05.ld): every lane calls it; `active` lanes own a row and store.
+__device__ __forceinline__ void normalize_bwd_store(uint32_t taddr, const unsigned char* tile, int r, float sc, float invn,
+                                                    __nv_bfloat16* dst, bool active) {
+  float dot = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t o[8];
+    tmem_ld8(taddr + c * 8, o);
+    ptx::tmem_ld_wait();
+    if (active) {
+      const uint4 w = *reinterpret_cast<const uint4*>(tile + sw64_off(r, c));
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+        dot = fmaf(__uint_as_float(o[2 * e]), f.x, dot);
+        dot = fmaf(__uint_as_float(o[2 * e + 1]), f.y, dot);
+      }
+    }
+  }
+  dot *= sc;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t o[8];
+    tmem_ld8(taddr + c * 8, o);
+    ptx::tmem_ld_wait();
+    if (active) {
+      const uint4 w = *reinterpret_cast<const uint4*>(tile + sw64_off(r, c));
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+        pk[e] = pack_bf16((__uint_as_float(o[2 * e]) * sc - f.x * dot) * invn,
+                          (__uint_as_float(o[2 * e + 1]) * sc - f.y * dot) * invn);
+      }
+      reinterpret_cast<uint4*>(dst)[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
+// per-row constants of a compute thread
+struct RowCtx {
+  int base_i;        // table index base: (yi * TW + xi) + (WS-1) * (TW+1); bias index = base_i - (yj * TW + xj)
+  float lse2, D;     // log-sum-exp in log2 units (+inf: row does not exist -> P = 0), <dO, O>
+  uint32_t by, bx;   // shift-mask bit sets (bit y / x set: keys of that window row / column are masked)
+  bool valid;
+};
+
+// Main unit: one thread = query row (TMEM lane) x NC keys starting at key c0.  Reads S and dP in 4-column steps,
+// writes P and dS (bf16) into the shared-memory panels, accumulates dS (bias gradient, registers) and dS.cos (scale
+// gradient).  `sdp_free` is signalled after the last TMEM read, `pds_free_wait` is called before the first panel
+// write.  The code is unrolled over the NC keys (the sums need compile-time register indices) and therefore kept
+// to ONE copy shared by all key thirds: c0 is a run-time value, a multiple of 8 and -- when ROWALIGNED -- of WS, so
+// that the in-window key coordinates split into a run-time row offset and compile-time parts.  (Instruction fetch,
+// not issue, limited the first version, which had a copy per key range.)
+template <int WS, int NC, bool MASK, bool ROWALIGNED, typename WaitFn>
+__device__ __forceinline__ void bwd_main(uint32_t t_row, uint32_t s_col, uint32_t dp_col, int c0, const RowCtx& rc,
+                                         float scale2, const float* __restrict__ tab, const int* __restrict__ meta,
+                                         unsigned char* Pp, unsigned char* dSp, int row_local, float* acc, float& dsc,
+                                         uint64_t* sdp_free, int lane, WaitFn pds_free_wait) {
+  constexpr int N = WS * WS, TW = 2 * WS - 1;
+  if constexpr (NC > 0) {
+    const int y0 = c0 / WS;                                            // first key row of this range (ROWALIGNED)
+    const float* trow = tab + rc.base_i - (ROWALIGNED ? y0 * TW : 0);
+    const uint32_t by = rc.by >> (ROWALIGNED ? y0 : 0), bx = rc.bx;
+    const float nlse = -rc.lse2, nD = -rc.D;
+    const uint32_t s_base = t_row + s_col + c0, dp_base = t_row + dp_col + c0;
+    const int slot0 = c0 >> 3, r7 = row_local & 7;
+    unsigned char* prow = Pp + row_local * 128;
+    unsigned char* drow = dSp + row_local * 128;
+#pragma unroll
+    for (int cc = 0; cc < NC / 4; ++cc) {
+      uint32_t sv[4], dv[4];
+      tmem_ld4(s_base + cc * 4, sv);
+      tmem_ld4(dp_base + cc * 4, dv);
+      ptx::tmem_ld_wait();
+      if (cc == NC / 4 - 1) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(sdp_free);        // this warp no longer needs S / dP of the unit
+      }
+      uint32_t pk[2], dk[2];
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) {
+        float p2[2], d2[2];
+#pragma unroll
+        for (int e1 = 0; e1 < 2; ++e1) {
+          const int e = e2 * 2 + e1, jj = cc * 4 + e;
+          float bias;
+          bool masked = false, exists = true;
+          if constexpr (ROWALIGNED) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int yj = jj / WS, xj = jj % WS;                       // relative to y0; compile-time
+            bias = trow[-(yj * TW + xj)];
+            if (MASK) masked = (((by >> yj) | (bx >> xj)) & 1u) != 0;
+          } else {
+            const int mj = meta[c0 + jj];                               // koff | yj << 16 | xj << 24
+            bias = trow[-(mj & 0xffff)];
+            if (MASK) masked = (((by >> ((mj >> 16) & 0xff)) | (bx >> (mj >> 24))) & 1u) != 0;
+            exists = c0 + jj < N;
+          }
+          const float cosv = __uint_as_float(sv[e]);
+          float s2 = fmaf(cosv, scale2, bias);
+          if (MASK && masked) s2 += kMaskLog2;
+          float pv = ex2(s2 + nlse);
+          if (!ROWALIGNED && !exists) pv = 0.f;
+          const float dsv = pv * (__uint_as_float(dv[e]) + nD);
+          p2[e1] = pv;
+          d2[e1] = dsv;
+          dsc = fmaf(dsv, cosv, dsc);
+          acc[jj] += dsv;
+        }
+        pk[e2] = pack_bf16(p2[0], p2[1]);
+        dk[e2] = pack_bf16(d2[0], d2[1]);
+      }
+      if (cc == 0) pds_free_wait();
+      const int slot = slot0 + (cc >> 1);                               // 16-byte slot of keys [8 slot, 8 slot + 8)
+      const uint32_t off = (uint32_t)((slot >> 3) * kPanel + (((slot & 7) ^ r7) << 4) + (cc & 1) * 8);
+      *reinterpret_cast<uint2*>(prow + off) = make_uint2(pk[0], pk[1]);
+      *reinterpret_cast<uint2*>(drow + off) = make_uint2(dk[0], dk[1]);
+    }
+  }
+}
+
+// Tail unit (quarter-0 warps only): 16 query rows x keys [c0, c0 + nc) spread over the 32 lanes with the 16x256b
+// shape: thread t owns rows t/4 and t/4 + 8 and the column pairs 2 (t % 4) of every 8-column group.  A rolled loop
+// (its bias-gradient sums live in shared memory, nothing needs a compile-time index).
+template <int WS, typename WaitFn>
+__device__ __forceinline__ void bwd_tail(uint32_t t_q0, uint32_t s_col, uint32_t dp_col, int c0, int nc, const RowCtx (&rc)[2],
+                                         float scale2, bool need_mask, const float* __restrict__ tab,
+                                         const int* __restrict__ meta, unsigned char* Pp, unsigned char* dSp, float* tacc,
+                                         float& dsc, uint64_t* sdp_free, int lane, WaitFn pds_free_wait) {
+  constexpr int N = WS * WS, NPAD = (N + 15) / 16 * 16;
+  const int rho[2] = {lane >> 2, (lane >> 2) + 8};
+  const int ngroups = nc >> 3;
+#pragma unroll 1
+  for (int gq = 0; gq < ngroups; ++gq) {
+    const int j = c0 + gq * 8 + 2 * (lane & 3);             // this thread's column pair (j, j + 1)
+    uint32_t sv[4], dv[4];
+    tmem_ld_16x256b(t_q0 + s_col + c0 + gq * 8, sv);
+    tmem_ld_16x256b(t_q0 + dp_col + c0 + gq * 8, dv);
+    ptx::tmem_ld_wait();
+    if (gq == ngroups - 1) {
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(sdp_free);
+    }
+    if (gq == 0) pds_free_wait();
+    const int m0 = meta[j], m1 = meta[j + 1];               // koff | yj << 16 | xj << 24
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      float p[2], ds[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int mj = e ? m1 : m0;
+        const float cosv = __uint_as_float(sv[rr * 2 + e]);
+        float s2 = fmaf(cosv, scale2, tab[rc[rr].base_i - (mj & 0xffff)]);
+        if (need_mask && (((rc[rr].by >> ((mj >> 16) & 0xff)) | (rc[rr].bx >> (mj >> 24))) & 1u)) s2 += kMaskLog2;
+        float pv = ex2(s2 - rc[rr].lse2);
+        float dsv = pv * (__uint_as_float(dv[rr * 2 + e]) - rc[rr].D);
+        if (j + e >= N) { pv = 0.f; dsv = 0.f; }
+        p[e] = pv;
+        ds[e] = dsv;
+        dsc = fmaf(dsv, cosv, dsc);
+      }
+      const int r = rho[rr];
+      const uint32_t off = (uint32_t)((j >> 6) * kPanel + r * 128 + ((((j & 63) >> 3) ^ (r & 7)) << 4) + (j & 7) * 2);
+      *reinterpret_cast<uint32_t*>(Pp + off) = pack_bf16(p[0], p[1]);
+      *reinterpret_cast<uint32_t*>(dSp + off) = pack_bf16(ds[0], ds[1]);
+      float2* ta = reinterpret_cast<float2*>(tacc + r * NPAD + j);
+      float2 t = *ta;
+      t.x += ds[0];
+      t.y += ds[1];
+      *ta = t;
+    }
+  }
+}
+
+template <int WS>
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
+  using CF = Cfg<WS>;
+  constexpr int N = CF::N, NPAD = CF::NPAD, MT = CF::MT, NSTAGE = CF::NSTAGE, TW = CF::TW;
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t kv_full[NSTAGE], kv_empty[NSTAGE];
+  __shared__ __align__(8) uint64_t sdp_full, sdp_free, pds_full, pds_free, dq_full[2], dq_free[2], dkv_full, dkv_free;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float red_s[kComputeWarps];
+
+  const WinGeom& g = a.g;
+  const uint32_t base_u32 = (ptx::smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* sm = smem_dyn + (base_u32 - ptx::smem_u32(smem_dyn));
+  unsigned char* Pp = sm;                                           // panels first: 1024-byte aligned
+  unsigned char* dSp = Pp + CF::kPBytes;
+  unsigned char* ring = dSp + CF::kPBytes;
+  float* tab = reinterpret_cast<float*>(ring + (size_t)NSTAGE * CF::kStage);
+  float* dtab = tab + CF::NTAB;
+  int* meta = reinterpret_cast<int*>(dtab + CF::NTAB);             // [NPAD] koff | yj << 16 | xj << 24
+  float* tacc = reinterpret_cast<float*>(meta + NPAD);             // [16][NPAD] (MT > 1 only)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef B200SWIN_TRACE
+  int trc_ = 0;
+#endif
+  const int64_t per = a.nitems / gridDim.x, rem = a.nitems % gridDim.x;
+  const int64_t g0 = (int64_t)blockIdx.x * per + min((int64_t)blockIdx.x, rem);
+  const int n = (int)(per + ((int64_t)blockIdx.x < rem ? 1 : 0));
+  const int nW = g.nWh * g.nWw;
+
+  // zero the panels once (rows / keys that no thread ever writes must be finite) and the static tables
+  for (int i = threadIdx.x; i < (int)(2 * CF::kPBytes / 16); i += kThreads) reinterpret_cast<uint4*>(Pp)[i] = make_uint4(0, 0, 0, 0);
+  for (int j = threadIdx.x; j < NPAD; j += kThreads) {
+    const int yj = j / WS, xj = j % WS;
+    meta[j] = j < N ? ((yj * TW + xj) | (yj << 16) | (xj << 24)) : 0;
+  }
+  if (MT > 1) for (int i = threadIdx.x; i < 16 * NPAD; i += kThreads) tacc[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&kv_full[s], kLoaders); ptx::mbar_init(&kv_empty[s], 1 + kComputeWarps); }
+    ptx::mbar_init(&sdp_full, 1);
+    ptx::mbar_init(&sdp_free, kComputeWarps);
+    ptx::mbar_init(&pds_full, kComputeWarps);
+    ptx::mbar_init(&pds_free, 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&dq_full[i], 1); ptx::mbar_init(&dq_free[i], 4); }
+    ptx::mbar_init(&dkv_full, 1);
+    ptx::mbar_init(&dkv_free, kComputeWarps);
+    ptx::fence_mbar_init();
+  }
+  if (warp == kIssuerWarp) {
+    ptx::tmem_alloc(&tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp >= kComputeWarps) {
+    reg_dec<kRegService>();
+    if (warp == kIssuerWarp) {
+      // =================================================================================== MMA issuer
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, NPAD, 0, 0);
+        constexpr uint32_t idesc_dq = ptx::make_idesc_bf16(128, HD, 0, 1);    // A = dS (K-major), B = K MN-major
+        constexpr uint32_t idesc_t = ptx::make_idesc_bf16(128, HD, 1, 1);     // A = P^T / dS^T (MN-major), B MN-major
+        constexpr uint32_t idesc_t64 = ptx::make_idesc_bf16(64, HD, 1, 1);    // keys 128.. (M = 64)
+        const uint64_t desc_k64 = ptx::make_smem_desc(0, 16, 512, kSw64);      // K-major 64 B rows (Q, dO, K, V)
+        const uint64_t desc_mn64 = ptx::make_smem_desc(0, 512, 512, kSw64);    // the same tiles read MN-major
+        const uint64_t desc_pk = ptx::make_smem_desc(0, 16, 1024, 2);          // panel, K-major (dQ)
+        const uint64_t desc_pmn = ptx::make_smem_desc(0, kPanel, 1024, 2);     // panel, MN-major (dV, dK)
+        const uint32_t p_s = ptx::smem_u32(Pp), ds_s = ptx::smem_u32(dSp), ring_s = ptx::smem_u32(ring);
+        const int U = n * MT;
+        auto issue_b = [&](int v) {
+          const int il = v / MT, tile = v - il * MT, stage = il % NSTAGE;
+          const int rows_valid = (MT > 1 && tile == MT - 1) ? CF::TAIL : (N < 128 ? N : 128);
+          const uint32_t q_s = ring_s + (uint32_t)stage * CF::kStage, g_s = q_s + CF::kRow, k_s = g_s + CF::kRow;
+          const int qb = v & 1;
+          TR(14, v);
+          ptx::mbar_wait(&pds_full, v & 1);
+          TR(15, v);
+          ptx::mbar_wait(&dq_free[qb], ((v >> 1) & 1) ^ 1);
+          if (tile == 0) ptx::mbar_wait(&dkv_free, (il & 1) ^ 1);
+          ptx::tc_fence_after();
+          // dQ_t = dS K
+#pragma unroll
+          for (int ks = 0; ks < NPAD / 16; ++ks)
+            ptx::mma_bf16_ss(tmem_base + CF::DQ_COL + qb * 32, desc_pk + ((ds_s + (ks >> 2) * kPanel + (ks & 3) * 32) >> 4),
+                             desc_mn64 + ((k_s + ks * 1024) >> 4), idesc_dq, ks);
+          ptx::mma_commit(&dq_full[qb]);
+          // dV += P^T dO_t,  dK += dS^T Q_t   (contraction over the query rows of this tile)
+          const int ksteps = (rows_valid + 15) / 16;
+#pragma unroll 1
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t accf = (tile | ks) != 0 ? 1u : 0u;
+            const uint64_t bg = desc_mn64 + ((g_s + (tile * 128 + ks * 16) * 64) >> 4);
+            const uint64_t bq = desc_mn64 + ((q_s + (tile * 128 + ks * 16) * 64) >> 4);
+            ptx::mma_bf16_ss(tmem_base + CF::DV_COL, desc_pmn + ((p_s + ks * 2048) >> 4), bg, idesc_t, accf);
+            ptx::mma_bf16_ss(tmem_base + CF::DK_COL, desc_pmn + ((ds_s + ks * 2048) >> 4), bq, idesc_t, accf);
+            if (NPAD > 128) {
+              ptx::mma_bf16_ss(tmem_base + CF::DVT_COL, desc_pmn + ((p_s + 2 * kPanel + ks * 2048) >> 4), bg, idesc_t64, accf);
+              ptx::mma_bf16_ss(tmem_base + CF::DKT_COL, desc_pmn + ((ds_s + 2 * kPanel + ks * 2048) >> 4), bq, idesc_t64, accf);
+            }
+          }
+          ptx::mma_commit(&pds_free);                       // panels may be overwritten
+          TR(16, v);
+          if (tile == MT - 1) {
+            ptx::mma_commit(&dkv_full);
+            ptx::mma_commit(&kv_empty[stage]);
+          }
+        };
+        for (int u = 0; u < U; ++u) {
+          const int il = u / MT, tile = u - il * MT, stage = il % NSTAGE;
+          TR(10, u);
+          if (tile == 0) ptx::mbar_wait(&kv_full[stage], (il / NSTAGE) & 1);
+          TR(11, u);
+          ptx::mbar_wait(&sdp_free, (u & 1) ^ 1);
+          TR(12, u);
+          ptx::tc_fence_after();
+          const uint32_t q_s = ring_s + (uint32_t)stage * CF::kStage, g_s = q_s + CF::kRow, k_s = g_s + CF::kRow,
+                         v_s = k_s + CF::kRow;
+          const uint64_t aq = desc_k64 + ((q_s + tile * 8192) >> 4), ag = desc_k64 + ((g_s + tile * 8192) >> 4);
+          const uint64_t bk = desc_k64 + (k_s >> 4), bv = desc_k64 + (v_s >> 4);
+          ptx::mma_bf16_ss(tmem_base + CF::S_COL, aq, bk, idesc_s, 0u);
+          ptx::mma_bf16_ss(tmem_base + CF::S_COL, aq + 2, bk + 2, idesc_s, 1u);
+          ptx::mma_bf16_ss(tmem_base + CF::DP_COL, ag, bv, idesc_s, 0u);
+          ptx::mma_bf16_ss(tmem_base + CF::DP_COL, ag + 2, bv + 2, idesc_s, 1u);
+          ptx::mma_commit(&sdp_full);
+          TR(13, u);
+          if (u > 0) issue_b(u - 1);
+        }
+        if (U > 0) issue_b(U - 1);
+      }
+    } else {
+      // =================================================================================== gather warps
+      const int lt = threadIdx.x - kCompute;
+      const int C3 = 3 * a.C;
+      int pending = 0;
+      for (int i = 0; i < n; ++i) {
+        const int stage = i % NSTAGE;
+        const uint32_t par = ((i / NSTAGE) & 1) ^ 1;
+        if (!ptx::mbar_test_wait(&kv_empty[stage], par)) {
+          if (pending) {
+            ptx::cp_async_wait<0>();
+            ptx::fence_proxy_async_smem();
+            for (int k = i - pending; k < i; ++k) ptx::mbar_arrive(&kv_full[k % NSTAGE]);
+            pending = 0;
+          }
+          TR(20, i);
+          ptx::mbar_wait(&kv_empty[stage], par);
+        }
+        TR(21, i);
+        const int64_t gi = g0 + i;
+        const int h = (int)(gi / a.nwin);
+        const int64_t win = gi - (int64_t)h * a.nwin;
+        const int b = (int)(win / nW);
+        const int w = (int)(win - (int64_t)b * nW);
+        const int wh = w / g.nWw, ww = w - wh * g.nWw;
+        unsigned char* st = ring + (size_t)stage * CF::kStage;
+        const uint32_t q_s = ptx::smem_u32(st), g_s = q_s + CF::kRow, k_s = g_s + CF::kRow, v_s = k_s + CF::kRow;
+        const uint32_t lse_s = v_s + CF::kRow, d_s = lse_s + NPAD * 4;
+        float* lse_p = reinterpret_cast<float*>(st + 4 * CF::kRow);
+        float* d_p = lse_p + NPAD;
+        for (int idx = lt; idx < NPAD * 4; idx += kLoaders) {
+          const int r = idx >> 2, c = idx & 3;
+          const int t = r < N ? src_token(g, b, wh, ww, r / WS, r % WS) : -2;
+          const uint32_t off = sw64_off(r, c);
+          if (t >= 0) {
+            const __nv_bfloat16* src = a.qkv + (int64_t)t * C3 + h * HD + c * 8;
+            ptx::cp_async_16(q_s + off, src);
+            ptx::cp_async_16(k_s + off, src + a.C);
+            ptx::cp_async_16(v_s + off, src + 2 * a.C);
+            ptx::cp_async_16(g_s + off, a.dout + (int64_t)t * a.C + h * HD + c * 8);
+            if (c == 0) cp_async_4(d_s + r * 4, a.dvec + (int64_t)t * a.nH + h);
+          } else {
+            // pad token: q = normalised q_bias, k = 0, v = v_bias, dO = 0 (cropped row); key padding rows: all zero
+            uint4 qv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+            if (t == -1) {
+              if (a.qpad) {
+                const float* p = a.qpad + h * HD + c * 8;
+                qv = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+              }
+              if (a.vpad) {
+                const float* p = a.vpad + h * HD + c * 8;
+                vv = make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7]));
+              }
+            }
+            *reinterpret_cast<uint4*>(st + off) = qv;
+            *reinterpret_cast<uint4*>(st + CF::kRow + off) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(st + 2 * CF::kRow + off) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(st + 3 * CF::kRow + off) = vv;
+            if (c == 0) d_p[r] = 0.f;
+          }
+          if (c == 1) {
+            // log-sum-exp of the row, in log2 units at use; rows beyond the window: +inf (P = 0)
+            if (r < N) cp_async_4(lse_s + r * 4, a.lse + (win * a.nH + h) * N + r);
+            else lse_p[r] = INFINITY;
+          }
+        }
+        ptx::cp_async_commit();
+        TR(22, i);
+        if (++pending > LAG) {
+          ptx::cp_async_wait<LAG>();
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&kv_full[(i - LAG) % NSTAGE]);
+          --pending;
+        }
+      }
+      if (pending) {
+        ptx::cp_async_wait<0>();
+        ptx::fence_proxy_async_smem();
+        for (int k = n - pending; k < n; ++k) ptx::mbar_arrive(&kv_full[k % NSTAGE]);
+      }
+    }
+  } else {
+    // ===================================================================================== compute warps
+    reg_inc<kRegCompute>();
+    const int q = warp & 3, kq = warp >> 2;
+    const int row_local = q * 32 + lane;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    float acc[CF::NCMAX];
+#pragma unroll
+    for (int c = 0; c < CF::NCMAX; ++c) acc[c] = 0.f;
+    float dsc = 0.f;
+    int cur_head = -1;
+    float sc = 0.f, scale2 = 0.f;
+
+    // flush of the per-thread / per-CTA sums of one head into global memory
+    auto flush_head = [&](int h) {
+      // register sums of the main rows -> smem table space
+      {
+        const int r = row_local;
+        if (r < N) {
+          const int base_i = ((r / WS) * TW + (r % WS)) + (WS - 1) * (TW + 1);
+          const int c0 = kq == 0 ? CF::K0 : kq == 1 ? CF::K1 : CF::K2;
+          const int c1 = kq == 0 ? CF::K1 : kq == 1 ? CF::K2 : CF::K3;
+#pragma unroll
+          for (int c = 0; c < CF::NCMAX; ++c) {
+            const int j = c0 + c;
+            if (j < c1 && j < N) atomicAdd(dtab + base_i - ((j / WS) * TW + (j % WS)), acc[c]);
+            acc[c] = 0.f;
+          }
+        }
+      }
+      dsc = warp_sum(dsc);
+      if (lane == 0) red_s[warp] = dsc;
+      dsc = 0.f;
+      named_bar_sync(1, kCompute);
+      if (MT > 1) {
+        for (int e = threadIdx.x; e < CF::TAIL * N; e += kCompute) {
+          const int rr = e / N, j = e - rr * N, r = 128 + rr;
+          const float v = tacc[rr * NPAD + j];
+          tacc[rr * NPAD + j] = 0.f;
+          if (v != 0.f)
+            atomicAdd(dtab + ((r / WS) * TW + (r % WS)) + (WS - 1) * (TW + 1) - ((j / WS) * TW + (j % WS)), v);
+        }
+        named_bar_sync(1, kCompute);
+      }
+      for (int r = threadIdx.x; r < CF::NTAB; r += kCompute) {
+        const float v = dtab[r];
+        dtab[r] = 0.f;
+        if (v != 0.f) atomicAdd(a.dtable16 + r * a.nH + h, v);
+      }
+      if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < kComputeWarps; ++w) s += red_s[w];
+        atomicAdd(a.dscale + h, s);
+      }
+      named_bar_sync(1, kCompute);
+    };
+
+    // deferred epilogues (run after the compute of the NEXT unit, when their MMAs have long retired)
+    // (only the unit index is carried; everything else is recomputed -- registers are the scarce resource here)
+    struct Pend { int u, il, tile, stage, h, b, wh, ww; float sc; bool item_end; };
+    int pend_u = -1;
+    auto run_epilogue = [&](int pu) {
+      Pend pe;
+      pe.u = pu;
+      pe.il = pu / MT;
+      pe.tile = pu - pe.il * MT;
+      pe.stage = pe.il % NSTAGE;
+      pe.item_end = pe.tile == MT - 1;
+      {
+        const int64_t gi = g0 + pe.il;
+        pe.h = (int)(gi / a.nwin);
+        const int64_t win = gi - (int64_t)pe.h * a.nwin;
+        pe.b = (int)(win / nW);
+        const int w = (int)(win - (int64_t)pe.b * nW);
+        pe.wh = w / g.nWw;
+        pe.ww = w - pe.wh * g.nWw;
+        pe.sc = a.scale[pe.h];
+      }
+      unsigned char* st = ring + (size_t)pe.stage * CF::kStage;
+      // ---- dQ rows of unit pe.u (warps of key third 0; one row per lane)
+      if (kq == 0) {
+        const int qb = pe.u & 1;
+        const bool tail = MT > 1 && pe.tile == MT - 1;
+        const int r = tail ? ((q == 0 && lane < CF::TAIL) ? 128 + lane : -1) : (row_local < N ? row_local : -1);
+        ptx::mbar_wait(&dq_full[qb], (pe.u >> 1) & 1);
+        ptx::tc_fence_after();
+        if (__any_sync(0xffffffffu, r >= 0)) {
+          const int t = r >= 0 ? src_token(g, pe.b, pe.wh, pe.ww, r / WS, r % WS) : -1;
+          const float invn = t >= 0 ? a.inv_norm[((int64_t)t * 2 + 0) * a.nH + pe.h] : 0.f;
+          normalize_bwd_store(t_row + CF::DQ_COL + qb * 32, st, r >= 0 ? r : 0, pe.sc, invn,
+                              a.dqkv + (int64_t)(t >= 0 ? t : 0) * 3 * a.C + pe.h * HD, t >= 0);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&dq_free[qb]);
+      }
+      if (!pe.item_end) return;
+      // ---- dK (key third 1) / dV (key third 2) rows: keys 0..127 one per lane, then (quarter 0 only) the tail keys
+      if (kq >= 1) {
+        ptx::mbar_wait(&dkv_full, pe.il & 1);
+        ptx::tc_fence_after();
+      }
+#pragma unroll 1
+      for (int part = 0; part < (MT > 1 ? 2 : 1); ++part) {
+        const bool tail_kv = part == 1;
+        if (kq == 0 || (tail_kv && q != 0)) break;
+        const int j = tail_kv ? 128 + lane : row_local;
+        const bool jvalid = j < N && (!tail_kv || lane < 16);
+        const int t = jvalid ? src_token(g, pe.b, pe.wh, pe.ww, j / WS, j % WS) : -2;
+        if (kq == 1) {
+          const float invn = t >= 0 ? a.inv_norm[((int64_t)t * 2 + 1) * a.nH + pe.h] : 0.f;
+          normalize_bwd_store(t_row + (tail_kv ? CF::DKT_COL : CF::DK_COL), st + 2 * CF::kRow, jvalid ? j : 0, pe.sc, invn,
+                              a.dqkv + (int64_t)(t >= 0 ? t : 0) * 3 * a.C + pe.h * HD + a.C, t >= 0);
+        } else {
+          // pad tokens carry v = v_bias: their dV rows belong to v_bias (reduced over the warp; one atomic per channel
+          // straight to the head's slot -- this epilogue runs after the sums of the NEXT unit, possibly of the next head)
+          const bool is_pad = t == -1;
+          const bool any_pad = __any_sync(0xffffffffu, is_pad);
+          uint4* d4 = reinterpret_cast<uint4*>(a.dqkv + (int64_t)(t >= 0 ? t : 0) * 3 * a.C + pe.h * HD + 2 * a.C);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t ov[8];
+            tmem_ld8(t_row + (tail_kv ? CF::DVT_COL : CF::DV_COL) + c * 8, ov);
+            ptx::tmem_ld_wait();
+            if (t >= 0)
+              d4[c] = make_uint4(pack_bf16(__uint_as_float(ov[0]), __uint_as_float(ov[1])),
+                                 pack_bf16(__uint_as_float(ov[2]), __uint_as_float(ov[3])),
+                                 pack_bf16(__uint_as_float(ov[4]), __uint_as_float(ov[5])),
+                                 pack_bf16(__uint_as_float(ov[6]), __uint_as_float(ov[7])));
+            if (any_pad) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float v = warp_sum(is_pad ? __uint_as_float(ov[e]) : 0.f);
+                if (lane == 0 && a.dvpad) atomicAdd(a.dvpad + pe.h * HD + c * 8 + e, v);
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&dkv_free);
+        ptx::mbar_arrive(&kv_empty[pe.stage]);       // this warp is done with the item's operand tiles
+      }
+    };
+
+    // One flat loop over the units plus a drain step, so that flush_head and run_epilogue each have exactly ONE call
+    // site: they are inlined and the long-lived sums stay in registers (a real call would force them to the stack).
+    const int U = n * MT;
+    int h = -1;
+    bool need_mask = false, last_h = false, last_w = false;
+#pragma unroll 1
+    for (int u = 0; u <= U; ++u) {
+      const bool has = u < U;
+      const int il = u / MT, tile = u - il * MT;
+      const int stage = il % NSTAGE;
+      if (tile == 0) {
+        // new item (or the drain step): geometry, and a head change flushes the sums of the previous head
+        const int64_t gi = g0 + il;
+        h = has ? (int)(gi / a.nwin) : -1;
+        if (h != cur_head) {
+          named_bar_sync(1, kCompute);                 // every warp has finished accumulating for the old head
+          if (cur_head >= 0) flush_head(cur_head);
+          if (h >= 0) {
+            for (int t = threadIdx.x; t < CF::NTAB; t += kCompute) { tab[t] = a.table16[t * a.nH + h] * kLog2e; dtab[t] = 0.f; }
+            sc = a.scale[h];
+            scale2 = sc * kLog2e;
+          }
+          named_bar_sync(1, kCompute);
+          cur_head = h;
+        }
+        if (has) {
+          const int64_t win = gi - (int64_t)h * a.nwin;
+          const int w = (int)(win % nW);
+          const int wh = w / g.nWw, ww = w - wh * g.nWw;
+          last_h = wh == g.nWh - 1;
+          last_w = ww == g.nWw - 1;
+          need_mask = g.shift > 0 && (last_h || last_w);
+        }
+      }
+      if (has) {
+        const float* lse_p = reinterpret_cast<const float*>(ring + (size_t)stage * CF::kStage + 4 * CF::kRow);
+        const float* d_p = lse_p + NPAD;
+        const int cut = WS - g.shift;
+        const uint32_t hi = (~0u << cut) & ((1u << WS) - 1u), lo = (1u << cut) - 1u;
+        auto make_row = [&](int r, RowCtx& rc) {
+          rc.valid = r >= 0 && r < N;
+          const int rr = rc.valid ? r : 0;
+          const int yi = rr / WS, xi = rr - yi * WS;
+          rc.base_i = (yi * TW + xi) + (WS - 1) * (TW + 1);
+          rc.lse2 = rc.valid ? lse_p[rr] * kLog2e : INFINITY;
+          rc.D = rc.valid ? d_p[rr] : 0.f;
+          rc.by = (need_mask && last_h) ? (yi >= cut ? lo : hi) : 0u;
+          rc.bx = (need_mask && last_w) ? (xi >= cut ? lo : hi) : 0u;
+        };
+        TR(30, u);
+        ptx::mbar_wait(&sdp_full, u & 1);          // implies the item's operand tiles (lse, D) have landed
+        TR(31, u);
+        ptx::tc_fence_after();
+        auto wait_pds = [&]() { TR(35, u); ptx::mbar_wait(&pds_free, (u & 1) ^ 1); TR(36, u); };
+        const int nc = kq == 0 ? CF::K1 - CF::K0 : kq == 1 ? CF::K2 - CF::K1 : CF::K3 - CF::K2;
+        bool arrived = false;
+        if (tile == 0) {
+          // rows that the transposed MMAs read as contraction index must be written (zeros where no row exists)
+          const int rows_needed = ((N < 128 ? N : 128) + 15) / 16 * 16;
+          if (q * 32 < rows_needed) {
+            RowCtx rc;
+            make_row(row_local, rc);
+            if constexpr (CF::UNIFIED) {
+              // equal key thirds that start on a window row: one copy of the unrolled code for all of them
+              constexpr int NC = CF::K1 - CF::K0;
+              const int c0 = kq * NC;
+              if (need_mask) bwd_main<WS, NC, true, true>(t_row, CF::S_COL, CF::DP_COL, c0, rc, scale2, tab, meta, Pp, dSp, row_local, acc, dsc, &sdp_free, lane, wait_pds);
+              else bwd_main<WS, NC, false, true>(t_row, CF::S_COL, CF::DP_COL, c0, rc, scale2, tab, meta, Pp, dSp, row_local, acc, dsc, &sdp_free, lane, wait_pds);
+            } else {
+              // small windows: a few keys per thread, one (mask-capable) copy per key third
+              if (kq == 0) bwd_main<WS, CF::K1 - CF::K0, true, false>(t_row, CF::S_COL, CF::DP_COL, CF::K0, rc, scale2, tab, meta, Pp, dSp, row_local, acc, dsc, &sdp_free, lane, wait_pds);
+              else if (kq == 1) bwd_main<WS, CF::K2 - CF::K1, true, false>(t_row, CF::S_COL, CF::DP_COL, CF::K1, rc, scale2, tab, meta, Pp, dSp, row_local, acc, dsc, &sdp_free, lane, wait_pds);
+              else bwd_main<WS, CF::K3 - CF::K2, true, false>(t_row, CF::S_COL, CF::DP_COL, CF::K2, rc, scale2, tab, meta, Pp, dSp, row_local, acc, dsc, &sdp_free, lane, wait_pds);
+            }
+            arrived = nc > 0;
+          }
+        } else if (q == 0) {
+          RowCtx rc2[2];
+          make_row(128 + (lane >> 2), rc2[0]);
+          make_row(128 + (lane >> 2) + 8, rc2[1]);
+          const int c0 = kq == 0 ? CF::K0 : kq == 1 ? CF::K1 : CF::K2;
+          if (nc > 0) bwd_tail<WS>(t_row, CF::S_COL, CF::DP_COL, c0, nc, rc2, scale2, need_mask, tab, meta, Pp, dSp, tacc, dsc, &sdp_free, lane, wait_pds);
+          arrived = nc > 0;
+        }
+        if (!arrived) {
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&sdp_free);
+        }
+        ptx::fence_proxy_async_smem();             // panel writes -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&pds_full);
+        TR(32, u);
+      }
+      // epilogues of the previous unit (its MMAs were issued right after this unit's S / dP)
+      if (pend_u >= 0) run_epilogue(pend_u);
+      TR(33, u);
+      pend_u = has ? u : -1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kIssuerWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// D[t, h] = <dO[t, h, :], O[t, h, :]>  (one thread per (token, head); 2 x 64 B in, 4 B out)
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out, float* __restrict__ dvec,
+                     int64_t n /* tokens * heads */) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4* g4 = reinterpret_cast<const uint4*>(dout + i * HD);
+    const uint4* o4 = reinterpret_cast<const uint4*>(out + i * HD);
+    float d = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 gv = g4[c], ov = o4[c];
+      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
+        const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[e]));
+        d = fmaf(gf.x, of.x, d);
+        d = fmaf(gf.y, of.y, d);
+      }
+    }
+    dvec[i] = d;
+  }
+}
+
+template <int WS>
+int launch_bw(const BwArgs& a, cudaStream_t st) {
+  using CF = Cfg<WS>;
+  static_assert(CF::kSmem <= 227 * 1024, "shared memory budget");
+  BSW_CUDA(cudaFuncSetAttribute(attn_bwd_ws_kernel<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::kSmem));
+  int64_t grid = sm_count();
+  if (grid > a.nitems) grid = a.nitems;
+#ifdef B200SWIN_TRACE
+  BwArgs at = a;
+  const char* tpath = getenv("B200SWIN_ATTN_TRACE_BWD");
+  const size_t tbytes = (1 + 4 * 60000) * sizeof(long long);
+  if (tpath) {
+    BSW_CUDA(cudaMalloc(&at.trace, tbytes));
+    BSW_CUDA(cudaMemsetAsync(at.trace, 0, tbytes, st));
+  }
+  attn_bwd_ws_kernel<WS><<<(unsigned)grid, kThreads, CF::kSmem, st>>>(at);
+  BSW_LAUNCH_CHECK();
+  if (tpath) {
+    std::vector<long long> hbuf(1 + 4 * 60000);
+    BSW_CUDA(cudaStreamSynchronize(st));
+    BSW_CUDA(cudaMemcpy(hbuf.data(), at.trace, tbytes, cudaMemcpyDeviceToHost));
+    BSW_CUDA(cudaFree(at.trace));
+    FILE* f = fopen(tpath, "w");
+    if (f) {
+      for (long long k = 0; k < 60000; ++k)
+        if (hbuf[4 + 4 * k] != 0) fprintf(f, "%lld %lld %lld %lld\n", hbuf[1 + 4 * k], hbuf[2 + 4 * k], hbuf[3 + 4 * k], hbuf[4 + 4 * k]);
+      fclose(f);
+    }
+  }
+  return B200SWIN_OK;
+#else
+  attn_bwd_ws_kernel<WS><<<(unsigned)grid, kThreads, CF::kSmem, st>>>(a);
+  BSW_LAUNCH_CHECK();
+  return B200SWIN_OK;
+#endif
+}
+}  // namespace
+
+bool attn_bwd_ws_supported(int ws) { return ws == 4 || ws == 6 || ws == 7 || ws == 8 || ws == 12; }
+
+size_t attn_bwd_ws_workspace_bytes(int B, int H, int W, int nH) { return (size_t)B * H * W * nH * sizeof(float); }
+
+int attn_bwd_ws(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
+                const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
+                float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH, int ws,
+                int shift, cudaStream_t st) {
+  BSW_REQUIRE(workspace, "attn_bwd(ws): workspace for D = <dO, O> missing");
+  BwArgs a;
+  a.qkv = (const __nv_bfloat16*)qkv; a.dout = (const __nv_bfloat16*)dout; a.lse = lse;
+  a.dvec = (const float*)workspace; a.inv_norm = inv_norm; a.table16 = table16; a.scale = scale; a.qpad = qpad;
+  a.vpad = vpad; a.dqkv = (__nv_bfloat16*)dqkv; a.dtable16 = dtable16; a.dscale = dscale; a.dvpad = dvpad;
+  make_geom(&a.g, B, H, W, ws, shift);
+  a.C = C; a.nH = nH;
+  a.nwin = (int64_t)B * a.g.nWh * a.g.nWw;
+  a.nitems = a.nwin * nH;
+  a.trace = nullptr;
+  {
+    const int64_t n = (int64_t)B * H * W * nH;
+    int64_t blocks = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
+    attn_bwd_prep_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(
+        (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (float*)workspace, n);
+    BSW_LAUNCH_CHECK();
+  }
+  switch (ws) {
+    case 4: return launch_bw<4>(a, st);
+    case 6: return launch_bw<6>(a, st);
+    case 7: return launch_bw<7>(a, st);
+    case 8: return launch_bw<8>(a, st);
+    case 12: return launch_bw<12>(a, st);
+    default: break;
+  }
+  set_error("attn_bwd(ws): window %dx%d not instantiated", ws, ws);
+  return B200SWIN_EINVAL;
+}
+
+}  // namespace b200swin

@@ -9,11 +9,15 @@
 //   warp 0      one thread issues tcgen05.mma:  S = Q K^T into one of up to four TMEM slots,  O = P V (P read
 //               from TMEM) -- scheduled by polling mbarriers, so S of the next items is in flight while the
 //               softmax warps work;
-//   warps 4-11  two softmax warpgroups on alternating items, one thread per query row: the whole fp32 row
-//               of S lives in registers (setmaxnreg), bias comes from a per-head [N][N] fp32 matrix in shared
-//               memory (conflict-free float4 reads), the shift mask from per-thread bit masks (only windows on
-//               the last window row / column pay for it), exp2 on the SFU, P written back to TMEM as packed bf16
-//               over the S columns, O scaled by 1/rowsum and stored to the natural [B,H,W,C] layout.
+//   warps 4-19  softmax: two unit groups on alternating items; inside a group every query row is owned by TWO
+//               threads (warp pair sharing a TMEM lane quarter), one per half of the keys.  Each half keeps its
+//               part of the fp32 S row in registers, adds the bias from a per-head [N][N] fp32 matrix in shared
+//               memory (conflict-free float4 reads), applies the shift mask from per-thread bit masks (only
+//               windows on the last window row / column pay for it), takes its OWN maximum and sum, and writes
+//               P = exp2(s - m_half) back to TMEM as packed bf16 over the S columns.  The two halves feed two
+//               accumulators O_a, O_b (split-K flash-attention style); the second-half thread combines them as
+//               (O_a 2^(m_a-m) + O_b 2^(m_b-m)) / (l_a 2^(m_a-m) + l_b 2^(m_b-m)) and stores the natural
+//               [B,H,W,C] layout.  No thread ever waits for the other half's maximum.
 //
 // A 12x12 window has 144 = 128 + 16 rows.  The 16-row tail is a second M=128 MMA whose A operand starts
 // 32*rot rows early, so the tail lands in TMEM lane quarter `rot` -- rot rotates per item and the extra softmax
@@ -21,6 +25,8 @@
 //
 // Items are ordered head-major and every CTA owns one contiguous range, so the expanded bias matrix is rebuilt
 // only when the head changes (at most a few times per CTA).
+#include <stdlib.h>
+#include <vector>
 #include "common.cuh"
 #include "wingeom.cuh"
 #include "tc_ptx.cuh"
@@ -30,8 +36,15 @@ namespace b200swin {
 
 namespace {
 constexpr int HD = 32;
-constexpr int kThreads = 384;
+// Warps 0-15: softmax; warps 16-18: gather; warp 19: MMA issuer.  The warp scheduler favours the highest warp id
+// of a sub-partition, so the latency-critical (but nearly idle) issuer and gather warps sit ABOVE the softmax warps:
+// as warp 0 the issuer was starved of issue slots and every MMA hand-off took ~500 cycles.
+constexpr int kThreads = 640;
+constexpr int kIssuerWarp = 19;
+constexpr int kSoftmax = 512;
 constexpr int kLoaders = 96;
+// register budget: 640 threads x 96 at launch = 61440 = 128 x kRegService + 512 x kRegSoftmax
+constexpr int kRegService = 64, kRegSoftmax = 104;
 constexpr int NSTAGE = 4, LAG = 2;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -50,7 +63,22 @@ struct WsArgs {
   int C, nH;
   int64_t nwin;       // B * nWh * nWw
   int64_t nitems;     // nH * nwin, item = head * nwin + win
+  long long* trace;   // debug builds (-DB200SWIN_TRACE): [0] = event count, then (event, warp, index, clock) records
 };
+
+#ifdef B200SWIN_TRACE
+// per-warp private event log (no atomics: a returning global atomic costs ~500 cycles and hides what it measures)
+#define TR(ev, idx)                                                                           \
+  do {                                                                                        \
+    if (a.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trc_ < 3000) {               \
+      long long* e_ = a.trace + 1 + 4 * ((threadIdx.x >> 5) * 3000 + trc_);                   \
+      e_[0] = (ev); e_[1] = threadIdx.x >> 5; e_[2] = (idx); e_[3] = clock64();               \
+      ++trc_;                                                                                 \
+    }                                                                                         \
+  } while (0)
+#else
+#define TR(ev, idx) do {} while (0)
+#endif
 
 template <int WS>
 struct Cfg {
@@ -59,16 +87,17 @@ struct Cfg {
   static constexpr int MT = (NPAD + 127) / 128;
   static constexpr int TAIL = N - 128 * (MT - 1);                  // valid rows of the last tile
   static constexpr bool ROT = MT > 1 && TAIL <= 32;
-  static constexpr int SLOTW = NPAD < 64 ? 64 : NPAD;               // TMEM columns per slot: S, then P + O over it
+  static constexpr int KA = (NPAD + 31) / 32 * 16, KB = NPAD - KA;  // keys of the first / second half
+  static constexpr int OA = (NPAD / 2 + 15) / 16 * 16, OB = OA + HD;  // O_a, O_b behind the packed P
+  static constexpr int SLOTW = NPAD > OB + HD ? NPAD : OB + HD;       // TMEM columns per slot: S, then P|O_a|O_b
   static constexpr int NSLOT = 512 / SLOTW > 4 ? 4 : 512 / SLOTW;
-  static constexpr int OCOL = (NPAD / 2 + 31) / 32 * 32;            // O accumulator behind the packed P
-  static_assert(OCOL + HD <= SLOTW, "O must fit into the slot");
   static constexpr int NS = N + ((12 - N % 8) % 8);                 // bias row stride, NS % 8 == 4: float4 reads
   static_assert(NS % 8 == 4 && NS >= N, "bias stride");             //   of 8 consecutive rows hit 8 bank groups
   static constexpr uint32_t kRow = NPAD * 64;                       // one [NPAD][64 B] operand tile
   static constexpr uint32_t kStage = 3 * kRow;                      // Q | K | V
   static constexpr int TW = 2 * WS - 1, NTAB = TW * TW;
-  static constexpr size_t kSmem = 1024 + (size_t)NSTAGE * kStage + (size_t)N * NS * 4 + (size_t)NTAB * 4;
+  static constexpr size_t kSmem =
+      1024 + 16 + (size_t)NSTAGE * kStage + (size_t)N * NS * 4 + (size_t)NTAB * 4 + (size_t)NSLOT * 128 * 8;
 };
 
 __device__ __forceinline__ uint32_t sw64_off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
@@ -110,6 +139,69 @@ __device__ __forceinline__ int src_token(const WinGeom& g, int b, int wh, int ww
   return (i < g.H && j < g.W) ? (b * g.H + i) * g.W + j : -1;
 }
 
+// One thread = one query row x the keys [C0, C0 + NC) of the window.  Reads its part of S from TMEM, turns it into
+// logits in log2 units (scale * cos + bias, shift mask), takes the maximum m and sum l over ITS keys and writes
+// P = exp2(s - m) as packed bf16 over the S columns [C0/2, (C0+NC)/2).  All lanes of the warp must call it
+// (tcgen05.ld / st are warp-collective); `valid` lanes own a real row.
+template <int WS, int C0, int NC>
+__device__ __forceinline__ void softmax_half(uint32_t t_s, const float* brow, float scale2, bool need_mask, uint32_t by,
+                                             uint32_t bx, bool valid, float& m_out, float& l_out
+#ifdef B200SWIN_TRACE
+                                             , const WsArgs& a, int& trc_, int u
+#endif
+                                             ) {
+  constexpr int N = WS * WS;
+  static_assert(C0 % 16 == 0 && NC % 16 == 0, "key halves are whole k-steps");
+  if constexpr (NC > 0) {
+    uint32_t sv[NC];
+#pragma unroll
+    for (int c = 0; c < NC / 16; ++c) tmem_ld16(t_s + C0 + c * 16, &sv[c * 16]);
+    ptx::tmem_ld_wait();
+    TR(40, u);
+    if (valid) {
+      const float4* b4 = reinterpret_cast<const float4*>(brow + C0);
+#pragma unroll
+      for (int j4 = 0; j4 < NC / 4; ++j4) {
+        if (C0 + j4 * 4 < N) {
+          const float4 bb = b4[j4];
+          const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (C0 + j4 * 4 + k < N) sv[j4 * 4 + k] = __float_as_uint(fmaf(__uint_as_float(sv[j4 * 4 + k]), scale2, bv[k]));
+        }
+      }
+      if (need_mask) {
+#pragma unroll
+        for (int jj = 0; jj < NC; ++jj) {
+          const int j = C0 + jj, yj = j / WS, xj = j % WS;
+          if (j < N && (((by >> yj) | (bx >> xj)) & 1u)) sv[jj] = __float_as_uint(__uint_as_float(sv[jj]) + kMaskLog2);
+        }
+      }
+      float m = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < NC; ++jj)
+        if (C0 + jj < N) m = fmaxf(m, __uint_as_float(sv[jj]));
+      TR(41, u);
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < NC; jj += 2) {
+        const float p0 = C0 + jj < N ? ex2(__uint_as_float(sv[jj]) - m) : 0.f;
+        const float p1 = C0 + jj + 1 < N ? ex2(__uint_as_float(sv[jj + 1]) - m) : 0.f;
+        l0 += p0;
+        l1 += p1;
+        sv[jj >> 1] = pack_bf16(p0, p1);
+      }
+      m_out = m;
+      l_out = l0 + l1;
+    }
+    TR(42, u);
+#pragma unroll
+    for (int c = 0; c < NC / 16; ++c) tmem_st8(t_s + C0 / 2 + c * 8, &sv[c * 8]);
+    ptx::tmem_st_wait();
+    TR(43, u);
+  }
+}
+
 template <int WS>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
@@ -125,8 +217,12 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
   unsigned char* sm = smem_dyn + (base_u32 - ptx::smem_u32(smem_dyn));
   float* bias = reinterpret_cast<float*>(sm + (size_t)NSTAGE * CF::kStage);
   float* tab = bias + N * NS;
+  float2* ml = reinterpret_cast<float2*>(tab + CF::NTAB + (CF::NTAB & 1));   // [NSLOT][128] (m, l) of the first half
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef B200SWIN_TRACE
+  int trc_ = 0;
+#endif
 
   // contiguous, balanced item range of this CTA (items are head-major)
   const int64_t per = a.nitems / gridDim.x, rem = a.nitems % gridDim.x;
@@ -138,13 +234,13 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
     for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&kv_full[s], kLoaders); ptx::mbar_init(&kv_empty[s], 1); }
     for (int s = 0; s < NSLOT; ++s) {
       ptx::mbar_init(&s_full[s], 1);
-      ptx::mbar_init(&p_full[s], 4);
+      ptx::mbar_init(&p_full[s], 8);
       ptx::mbar_init(&o_full[s], 1);
-      ptx::mbar_init(&slot_free[s], 4);
+      ptx::mbar_init(&slot_free[s], 8);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 0) {
+  if (warp == kIssuerWarp) {
     ptx::tmem_alloc(&tmem_slot, 512);
     ptx::tmem_relinquish();
   }
@@ -153,66 +249,84 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp < 4) {
-    reg_dec<56>();
-    if (warp == 0) {
+  if (warp >= 16) {
+    reg_dec<kRegService>();
+    if (warp == kIssuerWarp) {
       // =================================================================================== MMA issuer
       if (lane == 0) {
+        // Fixed software pipeline (blocking, hardware-sleep waits -- a polling scheduler costs more issue slots than
+        // the MMAs themselves):  S runs D units ahead of PV, so the softmax warps always find their next S ready.
         constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(128, NPAD, 0, 0);
         constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, HD, 0, 1);   // A = P (TMEM), B = V MN-major
+        constexpr int D = NSLOT - 1;
+        const uint64_t desc_k = ptx::make_smem_desc(0, 16, 512, kSw64);      // K-major Q / K tiles (64 B rows)
+        const uint64_t desc_v = ptx::make_smem_desc(0, 512, 512, kSw64);     // MN-major V tile
         const int U = n * MT;
-        int su = 0, pu = 0;
-        long long t0 = clock64();
-        while (pu < U) {
-          bool progressed = false;
-          if (pu < su) {
-            const int slot = pu % NSLOT;
-            if (ptx::mbar_test_wait(&p_full[slot], (pu / NSLOT) & 1)) {
-              const int il = pu / MT, tile = pu - il * MT, stage = il % NSTAGE;
-              ptx::tc_fence_after();
-              const uint32_t v_s = base_u32 + (uint32_t)stage * CF::kStage + 2 * CF::kRow;
-              const uint32_t t_s = tmem_base + (uint32_t)slot * CF::SLOTW;
+        auto issue_s = [&](int u) {
+          const int slot = u % NSLOT;
+          const int il = u / MT, tile = u - il * MT, stage = il % NSTAGE;
+          TR(10, u);
+          ptx::mbar_wait(&slot_free[slot], ((u / NSLOT) & 1) ^ 1);
+          TR(11, u);
+          if (tile == 0) ptx::mbar_wait(&kv_full[stage], (il / NSTAGE) & 1);
+          TR(12, u);
+          ptx::tc_fence_after();
+          const uint32_t q_s = base_u32 + (uint32_t)stage * CF::kStage, k_s = q_s + CF::kRow;
+          int row0 = tile * 128;
+          if (CF::ROT && tile == MT - 1) row0 -= 32 * ((il >> 1) & 3);
+          const uint32_t t_s = tmem_base + (uint32_t)slot * CF::SLOTW;
+          const uint64_t ad = desc_k + ((q_s + row0 * 64) >> 4), bd = desc_k + (k_s >> 4);
+          ptx::mma_bf16_ss(t_s, ad, bd, idesc_qk, 0u);
+          ptx::mma_bf16_ss(t_s, ad + 2, bd + 2, idesc_qk, 1u);               // second k-step: +32 B
+          ptx::mma_commit(&s_full[slot]);
+          TR(13, u);
+        };
+        for (int u = 0; u < D && u < U; ++u) issue_s(u);
+        for (int u = 0; u < U; ++u) {
+          if (u + D < U) issue_s(u + D);
+          const int slot = u % NSLOT;
+          const int il = u / MT, tile = u - il * MT, stage = il % NSTAGE;
+          TR(14, u);
+          ptx::mbar_wait(&p_full[slot], (u / NSLOT) & 1);
+          TR(15, u);
+          ptx::tc_fence_after();
+          const uint32_t v_s = base_u32 + (uint32_t)stage * CF::kStage + 2 * CF::kRow;
+          const uint32_t t_s = tmem_base + (uint32_t)slot * CF::SLOTW;
+          const uint64_t bd = desc_v + (v_s >> 4);
 #pragma unroll
-              for (int ks = 0; ks < NPAD / 16; ++ks)
-                ptx::mma_bf16_ts(t_s + CF::OCOL, t_s + ks * 8, ptx::make_smem_desc(v_s + ks * 1024, 512, 512, kSw64),
-                                 idesc_pv, ks);
-              ptx::mma_commit(&o_full[slot]);
-              if (tile == MT - 1) ptx::mma_commit(&kv_empty[stage]);   // every MMA that reads this stage has retired
-              ++pu;
-              progressed = true;
-            }
+          for (int ks = 0; ks < NPAD / 16; ++ks) {
+            const bool second = ks >= CF::KA / 16;                           // keys of the second half -> O_b
+            ptx::mma_bf16_ts(t_s + (second ? CF::OB : CF::OA), t_s + ks * 8, bd + ks * 64, idesc_pv,
+                             (ks != 0 && ks != CF::KA / 16) ? 1u : 0u);
           }
-          if (su < U && su - pu < NSLOT) {
-            const int slot = su % NSLOT;
-            const int il = su / MT, tile = su - il * MT, stage = il % NSTAGE;
-            if (ptx::mbar_test_wait(&slot_free[slot], ((su / NSLOT) & 1) ^ 1) &&
-                ptx::mbar_test_wait(&kv_full[stage], (il / NSTAGE) & 1)) {
-              ptx::tc_fence_after();
-              const uint32_t q_s = base_u32 + (uint32_t)stage * CF::kStage, k_s = q_s + CF::kRow;
-              int row0 = tile * 128;
-              if (CF::ROT && tile == MT - 1) row0 -= 32 * ((il >> 1) & 3);
-              const uint32_t t_s = tmem_base + (uint32_t)slot * CF::SLOTW;
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks)
-                ptx::mma_bf16_ss(t_s, ptx::make_smem_desc(q_s + row0 * 64 + ks * 32, 16, 512, kSw64),
-                                 ptx::make_smem_desc(k_s + ks * 32, 16, 512, kSw64), idesc_qk, ks);
-              ptx::mma_commit(&s_full[slot]);
-              ++su;
-              progressed = true;
-            }
-          }
-          if (progressed) t0 = clock64();
-          else if (clock64() - t0 > 4000000000ll) __trap();
+          ptx::mma_commit(&o_full[slot]);
+          if (tile == MT - 1) ptx::mma_commit(&kv_empty[stage]);             // every MMA reading this stage retired
+          TR(16, u);
         }
       }
     } else {
       // =================================================================================== gather warps
-      const int lt = threadIdx.x - 32;
+      const int lt = threadIdx.x - 512;
       const int C3 = 3 * a.C;
-      for (int i = 0; i < n + LAG; ++i) {
-        if (i < n) {
+      // `pending` gathers are in flight (items i-pending .. i-1, one cp.async group each).  An item is published
+      // (kv_full) as soon as it is LAG groups old -- and everything in flight is published before the warp goes to
+      // sleep on a full ring, so the MMA warp can always run ahead on what has already landed.
+      int pending = 0;
+      for (int i = 0; i < n; ++i) {
+        {
           const int stage = i % NSTAGE;
-          ptx::mbar_wait(&kv_empty[stage], ((i / NSTAGE) & 1) ^ 1);
+          const uint32_t par = ((i / NSTAGE) & 1) ^ 1;
+          if (!ptx::mbar_test_wait(&kv_empty[stage], par)) {
+            if (pending) {
+              ptx::cp_async_wait<0>();
+              ptx::fence_proxy_async_smem();
+              for (int k = i - pending; k < i; ++k) ptx::mbar_arrive(&kv_full[k % NSTAGE]);
+              pending = 0;
+            }
+            TR(20, i);
+            ptx::mbar_wait(&kv_empty[stage], par);
+          }
+          TR(21, i);
           const int64_t gi = g0 + i;
           const int h = (int)(gi / a.nwin);
           const int64_t win = gi - (int64_t)h * a.nwin;
@@ -250,19 +364,29 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
           }
         }
         ptx::cp_async_commit();
-        if (i >= LAG) {
+        TR(22, i);
+        if (++pending > LAG) {
           ptx::cp_async_wait<LAG>();              // the gather of item i - LAG has landed
           ptx::fence_proxy_async_smem();          // generic-proxy writes -> visible to tcgen05.mma
           ptx::mbar_arrive(&kv_full[(i - LAG) % NSTAGE]);
+          TR(23, i - LAG);
+          --pending;
         }
+      }
+      if (pending) {
+        ptx::cp_async_wait<0>();
+        ptx::fence_proxy_async_smem();
+        for (int k = n - pending; k < n; ++k) ptx::mbar_arrive(&kv_full[k % NSTAGE]);
       }
     }
   } else {
-    // ===================================================================================== softmax warpgroups
-    reg_inc<224>();
-    const int wg = (warp - 4) >> 2;                 // 0 / 1: items of even / odd local index
+    // ===================================================================================== softmax warps
+    reg_inc<kRegSoftmax>();
+    const int sw = warp;
+    const int ug = sw >> 3;                         // unit group: items of even / odd local index
+    const int half = (sw >> 2) & 1;                 // which half of the keys this warp owns
     const int q = warp & 3;                         // TMEM lane quarter of this warp
-    const int st = threadIdx.x - 128;               // 0..255 over both softmax warpgroups
+    const int st = threadIdx.x;                     // 0..511 over all softmax warps
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     int cur_head = -1;
     float scale2 = 0.f;
@@ -271,19 +395,19 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
       const int64_t gi = g0 + il;
       const int h = (int)(gi / a.nwin);
       if (h != cur_head) {
-        // both warpgroups have finished every earlier item: rebuild the expanded bias matrix of head h (log2 units)
-        named_bar_sync(1, 256);
-        for (int t = st; t < CF::NTAB; t += 256) tab[t] = a.table16[t * a.nH + h] * kLog2e;
-        named_bar_sync(1, 256);
-        for (int e = st; e < N * N; e += 256) {
+        // every softmax warp has finished all earlier items: rebuild the expanded bias matrix of head h (log2 units)
+        named_bar_sync(1, kSoftmax);
+        for (int t = st; t < CF::NTAB; t += kSoftmax) tab[t] = a.table16[t * a.nH + h] * kLog2e;
+        named_bar_sync(1, kSoftmax);
+        for (int e = st; e < N * N; e += kSoftmax) {
           const int i = e / N, j = e - i * N;
           bias[i * NS + j] = tab[(i / WS - j / WS + WS - 1) * CF::TW + (i % WS - j % WS + WS - 1)];
         }
-        named_bar_sync(1, 256);
+        named_bar_sync(1, kSoftmax);
         cur_head = h;
         scale2 = a.scale[h] * kLog2e;
       }
-      if ((il & 1) != wg) continue;
+      if ((il & 1) != ug) continue;
       const int64_t win = gi - (int64_t)h * a.nwin;
       const int b = (int)(win / nW);
       const int w = (int)(win - (int64_t)b * nW);
@@ -302,92 +426,75 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
         else { r = tile * 128 + q * 32 + lane; if (r >= N) r = -1; }
         const bool warp_active = __any_sync(0xffffffffu, r >= 0);
         const uint32_t t_s = t_lane + (uint32_t)slot * CF::SLOTW;
+        float2* ml_row = ml + slot * 128 + q * 32 + lane;
 
+        TR(30, u);
         ptx::mbar_wait(&s_full[slot], par);
+        TR(31, u);
         ptx::tc_fence_after();
-        float m = -INFINITY, l0 = 0.f, l1 = 0.f;
-        if (warp_active) {
-          uint32_t sv[NPAD];
-#pragma unroll
-          for (int c = 0; c < NPAD / 16; ++c) tmem_ld16(t_s + c * 16, &sv[c * 16]);
-          ptx::tmem_ld_wait();
-          if (r >= 0) {
+        float m = -INFINITY, l = 0.f;
+        if (warp_active && (half == 0 || CF::KB > 0)) {
+          uint32_t by = 0, bx = 0;
+          if (need_mask && r >= 0) {
+            // regions differ only across the roll seam of the last window row / column
             const int yi = r / WS, xi = r - yi * WS;
-            const float4* brow = reinterpret_cast<const float4*>(bias + r * NS);
-            // ---- pass A: logits in log2 units and the row maximum
-#pragma unroll
-            for (int j4 = 0; j4 < (N + 3) / 4; ++j4) {
-              const float4 bb = brow[j4];
-              const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int j = j4 * 4 + k;
-                if (j < N) sv[j] = __float_as_uint(fmaf(__uint_as_float(sv[j]), scale2, bv[k]));
-              }
-            }
-            if (need_mask) {
-              // regions differ only across the roll seam of the last window row / column
-              const int cut = WS - g.shift;                                 // in-window coordinate of the seam
-              const uint32_t hi = (~0u << cut) & ((1u << WS) - 1u), lo = (1u << cut) - 1u;
-              const uint32_t by = last_h ? (yi >= cut ? lo : hi) : 0u;      // bit y set: key row y is masked
-              const uint32_t bx = last_w ? (xi >= cut ? lo : hi) : 0u;
-#pragma unroll
-              for (int yj = 0; yj < WS; ++yj) {
-                const uint32_t rowm = ((by >> yj) & 1u) ? 0xffffffffu : bx;
-#pragma unroll
-                for (int xj = 0; xj < WS; ++xj) {
-                  const int j = yj * WS + xj;
-                  if ((rowm >> xj) & 1u) sv[j] = __float_as_uint(__uint_as_float(sv[j]) + kMaskLog2);
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < N; ++j) m = fmaxf(m, __uint_as_float(sv[j]));
-            // ---- pass B: P = exp2(s - m), row sum, packed bf16 over the S columns
-#pragma unroll
-            for (int j = 0; j < NPAD; j += 2) {
-              const float p0 = j < N ? ex2(__uint_as_float(sv[j]) - m) : 0.f;
-              const float p1 = j + 1 < N ? ex2(__uint_as_float(sv[j + 1]) - m) : 0.f;
-              l0 += p0;
-              l1 += p1;
-              sv[j >> 1] = pack_bf16(p0, p1);
-            }
+            const int cut = WS - g.shift;                                   // in-window coordinate of the seam
+            const uint32_t hi = (~0u << cut) & ((1u << WS) - 1u), lo = (1u << cut) - 1u;
+            by = last_h ? (yi >= cut ? lo : hi) : 0u;                       // bit y set: key row y is masked
+            bx = last_w ? (xi >= cut ? lo : hi) : 0u;
           }
-#pragma unroll
-          for (int c = 0; c < NPAD / 16; ++c) tmem_st8(t_s + c * 8, &sv[c * 8]);
-          ptx::tmem_st_wait();
+          const float* brow = bias + (r >= 0 ? r : 0) * NS;
+#ifdef B200SWIN_TRACE
+          if (half == 0) softmax_half<WS, 0, CF::KA>(t_s, brow, scale2, need_mask, by, bx, r >= 0, m, l, a, trc_, u);
+          else softmax_half<WS, CF::KA, CF::KB>(t_s, brow, scale2, need_mask, by, bx, r >= 0, m, l, a, trc_, u);
+#else
+          if (half == 0) softmax_half<WS, 0, CF::KA>(t_s, brow, scale2, need_mask, by, bx, r >= 0, m, l);
+          else softmax_half<WS, CF::KA, CF::KB>(t_s, brow, scale2, need_mask, by, bx, r >= 0, m, l);
+#endif
         }
+        if (half == 0) *ml_row = make_float2(m, l);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&p_full[slot]);
-
-        // ---- O = P V is on its way; read it back, release the slot, normalise and store
-        ptx::mbar_wait(&o_full[slot], par);
-        ptx::tc_fence_after();
-        uint32_t o[32];
-        if (warp_active) {
-          ptx::tmem_ld_32x32b_x32(t_s + CF::OCOL, o);
-          ptx::tmem_ld_wait();
+        TR(32, u);
+        if (half == 0 || !warp_active) {
+          // nothing more to do for this unit: the first half never reads O, idle quarters have no rows
+          if (lane == 0) ptx::mbar_arrive(&slot_free[slot]);
+          continue;
         }
+
+        // ---- second half: O_a, O_b are on their way; combine, normalise and store
+        ptx::mbar_wait(&o_full[slot], par);
+        TR(33, u);
+        ptx::tc_fence_after();
+        uint32_t oa[32], ob[32];
+        ptx::tmem_ld_32x32b_x32(t_s + CF::OA, oa);
+        if (CF::KB > 0) ptx::tmem_ld_32x32b_x32(t_s + CF::OB, ob);
+        const float2 mla = *ml_row;
+        ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&slot_free[slot]);
+        TR(34, u);
         if (r >= 0) {
-          const float l = l0 + l1;
-          a.lse[((int64_t)win * a.nH + h) * N + r] = (m + log2f(l)) * kLn2;
+          const float mm = fmaxf(mla.x, m);
+          const float wa = ex2(mla.x - mm), wb = CF::KB > 0 ? ex2(m - mm) : 0.f;
+          const float lt = mla.y * wa + l * wb;
+          a.lse[((int64_t)win * a.nH + h) * N + r] = (mm + log2f(lt)) * kLn2;
           const int t = src_token(g, b, wh, ww, r / WS, r % WS);
           if (t >= 0) {
-            const float inv = 1.0f / l;
+            const float ia = wa / lt, ib = wb / lt;
+            float o[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              o[c] = __uint_as_float(oa[c]) * ia;
+              if (CF::KB > 0) o[c] = fmaf(__uint_as_float(ob[c]), ib, o[c]);
+            }
             uint4* dst = reinterpret_cast<uint4*>(a.out + (int64_t)t * a.C + h * HD);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint4 wv;
-              wv.x = pack_bf16(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
-              wv.y = pack_bf16(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
-              wv.z = pack_bf16(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
-              wv.w = pack_bf16(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
-              dst[c] = wv;
-            }
+            for (int c = 0; c < 4; ++c)
+              dst[c] = make_uint4(pack_bf16(o[c * 8 + 0], o[c * 8 + 1]), pack_bf16(o[c * 8 + 2], o[c * 8 + 3]),
+                                  pack_bf16(o[c * 8 + 4], o[c * 8 + 5]), pack_bf16(o[c * 8 + 6], o[c * 8 + 7]));
           }
         }
       }
@@ -395,7 +502,7 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == kIssuerWarp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
@@ -408,9 +515,34 @@ int launch_ws(const WsArgs& a, cudaStream_t st) {
   BSW_CUDA(cudaFuncSetAttribute(attn_fwd_ws_kernel<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::kSmem));
   int64_t grid = sm_count();
   if (grid > a.nitems) grid = a.nitems;
+#ifdef B200SWIN_TRACE
+  WsArgs at = a;
+  const char* tpath = getenv("B200SWIN_ATTN_TRACE");
+  const size_t tbytes = (1 + 4 * 60000) * sizeof(long long);
+  if (tpath) {
+    BSW_CUDA(cudaMalloc(&at.trace, tbytes));
+    BSW_CUDA(cudaMemsetAsync(at.trace, 0, tbytes, st));
+  }
+  attn_fwd_ws_kernel<WS><<<(unsigned)grid, kThreads, CF::kSmem, st>>>(at);
+  BSW_LAUNCH_CHECK();
+  if (tpath) {
+    std::vector<long long> hbuf(1 + 4 * 60000);
+    BSW_CUDA(cudaStreamSynchronize(st));
+    BSW_CUDA(cudaMemcpy(hbuf.data(), at.trace, tbytes, cudaMemcpyDeviceToHost));
+    BSW_CUDA(cudaFree(at.trace));
+    FILE* f = fopen(tpath, "w");
+    if (f) {
+      for (long long k = 0; k < 60000; ++k)
+        if (hbuf[4 + 4 * k] != 0) fprintf(f, "%lld %lld %lld %lld\n", hbuf[1 + 4 * k], hbuf[2 + 4 * k], hbuf[3 + 4 * k], hbuf[4 + 4 * k]);
+      fclose(f);
+    }
+  }
+  return B200SWIN_OK;
+#else
   attn_fwd_ws_kernel<WS><<<(unsigned)grid, kThreads, CF::kSmem, st>>>(a);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
+#endif
 }
 }  // namespace
 
@@ -425,6 +557,7 @@ int attn_fwd_ws(const void* qkv, void* out, float* lse, const float* table16, co
   a.C = C; a.nH = nH;
   a.nwin = (int64_t)B * a.g.nWh * a.g.nWw;
   a.nitems = a.nwin * nH;
+  a.trace = nullptr;
   switch (ws) {
     case 4: return launch_ws<4>(a, st);
     case 6: return launch_ws<6>(a, st);

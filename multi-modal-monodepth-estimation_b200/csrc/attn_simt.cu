@@ -472,8 +472,9 @@ int attn_fwd_tc(const void* qkv, void* out, float* lse, const float* table16, co
                 cudaStream_t st);
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
                 const float* table16, const float* scale, const float* qpad, const float* vpad, const float* mask,
-                int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, int B, int H, int W, int C, int nH,
-                int ws, int shift, cudaStream_t st);
+                int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, void* workspace,
+                size_t workspace_bytes, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st);
+size_t attn_bwd_tc_workspace_bytes(int B, int H, int W, int nH, int ws);
 
 }  // namespace b200swin
 
@@ -498,11 +499,17 @@ extern "C" int b200swin_attn_fwd(const void* qkv, void* out, float* lse, const f
   return attn_fwd_simt<__nv_bfloat16>(qkv, out, lse, table16, scale, qpad, vpad, mask, d, threads, st);
 }
 
+extern "C" size_t b200swin_attn_bwd_workspace_bytes(int B, int H, int W, int nH, int ws, int dtype, int impl) {
+  // scratch of the backward: D = <dO, O> per (token, head) for the warp-specialised tensor-core kernel
+  if (impl != 1 || dtype != B200SWIN_BF16 || B <= 0 || H <= 0 || W <= 0 || nH <= 0) return 0;
+  return attn_bwd_tc_workspace_bytes(B, H, W, nH, ws);
+}
+
 extern "C" int b200swin_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                                  const float* inv_norm, const float* table16, const float* scale, const float* qpad,
                                  const float* vpad, const float* mask, int nWm, void* dqkv, float* dtable16,
                                  float* dscale, float* dvpad, int B, int H, int W, int C, int nH, int ws, int shift,
-                                 int dtype, int impl, void* stream) {
+                                 int dtype, int impl, void* workspace, size_t workspace_bytes, void* stream) {
   BSW_REQUIRE(qkv && out && dout && lse && inv_norm && table16 && scale && dqkv && dtable16 && dscale,
               "attn_bwd: null pointer");
   BSW_REQUIRE(dtype == B200SWIN_F32 || dtype == B200SWIN_BF16, "attn_bwd: bad dtype %d", dtype);
@@ -510,7 +517,7 @@ extern "C" int b200swin_attn_bwd(const void* qkv, const void* out, const void* d
   if (impl == 1) {
     BSW_REQUIRE(dtype == B200SWIN_BF16, "attn_bwd: the tensor-core path stores bf16");
     return attn_bwd_tc(qkv, out, dout, lse, inv_norm, table16, scale, qpad, vpad, mask, nWm, dqkv, dtable16, dscale,
-                       dvpad, B, H, W, C, nH, ws, shift, st);
+                       dvpad, workspace, workspace_bytes, B, H, W, C, nH, ws, shift, st);
   }
   BSW_REQUIRE(impl == 0, "attn_bwd: unknown impl %d", impl);
   AttnDims d;

@@ -314,6 +314,18 @@ static int launch_fwd(const TcArgs& a, cudaStream_t st) {
 bool attn_fwd_ws_supported(int ws);
 int attn_fwd_ws(const void* qkv, void* out, float* lse, const float* table16, const float* scale, const float* qpad,
                 const float* vpad, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st);
+// warp-specialised backward (attn_bwd_ws.cu)
+bool attn_bwd_ws_supported(int ws);
+size_t attn_bwd_ws_workspace_bytes(int B, int H, int W, int nH);
+int attn_bwd_ws(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
+                const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
+                float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH, int ws,
+                int shift, cudaStream_t st);
+static bool use_legacy_bwd() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200SWIN_ATTN_BWD_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 static bool use_legacy_fwd() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("B200SWIN_ATTN_FWD_LEGACY"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -813,10 +825,14 @@ bool attn_tc_bwd_supported(int ws, int C, int nH, const void* mask) {
   return mask == nullptr && C == nH * HD && npad <= 176 && ws >= 2;
 }
 
+size_t attn_bwd_tc_workspace_bytes(int B, int H, int W, int nH, int ws) {
+  return (attn_bwd_ws_supported(ws) && !use_legacy_bwd()) ? attn_bwd_ws_workspace_bytes(B, H, W, nH) : 0;
+}
+
 int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
                 const float* table16, const float* scale, const float* qpad, const float* vpad, const float* mask,
-                int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, int B, int H, int W, int C, int nH,
-                int ws, int shift, cudaStream_t st) {
+                int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, void* workspace,
+                size_t workspace_bytes, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st) {
   (void)nWm;
   BSW_REQUIRE(attn_tc_bwd_supported(ws, C, nH, mask),
               "attn_bwd(tc): needs head_dim 32, window <= 13x13 and the on-the-fly mask");
@@ -825,6 +841,12 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
                 reinterpret_cast<uintptr_t>(dqkv)) & 15) == 0 && C % 8 == 0,
               "attn_bwd(tc): tensors must be 16-byte aligned");
   BSW_REQUIRE((int64_t)B * H * W < (1ll << 29), "attn_bwd(tc): too many tokens");
+  if (attn_bwd_ws_supported(ws) && !use_legacy_bwd()) {
+    BSW_REQUIRE(workspace && workspace_bytes >= attn_bwd_ws_workspace_bytes(B, H, W, nH),
+                "attn_bwd(tc): workspace too small (b200swin_attn_bwd_workspace_bytes)");
+    return attn_bwd_ws(qkv, out, dout, lse, inv_norm, table16, scale, qpad, vpad, dqkv, dtable16, dscale, dvpad,
+                       workspace, B, H, W, C, nH, ws, shift, st);
+  }
   TcBwdArgs a;
   a.qkv = (const __nv_bfloat16*)qkv; a.out = (const __nv_bfloat16*)out; a.dout = (const __nv_bfloat16*)dout;
   a.lse = lse; a.inv_norm = inv_norm; a.table16 = table16; a.scale = scale; a.qpad = qpad; a.vpad = vpad;

@@ -504,11 +504,13 @@ class _AttnCore(torch.autograd.Function):
             dt16 = acc[:t16.numel()].view_as(t16)
             dsc = acc[t16.numel():t16.numel() + nH]
             dvp = acc[t16.numel() + nH:]
+            ws_bytes = lib.b200swin_attn_bwd_workspace_bytes(B, H, W, nH, ws, L.dtype_code(qkv), ctx.impl_bwd)
+            wsp = torch.empty(ws_bytes, dtype=torch.uint8, device=qkv.device) if ws_bytes else None
             L.check(lib.b200swin_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
                                           inv_norm.data_ptr(), t16.data_ptr(), sc.data_ptr(), L.ptr(qp), L.ptr(vp),
                                           L.ptr(mk), ctx.nWm, dqkv.data_ptr(), dt16.data_ptr(), dsc.data_ptr(),
                                           dvp.data_ptr(), B, H, W, C, nH, ws, shift, L.dtype_code(qkv), ctx.impl_bwd,
-                                          L.stream_of(qkv)), "attn_bwd")
+                                          L.ptr(wsp), ws_bytes, L.stream_of(qkv)), "attn_bwd")
         tdt, sdt, vdt = ctx.dtypes
         return (dqkv, None, dt16.to(tdt), dsc.view(sc.shape).to(sdt), None,
                 dvp.to(vdt) if vdt is not None else None, None, None)
