@@ -95,8 +95,12 @@ struct Cfg {
   // equal thirds that start on a window row -> the unrolled compute code is shared by all key thirds
   static constexpr bool UNIFIED = (K1 - K0 == K2 - K1) && (K2 - K1 == K3 - K2) && (K1 % WS == 0) && (NPAD == N);
   static constexpr uint32_t kRow = NPAD * 64;                     // one [NPAD][64 B] operand tile
-  // Q | dO | K | V | lse[NPAD] | D[NPAD], padded to 1 KB so that every tile keeps the swizzle phase of its address
-  static constexpr uint32_t kStage = (4 * kRow + 2 * NPAD * 4 + 1023) / 1024 * 1024;
+  // Q | dO | K | V | lse | D | 1/|q| | 1/|k| (NPAD floats each) | item header (8 ints), padded to 1 KB so that every
+  // tile keeps the swizzle phase of its address
+  static constexpr uint32_t kAux = 4 * kRow;                       // offset of the per-row float arrays
+  static constexpr uint32_t kHdr = kAux + 4 * NPAD * 4;            // offset of the item header
+  static constexpr uint32_t kStage = (kHdr + 32 + 1023) / 1024 * 1024;
+  static constexpr int DVP_ROWS = 128 + (MT > 1 ? 16 : 0), DVP_LD = 36;   // lane-private v_bias-gradient rows
   static constexpr uint32_t kPBytes = NP * kPanel;
   static constexpr int TW = 2 * WS - 1, NTAB = TW * TW;
   // TMEM columns
@@ -104,9 +108,10 @@ struct Cfg {
                             DK_COL = DV_COL + 32, DVT_COL = DK_COL + 32, DKT_COL = DVT_COL + 32;
   static_assert(2 * NPAD + 192 <= 512, "TMEM budget");
   static constexpr size_t kFixed = 2 * (size_t)kPBytes + 2 * (size_t)NTAB * 4 + (size_t)NPAD * 4 /* meta */ +
-                                   (MT > 1 ? 16 * (size_t)NPAD * 4 : 0) /* tail bias-gradient sums */ + 1024 + 64;
+                                   (MT > 1 ? 16 * (size_t)NPAD * 4 : 0) /* tail bias-gradient sums */ +
+                                   (size_t)DVP_ROWS * DVP_LD * 4 + 1024 + 64;
   static constexpr int NSTAGE_RAW = (int)((227 * 1024 - kFixed) / kStage);
-  static constexpr int NSTAGE = NSTAGE_RAW > 6 ? 6 : NSTAGE_RAW;
+  static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : NSTAGE_RAW;
   static_assert(NSTAGE >= 2, "shared memory budget");
   static constexpr size_t kSmem = kFixed + (size_t)NSTAGE * kStage;
 };
@@ -233,12 +238,18 @@ __device__ __forceinline__ void bwd_main(uint32_t t_row, uint32_t s_col, uint32_
     const int slot0 = c0 >> 3, r7 = row_local & 7;
     unsigned char* prow = Pp + row_local * 128;
     unsigned char* drow = dSp + row_local * 128;
+    uint32_t svb[2][4], dvb[2][4];
+    tmem_ld4(s_base, svb[0]);
+    tmem_ld4(dp_base, dvb[0]);
 #pragma unroll
     for (int cc = 0; cc < NC / 4; ++cc) {
-      uint32_t sv[4], dv[4];
-      tmem_ld4(s_base + cc * 4, sv);
-      tmem_ld4(dp_base + cc * 4, dv);
-      ptx::tmem_ld_wait();
+      ptx::tmem_ld_wait();                                 // step cc has landed ...
+      if (cc + 1 < NC / 4) {                               // ... step cc + 1 flies while step cc is computed
+        tmem_ld4(s_base + (cc + 1) * 4, svb[(cc + 1) & 1]);
+        tmem_ld4(dp_base + (cc + 1) * 4, dvb[(cc + 1) & 1]);
+      }
+      const uint32_t(&sv)[4] = svb[cc & 1];
+      const uint32_t(&dv)[4] = dvb[cc & 1];
       if (cc == NC / 4 - 1) {
         ptx::tc_fence_before();
         __syncwarp();
@@ -359,10 +370,12 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
   unsigned char* Pp = sm;                                           // panels first: 1024-byte aligned
   unsigned char* dSp = Pp + CF::kPBytes;
   unsigned char* ring = dSp + CF::kPBytes;
-  float* tab = reinterpret_cast<float*>(ring + (size_t)NSTAGE * CF::kStage);
+  // lane-private dV sums of pad tokens first: float4 accesses need the 16-byte alignment of the ring end
+  float* dvp = reinterpret_cast<float*>(ring + (size_t)NSTAGE * CF::kStage);   // [DVP_ROWS][DVP_LD]
+  float* tacc = dvp + CF::DVP_ROWS * CF::DVP_LD;                   // [16][NPAD] (MT > 1 only), 8-byte aligned
+  float* tab = tacc + (MT > 1 ? 16 * NPAD : 0);
   float* dtab = tab + CF::NTAB;
   int* meta = reinterpret_cast<int*>(dtab + CF::NTAB);             // [NPAD] koff | yj << 16 | xj << 24
-  float* tacc = reinterpret_cast<float*>(meta + NPAD);             // [16][NPAD] (MT > 1 only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef B200SWIN_TRACE
@@ -380,6 +393,7 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
     meta[j] = j < N ? ((yj * TW + xj) | (yj << 16) | (xj << 24)) : 0;
   }
   if (MT > 1) for (int i = threadIdx.x; i < 16 * NPAD; i += kThreads) tacc[i] = 0.f;
+  for (int i = threadIdx.x; i < CF::DVP_ROWS * CF::DVP_LD; i += kThreads) dvp[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&kv_full[s], kLoaders); ptx::mbar_init(&kv_empty[s], 1 + kComputeWarps); }
     ptx::mbar_init(&sdp_full, 1);
@@ -503,9 +517,17 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
         const int wh = w / g.nWw, ww = w - wh * g.nWw;
         unsigned char* st = ring + (size_t)stage * CF::kStage;
         const uint32_t q_s = ptx::smem_u32(st), g_s = q_s + CF::kRow, k_s = g_s + CF::kRow, v_s = k_s + CF::kRow;
-        const uint32_t lse_s = v_s + CF::kRow, d_s = lse_s + NPAD * 4;
-        float* lse_p = reinterpret_cast<float*>(st + 4 * CF::kRow);
+        const uint32_t lse_s = v_s + CF::kRow, d_s = lse_s + NPAD * 4, iq_s = d_s + NPAD * 4, ik_s = iq_s + NPAD * 4;
+        float* lse_p = reinterpret_cast<float*>(st + CF::kAux);
         float* d_p = lse_p + NPAD;
+        float* iq_p = d_p + NPAD;
+        float* ik_p = iq_p + NPAD;
+        if (lt == 0) {
+          // item header: the compute warps and their deferred epilogues read the geometry instead of re-deriving it
+          int* hdr = reinterpret_cast<int*>(st + CF::kHdr);
+          hdr[0] = h; hdr[1] = b; hdr[2] = wh; hdr[3] = ww;
+          hdr[4] = __float_as_int(a.scale[h]);
+        }
         for (int idx = lt; idx < NPAD * 4; idx += kLoaders) {
           const int r = idx >> 2, c = idx & 3;
           const int t = r < N ? src_token(g, b, wh, ww, r / WS, r % WS) : -2;
@@ -517,6 +539,8 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
             ptx::cp_async_16(v_s + off, src + 2 * a.C);
             ptx::cp_async_16(g_s + off, a.dout + (int64_t)t * a.C + h * HD + c * 8);
             if (c == 0) cp_async_4(d_s + r * 4, a.dvec + (int64_t)t * a.nH + h);
+            if (c == 2) cp_async_4(iq_s + r * 4, a.inv_norm + ((int64_t)t * 2 + 0) * a.nH + h);
+            if (c == 3) cp_async_4(ik_s + r * 4, a.inv_norm + ((int64_t)t * 2 + 1) * a.nH + h);
           } else {
             // pad token: q = normalised q_bias, k = 0, v = v_bias, dO = 0 (cropped row); key padding rows: all zero
             uint4 qv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
@@ -535,6 +559,8 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
             *reinterpret_cast<uint4*>(st + 2 * CF::kRow + off) = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4*>(st + 3 * CF::kRow + off) = vv;
             if (c == 0) d_p[r] = 0.f;
+            if (c == 2) iq_p[r] = 0.f;
+            if (c == 3) ik_p[r] = 0.f;
           }
           if (c == 1) {
             // log-sum-exp of the row, in log2 units at use; rows beyond the window: +inf (P = 0)
@@ -626,15 +652,12 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
       pe.stage = pe.il % NSTAGE;
       pe.item_end = pe.tile == MT - 1;
       {
-        const int64_t gi = g0 + pe.il;
-        pe.h = (int)(gi / a.nwin);
-        const int64_t win = gi - (int64_t)pe.h * a.nwin;
-        pe.b = (int)(win / nW);
-        const int w = (int)(win - (int64_t)pe.b * nW);
-        pe.wh = w / g.nWw;
-        pe.ww = w - pe.wh * g.nWw;
-        pe.sc = a.scale[pe.h];
+        const int* hdr = reinterpret_cast<const int*>(ring + (size_t)pe.stage * CF::kStage + CF::kHdr);
+        pe.h = hdr[0]; pe.b = hdr[1]; pe.wh = hdr[2]; pe.ww = hdr[3];
+        pe.sc = __int_as_float(hdr[4]);
       }
+      const float* iq_p = reinterpret_cast<const float*>(ring + (size_t)pe.stage * CF::kStage + CF::kAux) + 2 * NPAD;
+      const float* ik_p = iq_p + NPAD;
       unsigned char* st = ring + (size_t)pe.stage * CF::kStage;
       // ---- dQ rows of unit pe.u (warps of key third 0; one row per lane)
       if (kq == 0) {
@@ -645,7 +668,7 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
         ptx::tc_fence_after();
         if (__any_sync(0xffffffffu, r >= 0)) {
           const int t = r >= 0 ? src_token(g, pe.b, pe.wh, pe.ww, r / WS, r % WS) : -1;
-          const float invn = t >= 0 ? a.inv_norm[((int64_t)t * 2 + 0) * a.nH + pe.h] : 0.f;
+          const float invn = r >= 0 ? iq_p[r] : 0.f;
           normalize_bwd_store(t_row + CF::DQ_COL + qb * 32, st, r >= 0 ? r : 0, pe.sc, invn,
                               a.dqkv + (int64_t)(t >= 0 ? t : 0) * 3 * a.C + pe.h * HD, t >= 0);
         }
@@ -667,14 +690,14 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
         const bool jvalid = j < N && (!tail_kv || lane < 16);
         const int t = jvalid ? src_token(g, pe.b, pe.wh, pe.ww, j / WS, j % WS) : -2;
         if (kq == 1) {
-          const float invn = t >= 0 ? a.inv_norm[((int64_t)t * 2 + 1) * a.nH + pe.h] : 0.f;
+          const float invn = jvalid ? ik_p[j] : 0.f;
           normalize_bwd_store(t_row + (tail_kv ? CF::DKT_COL : CF::DK_COL), st + 2 * CF::kRow, jvalid ? j : 0, pe.sc, invn,
                               a.dqkv + (int64_t)(t >= 0 ? t : 0) * 3 * a.C + pe.h * HD + a.C, t >= 0);
         } else {
-          // pad tokens carry v = v_bias: their dV rows belong to v_bias (reduced over the warp; one atomic per channel
-          // straight to the head's slot -- this epilogue runs after the sums of the NEXT unit, possibly of the next head)
+          // pad tokens carry v = v_bias: their dV rows belong to v_bias.  Each lane adds its row into a lane-private
+          // row of shared memory (no reduction per item); the rows are summed when the head changes.
           const bool is_pad = t == -1;
-          const bool any_pad = __any_sync(0xffffffffu, is_pad);
+          float* myrow = dvp + (tail_kv ? 128 + lane : row_local) * CF::DVP_LD;
           uint4* d4 = reinterpret_cast<uint4*>(a.dqkv + (int64_t)(t >= 0 ? t : 0) * 3 * a.C + pe.h * HD + 2 * a.C);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -686,12 +709,13 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
                                  pack_bf16(__uint_as_float(ov[2]), __uint_as_float(ov[3])),
                                  pack_bf16(__uint_as_float(ov[4]), __uint_as_float(ov[5])),
                                  pack_bf16(__uint_as_float(ov[6]), __uint_as_float(ov[7])));
-            if (any_pad) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float v = warp_sum(is_pad ? __uint_as_float(ov[e]) : 0.f);
-                if (lane == 0 && a.dvpad) atomicAdd(a.dvpad + pe.h * HD + c * 8 + e, v);
-              }
+            if (is_pad) {
+              float4* m4 = reinterpret_cast<float4*>(myrow + c * 8);
+              float4 x = m4[0], y = m4[1];
+              x.x += __uint_as_float(ov[0]); x.y += __uint_as_float(ov[1]); x.z += __uint_as_float(ov[2]); x.w += __uint_as_float(ov[3]);
+              y.x += __uint_as_float(ov[4]); y.y += __uint_as_float(ov[5]); y.z += __uint_as_float(ov[6]); y.w += __uint_as_float(ov[7]);
+              m4[0] = x;
+              m4[1] = y;
             }
           }
         }
@@ -707,39 +731,43 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
     // One flat loop over the units plus a drain step, so that flush_head and run_epilogue each have exactly ONE call
     // site: they are inlined and the long-lived sums stay in registers (a real call would force them to the stack).
     const int U = n * MT;
-    int h = -1;
+    int h = -1, dvp_flush_head = -1;
     bool need_mask = false, last_h = false, last_w = false;
 #pragma unroll 1
     for (int u = 0; u <= U; ++u) {
       const bool has = u < U;
       const int il = u / MT, tile = u - il * MT;
       const int stage = il % NSTAGE;
+      if (has) {
+        TR(30, u);
+        ptx::mbar_wait(&sdp_full, u & 1);          // implies that the item's operand tiles and header have landed
+        TR(31, u);
+        ptx::tc_fence_after();
+      }
       if (tile == 0) {
-        // new item (or the drain step): geometry, and a head change flushes the sums of the previous head
-        const int64_t gi = g0 + il;
-        h = has ? (int)(gi / a.nwin) : -1;
+        // new item (or the drain step): geometry from the item header; a head change flushes the sums of the old head
+        const int* hdr = reinterpret_cast<const int*>(ring + (size_t)stage * CF::kStage + CF::kHdr);
+        h = has ? hdr[0] : -1;
         if (h != cur_head) {
           named_bar_sync(1, kCompute);                 // every warp has finished accumulating for the old head
           if (cur_head >= 0) flush_head(cur_head);
           if (h >= 0) {
             for (int t = threadIdx.x; t < CF::NTAB; t += kCompute) { tab[t] = a.table16[t * a.nH + h] * kLog2e; dtab[t] = 0.f; }
-            sc = a.scale[h];
+            sc = __int_as_float(hdr[4]);
             scale2 = sc * kLog2e;
           }
           named_bar_sync(1, kCompute);
+          dvp_flush_head = cur_head;                   // its last epilogue (pad-token dV rows) is still to come
           cur_head = h;
         }
         if (has) {
-          const int64_t win = gi - (int64_t)h * a.nwin;
-          const int w = (int)(win % nW);
-          const int wh = w / g.nWw, ww = w - wh * g.nWw;
-          last_h = wh == g.nWh - 1;
-          last_w = ww == g.nWw - 1;
+          last_h = hdr[2] == g.nWh - 1;
+          last_w = hdr[3] == g.nWw - 1;
           need_mask = g.shift > 0 && (last_h || last_w);
         }
       }
       if (has) {
-        const float* lse_p = reinterpret_cast<const float*>(ring + (size_t)stage * CF::kStage + 4 * CF::kRow);
+        const float* lse_p = reinterpret_cast<const float*>(ring + (size_t)stage * CF::kStage + CF::kAux);
         const float* d_p = lse_p + NPAD;
         const int cut = WS - g.shift;
         const uint32_t hi = (~0u << cut) & ((1u << WS) - 1u), lo = (1u << cut) - 1u;
@@ -753,10 +781,6 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
           rc.by = (need_mask && last_h) ? (yi >= cut ? lo : hi) : 0u;
           rc.bx = (need_mask && last_w) ? (xi >= cut ? lo : hi) : 0u;
         };
-        TR(30, u);
-        ptx::mbar_wait(&sdp_full, u & 1);          // implies the item's operand tiles (lse, D) have landed
-        TR(31, u);
-        ptx::tc_fence_after();
         auto wait_pds = [&]() { TR(35, u); ptx::mbar_wait(&pds_free, (u & 1) ^ 1); TR(36, u); };
         const int nc = kq == 0 ? CF::K1 - CF::K0 : kq == 1 ? CF::K2 - CF::K1 : CF::K3 - CF::K2;
         bool arrived = false;
@@ -801,6 +825,19 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
       if (pend_u >= 0) run_epilogue(pend_u);
       TR(33, u);
       pend_u = has ? u : -1;
+      if (dvp_flush_head >= 0) {
+        // the old head's last epilogue has just run in every warp: sum the lane-private pad-token dV rows
+        named_bar_sync(1, kCompute);
+        if (threadIdx.x < HD && a.dvpad) {
+          float v = 0.f;
+          for (int r = 0; r < CF::DVP_ROWS; ++r) v += dvp[r * CF::DVP_LD + threadIdx.x];
+          if (v != 0.f) atomicAdd(a.dvpad + dvp_flush_head * HD + threadIdx.x, v);
+        }
+        named_bar_sync(1, kCompute);
+        for (int i = threadIdx.x; i < CF::DVP_ROWS * CF::DVP_LD; i += kCompute) dvp[i] = 0.f;
+        named_bar_sync(1, kCompute);
+        dvp_flush_head = -1;
+      }
     }
   }
   ptx::tc_fence_before();
