@@ -138,6 +138,15 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 // 16 lanes x 8 columns spread over the warp: thread t gets rows t/4 and t/4 + 8, columns 2 (t % 4) and + 1
 // (r0, r1: first row; r2, r3: second row) -- layout verified on hardware by tools/probe/tmem_shapes.cu
 __device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, uint32_t* r) {
@@ -170,40 +179,47 @@ __device__ __forceinline__ int src_token(const WinGeom& g, int b, int wh, int ww
 // Warp-collective (tcgen05.ld): every lane calls it; `active` lanes own a row and store.
 __device__ __forceinline__ void normalize_bwd_store(uint32_t taddr, const unsigned char* tile, int r, float sc, float invn,
                                                     __nv_bfloat16* dst, bool active) {
+  // two passes over the accumulator in 16-column pieces: at most 16 registers of it are live at a time
   float dot = 0.f;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t o[8];
-    tmem_ld8(taddr + c * 8, o);
+  for (int hf = 0; hf < 2; ++hf) {
+    uint32_t o[16];
+    tmem_ld16(taddr + hf * 16, o);
     ptx::tmem_ld_wait();
     if (active) {
-      const uint4 w = *reinterpret_cast<const uint4*>(tile + sw64_off(r, c));
-      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
-        dot = fmaf(__uint_as_float(o[2 * e]), f.x, dot);
-        dot = fmaf(__uint_as_float(o[2 * e + 1]), f.y, dot);
+      for (int c = 0; c < 2; ++c) {
+        const uint4 w = *reinterpret_cast<const uint4*>(tile + sw64_off(r, hf * 2 + c));
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+          dot = fmaf(__uint_as_float(o[c * 8 + 2 * e]), f.x, dot);
+          dot = fmaf(__uint_as_float(o[c * 8 + 2 * e + 1]), f.y, dot);
+        }
       }
     }
   }
   dot *= sc;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t o[8];
-    tmem_ld8(taddr + c * 8, o);
+  for (int hf = 0; hf < 2; ++hf) {
+    uint32_t o[16];
+    tmem_ld16(taddr + hf * 16, o);
     ptx::tmem_ld_wait();
     if (active) {
-      const uint4 w = *reinterpret_cast<const uint4*>(tile + sw64_off(r, c));
-      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-      uint32_t pk[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
-        pk[e] = pack_bf16((__uint_as_float(o[2 * e]) * sc - f.x * dot) * invn,
-                          (__uint_as_float(o[2 * e + 1]) * sc - f.y * dot) * invn);
+      for (int c = 0; c < 2; ++c) {
+        const uint4 w = *reinterpret_cast<const uint4*>(tile + sw64_off(r, hf * 2 + c));
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+          pk[e] = pack_bf16((__uint_as_float(o[c * 8 + 2 * e]) * sc - f.x * dot) * invn,
+                            (__uint_as_float(o[c * 8 + 2 * e + 1]) * sc - f.y * dot) * invn);
+        }
+        reinterpret_cast<uint4*>(dst)[hf * 2 + c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
-      reinterpret_cast<uint4*>(dst)[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
 }
@@ -310,13 +326,19 @@ __device__ __forceinline__ void bwd_tail(uint32_t t_q0, uint32_t s_col, uint32_t
   constexpr int N = WS * WS, NPAD = (N + 15) / 16 * 16;
   const int rho[2] = {lane >> 2, (lane >> 2) + 8};
   const int ngroups = nc >> 3;
-#pragma unroll 1
+  uint32_t svb[2][4], dvb[2][4];
+  tmem_ld_16x256b(t_q0 + s_col + c0, svb[0]);
+  tmem_ld_16x256b(t_q0 + dp_col + c0, dvb[0]);
+#pragma unroll 2
   for (int gq = 0; gq < ngroups; ++gq) {
     const int j = c0 + gq * 8 + 2 * (lane & 3);             // this thread's column pair (j, j + 1)
-    uint32_t sv[4], dv[4];
-    tmem_ld_16x256b(t_q0 + s_col + c0 + gq * 8, sv);
-    tmem_ld_16x256b(t_q0 + dp_col + c0 + gq * 8, dv);
-    ptx::tmem_ld_wait();
+    ptx::tmem_ld_wait();                                    // group gq has landed; group gq + 1 flies during the math
+    if (gq + 1 < ngroups) {
+      tmem_ld_16x256b(t_q0 + s_col + c0 + (gq + 1) * 8, svb[(gq + 1) & 1]);
+      tmem_ld_16x256b(t_q0 + dp_col + c0 + (gq + 1) * 8, dvb[(gq + 1) & 1]);
+    }
+    const uint32_t(&sv)[4] = svb[gq & 1];
+    const uint32_t(&dv)[4] = dvb[gq & 1];
     if (gq == ngroups - 1) {
       ptx::tc_fence_before();
       __syncwarp();
@@ -439,7 +461,6 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
           ptx::mbar_wait(&pds_full, v & 1);
           TR(15, v);
           ptx::mbar_wait(&dq_free[qb], ((v >> 1) & 1) ^ 1);
-          if (tile == 0) ptx::mbar_wait(&dkv_free, (il & 1) ^ 1);
           ptx::tc_fence_after();
           // dQ_t = dS K
 #pragma unroll
@@ -447,7 +468,12 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
             ptx::mma_bf16_ss(tmem_base + CF::DQ_COL + qb * 32, desc_pk + ((ds_s + (ks >> 2) * kPanel + (ks & 3) * 32) >> 4),
                              desc_mn64 + ((k_s + ks * 1024) >> 4), idesc_dq, ks);
           ptx::mma_commit(&dq_full[qb]);
-          // dV += P^T dO_t,  dK += dS^T Q_t   (contraction over the query rows of this tile)
+          // dV += P^T dO_t,  dK += dS^T Q_t   (contraction over the query rows of this tile); the first tile overwrites
+          // the accumulators, which the epilogue of the previous item must have drained
+          if (tile == 0) {
+            ptx::mbar_wait(&dkv_free, (il & 1) ^ 1);
+            ptx::tc_fence_after();
+          }
           const int ksteps = (rows_valid + 15) / 16;
 #pragma unroll 1
           for (int ks = 0; ks < ksteps; ++ks) {
@@ -701,9 +727,12 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
           uint4* d4 = reinterpret_cast<uint4*>(a.dqkv + (int64_t)(t >= 0 ? t : 0) * 3 * a.C + pe.h * HD + 2 * a.C);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            uint32_t ov[8];
-            tmem_ld8(t_row + (tail_kv ? CF::DVT_COL : CF::DV_COL) + c * 8, ov);
-            ptx::tmem_ld_wait();
+            uint32_t ovv[16];
+            if ((c & 1) == 0) {
+              tmem_ld16(t_row + (tail_kv ? CF::DVT_COL : CF::DV_COL) + c * 8, ovv);
+              ptx::tmem_ld_wait();
+            }
+            const uint32_t* ov = &ovv[(c & 1) * 8];
             if (t >= 0)
               d4[c] = make_uint4(pack_bf16(__uint_as_float(ov[0]), __uint_as_float(ov[1])),
                                  pack_bf16(__uint_as_float(ov[2]), __uint_as_float(ov[3])),
