@@ -31,31 +31,58 @@ split_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
 }
 
 // out[n] = sum_m x[m, col_offset + n] over a [M, ld] matrix; two-stage, fixed order.
+// A block covers 128 columns with 16-byte loads (8 bf16 / 4 fp32 per thread) and 256 / (128 / VEC) row lanes; the row
+// loop is unrolled four times with independent accumulators so that 64 bytes per thread are in flight (HBM-bound).
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const T* __restrict__ x, int64_t M, int64_t ld, int64_t col0, int ncols,
                       float* __restrict__ part, int rows_per_block) {
-  // block = 32 column-quads (128 columns) x 8 row lanes
-  const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
-  const int c = blockIdx.x * 128 + cq * 4;
+  constexpr int VEC = 16 / sizeof(T);              // elements per 16-byte load
+  constexpr int TPR = 128 / VEC;                   // threads per row
+  constexpr int RL = 256 / TPR;                    // row lanes
+  const int cq = threadIdx.x % TPR, rl = threadIdx.x / TPR;
+  const int c = blockIdx.x * 128 + cq * VEC;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min(M, r0 + rows_per_block);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (c < ncols) {
-    for (int64_t r = r0 + rl; r < r1; r += 8) {
-      float v[4];
-      ld4(x + r * ld + col0 + c, v);
-      acc[0] += v[0]; acc[1] += v[1]; acc[2] += v[2]; acc[3] += v[3];
-    }
-  }
-  __shared__ float sh[8][128];
+  float acc[4][VEC];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) sh[rl][cq * 4 + e] = acc[e];
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[u][e] = 0.f;
+  auto add = [&](int u, const uint4& w) {
+    if constexpr (sizeof(T) == 2) {
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+        acc[u][2 * e] += f.x;
+        acc[u][2 * e + 1] += f.y;
+      }
+    } else {
+      acc[u][0] += __uint_as_float(w.x); acc[u][1] += __uint_as_float(w.y);
+      acc[u][2] += __uint_as_float(w.z); acc[u][3] += __uint_as_float(w.w);
+    }
+  };
+  if (c < ncols) {
+    const T* base = x + col0 + c;
+    int64_t r = r0 + rl;
+    for (; r + 3 * RL < r1; r += 4 * RL) {
+      uint4 w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = *reinterpret_cast<const uint4*>(base + (r + u * RL) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) add(u, w[u]);
+    }
+    for (; r < r1; r += RL) add(0, *reinterpret_cast<const uint4*>(base + r * ld));
+  }
+  __shared__ float sh[RL][128 + 4];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) sh[rl][cq * VEC + e] = (acc[0][e] + acc[1][e]) + (acc[2][e] + acc[3][e]);
   __syncthreads();
   if (threadIdx.x < 128) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += sh[w][threadIdx.x];
+    for (int w = 0; w < RL; ++w) s += sh[w][threadIdx.x];
     int cc = blockIdx.x * 128 + threadIdx.x;
     if (cc < ncols) part[(int64_t)blockIdx.y * ncols + cc] = s;
   }
@@ -107,8 +134,10 @@ extern "C" int b200swin_colsum(const void* x, int dtype, int64_t M, int64_t ld, 
                                const float* extra, float* out, void* workspace, size_t workspace_bytes,
                                void* stream) {
   BSW_REQUIRE(x && out && workspace, "colsum: null pointer");
-  BSW_REQUIRE(M > 0 && ncols > 0 && ncols % 4 == 0 && col0 % 4 == 0 && ld % 4 == 0 && col0 + ncols <= ld,
-              "colsum: bad shape");
+  const int vec = dtype == B200SWIN_BF16 ? 8 : 4;      // 16-byte loads
+  BSW_REQUIRE(M > 0 && ncols > 0 && ncols % vec == 0 && col0 % vec == 0 && ld % vec == 0 && col0 + ncols <= ld,
+              "colsum: columns / leading dimension must be multiples of %d (16-byte loads)", vec);
+  BSW_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "colsum: x must be 16-byte aligned");
   BSW_REQUIRE(dtype == B200SWIN_F32 || dtype == B200SWIN_BF16, "colsum: bad dtype %d", dtype);
   int rpb = colsum_rows_per_block(M, ncols);
   int nparts = (int)((M + rpb - 1) / rpb);

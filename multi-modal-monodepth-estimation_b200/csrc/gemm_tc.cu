@@ -451,16 +451,26 @@ static int operand_map(CUtensorMap* m, const void* ptr, int mn_major, int64_t mn
 
 using namespace b200swin;
 
+static int pick_bn(int64_t N) { return (N % 256 == 0 || N >= 1024) ? 256 : 128; }
+
 extern "C" int b200swin_gemm_splits(int64_t M, int64_t N, int64_t K) {
-  // split-K factor the library would pick so that the grid covers the SMs about twice
-  int64_t tiles = ((M + BM - 1) / BM) * ((N + 127) / 128);
-  int64_t num_kb = (K + BK - 1) / BK;
-  int64_t want = (2 * (int64_t)sm_count() + tiles - 1) / tiles;
-  if (want < 1) want = 1;
-  int64_t max_splits = num_kb / 8 > 0 ? num_kb / 8 : 1;      // keep >= 8 k-blocks per split
-  if (want > max_splits) want = max_splits;
-  if (want > 256) want = 256;
-  return (int)want;
+  // Split-K factor for the persistent kernel: minimise  waves x (k-blocks per split + per-tile overhead)  where a
+  // wave is one tile per SM -- i.e. prefer tile counts just BELOW a multiple of the SM count over ones just above
+  // (160 tiles on 148 SMs cost two full waves).  Smaller factors win ties (fewer fp32 partials to reduce).
+  const int64_t tiles = ((M + BM - 1) / BM) * ((N + pick_bn(N) - 1) / pick_bn(N));
+  const int64_t num_kb = (K + BK - 1) / BK;
+  const int64_t sms = sm_count();
+  int64_t max_splits = num_kb / 4 > 0 ? num_kb / 4 : 1;      // keep >= 4 k-blocks per split
+  if (max_splits > 512) max_splits = 512;
+  int64_t best = 1, best_cost = -1;
+  for (int64_t s = 1; s <= max_splits; ++s) {
+    const int64_t kb = (num_kb + s - 1) / s;
+    const int64_t eff = (num_kb + kb - 1) / kb;               // splits that actually get work
+    const int64_t waves = (tiles * eff + sms - 1) / sms;
+    const int64_t cost = waves * (kb + 8) + eff / 8;          // + a small price per partial
+    if (best_cost < 0 || cost < best_cost) { best = s; best_cost = cost; }
+  }
+  return (int)best;
 }
 
 extern "C" size_t b200swin_gemm_workspace_bytes(int64_t M, int64_t N, int splits) {
@@ -498,7 +508,7 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
                 "gemm: split-K workspace too small");
   }
   // 128x256 tiles halve the A re-reads and the smem bandwidth per MMA; 128x128 when N does not fill them
-  const int bn = (N % 256 == 0 || N >= 1024) ? 256 : 128;
+  const int bn = pick_bn(N);
   int rc;
   if ((rc = operand_map(&p.tmA[0], a_hi, a_mn_major, M, K, BM))) return rc;
   if ((rc = operand_map(&p.tmB[0], b_hi, b_mn_major, N, K, bn))) return rc;
