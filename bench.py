@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--cpu-sample-pairs", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print per-entry-point CUDA-event times to stderr")
+    ap.add_argument("--no-graph", action="store_true", help="time eager steps instead of CUDA-graph replays")
     return ap.parse_args()
 
 
@@ -160,6 +161,17 @@ def peaks():
 
 
 def run_b200(args):
+    # Everything -- eager warm-up, the eager (roofline) pass, the graph capture and its replays -- runs on ONE
+    # non-default stream: autograd binds each parameter's gradient accumulation to the stream of its first backward,
+    # and a capture on any other stream would need cross-stream syncs that invalidate it.
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        _run_b200(args, stream)
+
+
+def _run_b200(args, stream):
     import torch.distributed as dist
     from b200swin import SiLogLoss, _lib, ops
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -173,25 +185,39 @@ def run_b200(args):
     ops.ATTN_IMPL["mode"] = args.attn
     torch.manual_seed(0)                                   # identical weights on every rank
     model = DepthModel().to(dev)
-    net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
-    net.train()
+    model.train()
     crit = SiLogLoss()
-    opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=0.05, fused=True)
+    params = [p for p in model.parameters() if p.requires_grad]
+    # one flat fp32 gradient buffer: autograd accumulates into views of it, and the data-parallel exchange is ONE
+    # NCCL all-reduce (average) over NVLink -- the only collective of the path
+    flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    off = 0
+    for p in params:
+        p.grad = flat_grad[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=0.05, fused=True, capturable=True)
     P = args.pairs
     host = make_batch(P, 1234 + rank, pin=True)
-    resident = [t.to(dev) for t in host]
+    static = [t.to(dev) for t in host]                     # device-resident batch (also the CUDA graph's input)
     use_amp = args.dtype == "bf16"
 
-    def step(batch):
+    def fwd_bwd(batch):
         img1, img2, d1, d2 = batch
+        flat_grad.zero_()
         with torch.autocast("cuda", torch.bfloat16, enabled=use_amp):
-            p1, p2 = net(img1, img2)
+            p1, p2 = model(img1, img2)
         loss = (crit(p1, d1) + crit(p2, d2)) / 2                 # train.py:215-217
-        opt.zero_grad(set_to_none=True)
         loss.backward()
+        return loss
+
+    def finish():
+        if world > 1:
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
         opt.step()
+
+    def step_eager(batch):
+        loss = fwd_bwd(batch)
+        finish()
         return loss
 
     def barrier():
@@ -214,18 +240,17 @@ def run_b200(args):
             ms = t.item()
         return ms
 
-    for _ in range(max(args.warmup, 3)):
-        loss = step(resident)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        loss = step_eager(static)
     torch.cuda.synchronize(dev)
     assert torch.isfinite(loss).item(), "non-finite loss in warm-up"
 
-    # ---- device-resident timing, with live per-launch timing of the GEMM for the roofline
-    clk_path = os.path.join(tempfile.gettempdir(), f"b200swin_clocks_{rank}.csv")
-    sampler = clocks_sampler(clk_path) if rank == 0 else None
+    # ---- eager pass: launch counts and live per-launch timing of the GEMM (CUDA events on the launching stream)
     _lib.reset_counters()
     _lib.TIMING.update(name="b200swin_gemm_bf16", events=[],
                        work=lambda a: 2.0 * a[6] * a[7] * a[8] * (3 if a[1] else 1))
-    ms = timed(lambda: step(resident), args.steps)
+    ms_eager = timed(lambda: step_eager(static), args.steps)
     _lib.TIMING["name"] = None
     launches = _lib.COUNTERS["launches"]
     calls = dict(_lib.COUNTERS["calls"])
@@ -237,7 +262,7 @@ def run_b200(args):
         # diagnostic: CUDA-event time of every C-ABI entry point over one more step (not part of the JSON contract)
         _lib.reset_counters()
         _lib.TIMING.update(name="*", events=[])
-        ms1 = timed(lambda: step(resident), 1)
+        ms1 = timed(lambda: step_eager(static), 1)
         _lib.TIMING["name"] = None
         agg = {}
         for e0, e1, _, nm in _lib.TIMING["events"]:
@@ -247,10 +272,36 @@ def run_b200(args):
             print("breakdown (ms/step):", json.dumps({k: round(v, 2) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}),
                   f"sum={tot:.1f} step={ms1:.1f} other(torch ops, gaps)={ms1 - tot:.1f}", file=sys.stderr)
 
-    # ---- end to end through the public API with host buffers
+    # ---- the product path: the whole step captured once in a CUDA graph (forward, backward and -- on one GPU -- the
+    # optimizer), replayed per step; with N > 1 the all-reduce and the optimizer follow the replay
+    graph = None
+    if not args.no_graph:
+        torch.cuda.synchronize(dev)
+        ops._weight_cache.clear()                      # the bf16 staging of every weight must be part of the capture
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            g_loss = fwd_bwd(static)
+            if world == 1:
+                finish()
+
+    def step_graph():
+        graph.replay()
+        if world > 1:
+            finish()
+        return g_loss
+
+    step = step_graph if graph is not None else (lambda: step_eager(static))
+    for _ in range(2):
+        step()
+    clk_path = os.path.join(tempfile.gettempdir(), f"b200swin_clocks_{rank}.csv")
+    sampler = clocks_sampler(clk_path) if rank == 0 else None
+    ms = timed(step, args.steps)
+
+    # ---- end to end through the public API with host buffers: per step H2D copy of the batch, the step, loss read-back
     def e2e_step():
-        batch = [t.to(dev, non_blocking=True) for t in host]
-        return step(batch).item()
+        for d, h in zip(static, host):
+            d.copy_(h, non_blocking=True)
+        return step().item()
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     if sampler is not None:
@@ -265,21 +316,24 @@ def run_b200(args):
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         line = {
             "metric": "train images/sec, Swin-V2-B depth @480^2 (hot path: encoder fwd+bwd + SiLog + AdamW)",
-            "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if use_amp else "f32(split-bf16 x3)", "data": "synthetic",
             "config": {"workload": "swin_v2_base_480x480_ws12_24pairs_per_gpu_train_step(encoder+pixelshuffle_readout"
                                    "+silog_x2+adamw; decoder_v2 outside hot path, not included)",
                        "pairs_per_gpu": P, "frames_per_gpu": 2 * P, "windows": CFG["window_size"],
                        "attn_impl": args.attn, "parallelism": f"dp{world}",
+                       "execution": "cuda_graph_replay" if graph is not None else "eager",
                        "l2": "inputs+activations >> 126 MB L2 (48x3x480x480 fp32 = 133 MB images alone)"},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host),
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
             "launch_calls": calls,
+            "eager_ms_per_step": ms_eager / args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": achieved / tf_peak, "traffic": None, "kernel": "gemm_tc_kernel (all launches)",
-                         "launches": n_gemm, "kernel_ms_per_step": gemm_ms / args.steps, "peak_source": how},
+                         "launches": n_gemm, "kernel_ms_per_step": gemm_ms / args.steps, "peak_source": how,
+                         "timed_in": "eager pass of the same K steps (CUDA events around every launch)"},
             "model_flops": {"encoder_fwd_gflop_per_frame": (gemm_f + attn_f) / 1e9,
                             "step_tflops_achieved": 3 * (gemm_f + attn_f) * 2 * P / (ms / args.steps / 1e3) / 1e12},
             "clocks": clocks_summary(clk_path, local),

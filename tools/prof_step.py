@@ -1,0 +1,31 @@
+"""torch.profiler view of one bench step: which aten ops (with shapes) own the non-b200swin GPU time."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from torch.profiler import profile, ProfilerActivity
+
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+model = bench.DepthModel().to(dev).train()
+from b200swin import SiLogLoss
+crit = SiLogLoss()
+opt = torch.optim.AdamW(model.parameters(), lr=5e-4, weight_decay=0.05, fused=True)
+batch = [t.to(dev) for t in bench.make_batch(24, 1234)]
+
+def step():
+    img1, img2, d1, d2 = batch
+    with torch.autocast("cuda", torch.bfloat16):
+        p1, p2 = model(img1, img2)
+    loss = (crit(p1, d1) + crit(p2, d2)) / 2
+    opt.zero_grad(set_to_none=True)
+    loss.backward()
+    opt.step()
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
+    step()
+    torch.cuda.synchronize()
+print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=60, max_shapes_column_width=70))
