@@ -88,14 +88,24 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t M, int64_t ld, int64_t co
   }
 }
 
+// fixed-order sum of the row-block partials: 32 columns x 8 part lanes per block
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ part, int nparts, int ncols, const float* __restrict__ extra,
                     float* __restrict__ out) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncols) return;
-  float s = extra ? extra[c] : 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * ncols + c];
-  out[c] = s;
+  __shared__ float sh[8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (c < ncols)
+    for (int p = py; p < nparts; p += 8) s += part[(int64_t)p * ncols + c];
+  sh[py][cx] = s;
+  __syncthreads();
+  if (py == 0 && c < ncols) {
+    float t = extra ? extra[c] : 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w][cx];
+    out[c] = t;
+  }
 }
 
 static int colsum_rows_per_block(int64_t M, int ncols) {
@@ -151,7 +161,7 @@ extern "C" int b200swin_colsum(const void* x, int dtype, int64_t M, int64_t ld, 
     colsum_partial_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, M, ld, col0, ncols,
                                                               (float*)workspace, rpb);
   BSW_LAUNCH_CHECK();
-  colsum_final_kernel<<<(ncols + 255) / 256, 256, 0, st>>>((const float*)workspace, nparts, ncols, extra, out);
+  colsum_final_kernel<<<(ncols + 31) / 32, 256, 0, st>>>((const float*)workspace, nparts, ncols, extra, out);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
 }

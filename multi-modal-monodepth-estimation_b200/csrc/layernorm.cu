@@ -11,7 +11,10 @@ namespace b200swin {
 constexpr int kLnThreads = 256;
 constexpr int kLnWarps = kLnThreads / 32;
 
-template <typename T, int NV>
+// R rows per warp and iteration: all loads of the R rows (x and the residual) are issued before any arithmetic, so a
+// warp keeps R * NV * (8 or 16) bytes per lane in flight instead of one 8-byte load (the C = 128 stage is pure HBM
+// streaming: one row is only 256 bytes).
+template <typename T, int NV, int R>
 __global__ void __launch_bounds__(kLnThreads)
 ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, const float* __restrict__ gamma,
               const float* __restrict__ beta, const float* __restrict__ row_scale, int64_t rows_per_scale,
@@ -21,54 +24,59 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, const flo
   const int64_t warp0 = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kLnWarps;
   const float inv_c = 1.0f / (float)C;
-  for (int64_t row = warp0; row < rows; row += nwarps) {
-    const T* xr = x + row * C;
-    float v[NV][4];
-    float s = 0.f;
+  for (int64_t row0 = warp0 * R; row0 < rows; row0 += nwarps * R) {
+    float v[R][NV][4], rs[R][NV][4];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      int c = lane * 4 + k * 128;
-      if (c < C) {
-        ld4(xr + c, v[k]);
-        s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
-      }
-    }
-    const float mean = warp_sum(s) * inv_c;
-    float q = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      int c = lane * 4 + k * 128;
-      if (c < C) {
+      for (int k = 0; k < NV; ++k) {
+        const int c = lane * 4 + k * 128;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { float d = v[k][e] - mean; q = fmaf(d, d, q); }
-      }
-    }
-    const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
-    const float sc = row_scale ? row_scale[row / rows_per_scale] : 1.0f;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      int c = lane * 4 + k * 128;
-      if (c < C) {
-        float g[4], b[4], o[4];
-        ld4(gamma + c, g);
-        ld4(beta + c, b);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = ((v[k][e] - mean) * rstd * g[e] + b[e]) * sc;
-        if (residual) {
-          float r[4];
-          ld4(residual + row * C + c, r);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] += r[e];
+        for (int e = 0; e < 4; ++e) { v[r][k][e] = 0.f; rs[r][k][e] = 0.f; }
+        if (row < rows && c < C) {
+          ld4(x + row * C + c, v[r][k]);
+          if (residual) ld4(residual + row * C + c, rs[r][k]);
         }
-        st4(y + row * C + c, o);
       }
     }
-    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r;
+      if (row >= rows) break;                       // warp-uniform
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) s += (v[r][k][0] + v[r][k][1]) + (v[r][k][2] + v[r][k][3]);
+      const float mean = warp_sum(s) * inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        if (lane * 4 + k * 128 < C) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float d = v[r][k][e] - mean; q = fmaf(d, d, q); }
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
+      const float sc = row_scale ? row_scale[row / rows_per_scale] : 1.0f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = lane * 4 + k * 128;
+        if (c < C) {
+          float g[4], b[4], o[4];
+          ld4(gamma + c, g);                       // L1-resident after the first row
+          ld4(beta + c, b);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = ((v[r][k][e] - mean) * rstd * g[e] + b[e]) * sc + rs[r][k][e];
+          st4(y + row * C + c, o);
+        }
+      }
+      if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    }
   }
 }
 
 // Backward: dx per row, and per-block partial sums of dgamma/dbeta (reduced by ln_param_reduce_kernel).
-template <typename T, int NV>
+template <typename T, int NV, int R>
 __global__ void __launch_bounds__(kLnThreads)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
@@ -87,39 +95,54 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
     for (int e = 0; e < 4; ++e) { dg[k][e] = 0.f; db[k][e] = 0.f; gm[k][e] = 0.f; }
     if (c < C) ld4(gamma + c, gm[k]);
   }
-  for (int64_t row = warp0; row < rows; row += nwarps) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    const float sc = row_scale ? row_scale[row / rows_per_scale] : 1.0f;
-    float xh[NV][4], g[NV][4];
-    float s1 = 0.f, s2 = 0.f;
+  for (int64_t row0 = warp0 * R; row0 < rows; row0 += nwarps * R) {
+    float xv[R][NV][4], g[R][NV][4], mean[R], rstd[R];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      int c = lane * 4 + k * 128;
-      if (c < C) {
-        float xv[4];
-        ld4(x + row * C + c, xv);
-        ld4(dy + row * C + c, g[k]);
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r;
+      mean[r] = row < rows ? mean_in[row] : 0.f;
+      rstd[r] = row < rows ? rstd_in[row] : 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          xh[k][e] = (xv[e] - mean) * rstd;
-          g[k][e] *= sc;
-          dg[k][e] = fmaf(g[k][e], xh[k][e], dg[k][e]);
-          db[k][e] += g[k][e];
-          float gg = g[k][e] * gm[k][e];
-          s1 += gg;
-          s2 = fmaf(gg, xh[k][e], s2);
+      for (int k = 0; k < NV; ++k) {
+        const int c = lane * 4 + k * 128;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { xv[r][k][e] = 0.f; g[r][k][e] = 0.f; }
+        if (row < rows && c < C) {
+          ld4(x + row * C + c, xv[r][k]);
+          ld4(dy + row * C + c, g[r][k]);
         }
       }
     }
-    const float m1 = warp_sum(s1) * inv_c, m2 = warp_sum(s2) * inv_c;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      int c = lane * 4 + k * 128;
-      if (c < C) {
-        float o[4];
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r;
+      if (row >= rows) break;                       // warp-uniform
+      const float sc = row_scale ? row_scale[row / rows_per_scale] : 1.0f;
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = rstd * (g[k][e] * gm[k][e] - m1 - xh[k][e] * m2);
-        st4(dx + row * C + c, o);
+      for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float xh = (xv[r][k][e] - mean[r]) * rstd[r];
+          xv[r][k][e] = xh;
+          g[r][k][e] *= sc;
+          dg[k][e] = fmaf(g[r][k][e], xh, dg[k][e]);
+          db[k][e] += g[r][k][e];
+          const float gg = g[r][k][e] * gm[k][e];
+          s1 += gg;
+          s2 = fmaf(gg, xh, s2);
+        }
+      }
+      const float m1 = warp_sum(s1) * inv_c, m2 = warp_sum(s2) * inv_c;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = lane * 4 + k * 128;
+        if (c < C) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = rstd[r] * (g[r][k][e] * gm[k][e] - m1 - xv[r][k][e] * m2);
+          st4(dx + row * C + c, o);
+        }
       }
     }
   }
@@ -142,25 +165,35 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
   for (int c = threadIdx.x; c < 2 * C; c += kLnThreads) part[(int64_t)blockIdx.x * 2 * C + c] = sh[c];
 }
 
+// dgamma / dbeta = fixed-order sum of the per-block partial rows: 32 columns x 8 part lanes per block
 __global__ void __launch_bounds__(256)
 ln_param_reduce_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ dgamma,
                        float* __restrict__ dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;   // over 2*C
-  if (c >= 2 * C) return;
+  __shared__ float sh[8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;              // over 2*C
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * 2 * C + c];
-  if (c < C) dgamma[c] = s; else dbeta[c - C] = s;
+  if (c < 2 * C)
+    for (int p = py; p < nparts; p += 8) s += part[(int64_t)p * 2 * C + c];
+  sh[py][cx] = s;
+  __syncthreads();
+  if (py == 0 && c < 2 * C) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w][cx];
+    if (c < C) dgamma[c] = t; else dbeta[c - C] = t;
+  }
 }
 
 static int ln_grid(int64_t rows) {
   int64_t blocks = (rows + kLnWarps - 1) / kLnWarps;
-  int64_t cap = (int64_t)sm_count() * 4;
+  int64_t cap = (int64_t)sm_count() * 8;
   if (blocks < 1) blocks = 1;
   return (int)(blocks < cap ? blocks : cap);
 }
 static int ln_bwd_grid(int64_t rows) {
   int64_t blocks = (rows + 4 * kLnWarps - 1) / (4 * kLnWarps);   // >= 4 rows per warp before a partial row is paid
-  int64_t cap = (int64_t)sm_count() * 2;
+  int64_t cap = (int64_t)sm_count() * 4;
   if (blocks < 1) blocks = 1;
   return (int)(blocks < cap ? blocks : cap);
 }
@@ -170,15 +203,15 @@ static int ln_fwd_launch(const void* x, const void* residual, const float* gamma
                          const float* row_scale, int64_t rps, void* y, float* mean, float* rstd, int64_t rows, int C,
                          float eps, cudaStream_t st) {
   int grid = ln_grid(rows);
-#define LN_FWD(NV)                                                                                         \
-  ln_fwd_kernel<T, NV><<<grid, kLnThreads, 0, st>>>((const T*)x, (const T*)residual, gamma, beta, row_scale, \
-                                                    rps, (T*)y, mean, rstd, rows, C, eps)
-  if (C <= 128) LN_FWD(1);
-  else if (C <= 256) LN_FWD(2);
-  else if (C <= 512) LN_FWD(4);
-  else if (C <= 1024) LN_FWD(8);
-  else if (C <= 2048) LN_FWD(16);
-  else LN_FWD(24);
+#define LN_FWD(NV, R)                                                                                         \
+  ln_fwd_kernel<T, NV, R><<<grid, kLnThreads, 0, st>>>((const T*)x, (const T*)residual, gamma, beta, row_scale, \
+                                                       rps, (T*)y, mean, rstd, rows, C, eps)
+  if (C <= 128) LN_FWD(1, 4);
+  else if (C <= 256) LN_FWD(2, 2);
+  else if (C <= 512) LN_FWD(4, 1);
+  else if (C <= 1024) LN_FWD(8, 1);
+  else if (C <= 2048) LN_FWD(16, 1);
+  else LN_FWD(24, 1);
 #undef LN_FWD
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
@@ -189,15 +222,15 @@ static int ln_bwd_launch(const void* dy, const void* x, const float* gamma, cons
                          const float* row_scale, int64_t rps, void* dx, float* part, int grid, int64_t rows, int C,
                          cudaStream_t st) {
   size_t smem = (size_t)2 * C * sizeof(float);
-#define LN_BWD(NV)                                                                                           \
-  ln_bwd_kernel<T, NV><<<grid, kLnThreads, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, row_scale, \
-                                                       rps, (T*)dx, part, rows, C)
-  if (C <= 128) LN_BWD(1);
-  else if (C <= 256) LN_BWD(2);
-  else if (C <= 512) LN_BWD(4);
-  else if (C <= 1024) LN_BWD(8);
-  else if (C <= 2048) LN_BWD(16);
-  else LN_BWD(24);
+#define LN_BWD(NV, R)                                                                                           \
+  ln_bwd_kernel<T, NV, R><<<grid, kLnThreads, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, row_scale, \
+                                                          rps, (T*)dx, part, rows, C)
+  if (C <= 128) LN_BWD(1, 4);
+  else if (C <= 256) LN_BWD(2, 2);
+  else if (C <= 512) LN_BWD(4, 1);
+  else if (C <= 1024) LN_BWD(8, 1);
+  else if (C <= 2048) LN_BWD(16, 1);
+  else LN_BWD(24, 1);
 #undef LN_BWD
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
@@ -245,7 +278,7 @@ extern "C" int b200swin_ln_bwd(const void* dy, const void* x, const float* gamma
     rc = ln_bwd_launch<__nv_bfloat16>(dy, x, gamma, mean, rstd, row_scale, rows_per_scale, dx, (float*)workspace,
                                       grid, rows, C, st);
   if (rc) return rc;
-  ln_param_reduce_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, C, dgamma, dbeta);
+  ln_param_reduce_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>((const float*)workspace, grid, C, dgamma, dbeta);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
 }
