@@ -111,7 +111,13 @@ struct Cfg {
                                    (MT > 1 ? 16 * (size_t)NPAD * 4 : 0) /* tail bias-gradient sums */ +
                                    (size_t)DVP_ROWS * DVP_LD * 4 + 1024 + 64;
   static constexpr int NSTAGE_RAW = (int)((227 * 1024 - kFixed) / kStage);
-  static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : NSTAGE_RAW;
+// Ring depth is capped at 2.  KNOWN ISSUE (round 1): with a 4-deep ring (small windows, where it fits) the dK rows of
+// the first keys of a window were sporadically wrong at full size (tools/diag_attn.py 48 12 1024 6 0); depth 2 is
+// clean in every full-size cross-check (tests/test_attention_gpu.py::test_full_size_...).  Not yet explained.
+#ifndef BSW_BWD_MAX_STAGES
+#define BSW_BWD_MAX_STAGES 2
+#endif
+  static constexpr int NSTAGE = NSTAGE_RAW > BSW_BWD_MAX_STAGES ? BSW_BWD_MAX_STAGES : NSTAGE_RAW;
   static_assert(NSTAGE >= 2, "shared memory budget");
   static constexpr size_t kSmem = kFixed + (size_t)NSTAGE * kStage;
 };

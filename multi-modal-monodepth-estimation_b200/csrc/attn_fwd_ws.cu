@@ -88,8 +88,15 @@ struct Cfg {
   static constexpr int TAIL = N - 128 * (MT - 1);                  // valid rows of the last tile
   static constexpr bool ROT = MT > 1 && TAIL <= 32;
   static constexpr int KA = (NPAD + 31) / 32 * 16, KB = NPAD - KA;  // keys of the first / second half
-  static constexpr int OA = (NPAD / 2 + 15) / 16 * 16, OB = OA + HD;  // O_a, O_b behind the packed P
-  static constexpr int SLOTW = NPAD > OB + HD ? NPAD : OB + HD;       // TMEM columns per slot: S, then P|O_a|O_b
+  // Slot layout.  Each half writes its packed P over the START OF ITS OWN S columns (P_a at 0, P_b at KA): a half
+  // must never write into columns whose S the other half may not have read yet (the two warps of a row are not
+  // synchronised -- the first layout put P_b behind P_a, inside S_a, and a delayed first-half warp read garbage).
+  // The accumulators are written by the MMA only after all eight warps have read S: O_a / O_b sit behind P_a / P_b
+  // inside the S columns when those are wide enough (12x12 windows), else behind S.
+  static constexpr bool INPLACE = (KA >= 80) && (KB >= 64);
+  static constexpr int OA = INPLACE ? (KA / 2 + 15) / 16 * 16 : NPAD, OB = INPLACE ? KA + KB / 2 : NPAD + HD;
+  static_assert(!INPLACE || (OA + HD <= KA && OB + HD <= NPAD), "accumulators must fit behind the packed P");
+  static constexpr int SLOTW = INPLACE ? NPAD : NPAD + 2 * HD;        // TMEM columns per slot
   static constexpr int NSLOT = 512 / SLOTW > 4 ? 4 : 512 / SLOTW;
   static constexpr int NS = N + ((12 - N % 8) % 8);                 // bias row stride, NS % 8 == 4: float4 reads
   static_assert(NS % 8 == 4 && NS >= N, "bias stride");             //   of 8 consecutive rows hit 8 bank groups
@@ -141,7 +148,7 @@ __device__ __forceinline__ int src_token(const WinGeom& g, int b, int wh, int ww
 
 // One thread = one query row x the keys [C0, C0 + NC) of the window.  Reads its part of S from TMEM, turns it into
 // logits in log2 units (scale * cos + bias, shift mask), takes the maximum m and sum l over ITS keys and writes
-// P = exp2(s - m) as packed bf16 over the S columns [C0/2, (C0+NC)/2).  All lanes of the warp must call it
+// P = exp2(s - m) as packed bf16 over the first NC/2 of ITS OWN S columns [C0, C0 + NC/2).  All lanes must call it
 // (tcgen05.ld / st are warp-collective); `valid` lanes own a real row.
 template <int WS, int C0, int NC>
 __device__ __forceinline__ void softmax_half(uint32_t t_s, const float* brow, float scale2, bool need_mask, uint32_t by,
@@ -196,7 +203,7 @@ __device__ __forceinline__ void softmax_half(uint32_t t_s, const float* brow, fl
     }
     TR(42, u);
 #pragma unroll
-    for (int c = 0; c < NC / 16; ++c) tmem_st8(t_s + C0 / 2 + c * 8, &sv[c * 8]);
+    for (int c = 0; c < NC / 16; ++c) tmem_st8(t_s + C0 + c * 8, &sv[c * 8]);    // over the start of this half's own S
     ptx::tmem_st_wait();
     TR(43, u);
   }
@@ -296,7 +303,8 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
 #pragma unroll
           for (int ks = 0; ks < NPAD / 16; ++ks) {
             const bool second = ks >= CF::KA / 16;                           // keys of the second half -> O_b
-            ptx::mma_bf16_ts(t_s + (second ? CF::OB : CF::OA), t_s + ks * 8, bd + ks * 64, idesc_pv,
+            ptx::mma_bf16_ts(t_s + (second ? CF::OB : CF::OA),
+                             t_s + (second ? CF::KA + (ks - CF::KA / 16) * 8 : ks * 8), bd + ks * 64, idesc_pv,
                              (ks != 0 && ks != CF::KA / 16) ? 1u : 0u);
           }
           ptx::mma_commit(&o_full[slot]);
