@@ -261,12 +261,22 @@ def _run_b200(args, stream):
     if args.breakdown:
         # diagnostic: CUDA-event time of every C-ABI entry point over one more step (not part of the JSON contract)
         _lib.reset_counters()
-        _lib.TIMING.update(name="*", events=[])
+        _lib.TIMING.update(name="*", events=[], detail=True)
         ms1 = timed(lambda: step_eager(static), 1)
         _lib.TIMING["name"] = None
-        agg = {}
+        _lib.TIMING["detail"] = False
+        agg, gem = {}, {}
         for e0, e1, _, nm in _lib.TIMING["events"]:
-            agg[nm] = agg.get(nm, 0.0) + e0.elapsed_time(e1)
+            t = e0.elapsed_time(e1)
+            if nm.startswith("gemm "):
+                c = gem.setdefault(nm, [0, 0.0])
+                c[0] += 1
+                c[1] += t
+                nm = "b200swin_gemm_bf16"
+            agg[nm] = agg.get(nm, 0.0) + t
+        if rank == 0:
+            for k, (n, t) in sorted(gem.items(), key=lambda kv: -kv[1][1])[:40]:
+                print(f"  {t:7.3f} ms  x{n:3d}  {k}", file=sys.stderr)
         if rank == 0:
             tot = sum(agg.values())
             print("breakdown (ms/step):", json.dumps({k: round(v, 2) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}),

@@ -32,9 +32,9 @@ extern "C" {
 
 /* GEMM epilogues (b200swin_linear) */
 #define B200SWIN_EPI_NONE 0     /* out = acc (+ bias)                                   */
-#define B200SWIN_EPI_GELU 1     /* out = gelu_erf(acc + bias); aux (optional) = acc+bias */
+#define B200SWIN_EPI_GELU 1     /* out = gelu_erf(acc + bias); aux (optional) = gelu'(acc+bias) */
 #define B200SWIN_EPI_QKV 2      /* Swin-V2 qkv: + (q_bias,0,v_bias), L2-normalise q,k per head */
-#define B200SWIN_EPI_DGELU 3    /* out = (acc) * gelu'(aux)                              */
+#define B200SWIN_EPI_DGELU 3    /* out = acc * aux_in   (aux_in = the gelu' saved by EPI_GELU) */
 
 int b200swin_version(void);
 const char* b200swin_last_error(void);
@@ -133,8 +133,8 @@ int b200swin_attn_bwd(const void* qkv, const void* out, const void* dout, const 
  *    b_mn_major = 1, wgrad (dW = dY^T.X) passes dY and X with both = 1: no transposed copy is made.
  *  - a_lo / b_lo (both or neither): low bf16 halves from b200swin_split_bf16; the kernel then
  *    accumulates hi.hi + hi.lo + lo.hi, which reproduces an fp32 GEMM to ~1e-5 relative.
- *  - epilogue (B200SWIN_EPI_*): NONE: + bias[N] (nullable).  GELU: + bias, aux_out (nullable) receives
- *    the pre-activation, out = erf-GELU.  DGELU: out = acc * gelu'(aux_in).  QKV: N = 3C; adds bias
+ *  - epilogue (B200SWIN_EPI_*): NONE: + bias[N] (nullable).  GELU: + bias, out = erf-GELU, aux_out (nullable)
+ *    receives gelu'(pre-activation).  DGELU: out = acc * aux_in (that saved derivative).  QKV: N = 3C; adds bias
  *    (= q_bias[C]) to the q columns, nothing to k, bias2 (= v_bias[C]) to v; L2-normalises every
  *    32-wide head slice of q and k in fp32 (F.normalize, eps 1e-12, :292-293) and writes
  *    inv_norm[M,2,nH] = 1/max(|q|,eps), 1/max(|k|,eps) (nullable).

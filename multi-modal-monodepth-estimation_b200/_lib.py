@@ -103,8 +103,13 @@ def _wrap(name, fn):
             e0.record(st)
             rc = fn(*args)
             e1.record(st)
+            tag = name
+            if name == "b200swin_gemm_bf16" and TIMING.get("detail"):
+                # (a_mn, b_mn, M, N, K, epilogue, splits)
+                tag = "gemm a_mn=%d b_mn=%d M=%d N=%d K=%d epi=%d splits=%d" % (args[2], args[5], args[6], args[7], args[8],
+                                                                              args[9], args[18])
             TIMING["events"].append((e0, e1, TIMING["work"](args) if (TIMING["work"] and name == "b200swin_gemm_bf16")
-                                     else 0.0, name))
+                                     else 0.0, tag))
             return rc
         return fn(*args)
 

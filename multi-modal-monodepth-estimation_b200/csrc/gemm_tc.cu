@@ -13,8 +13,9 @@
 //   registers, stage 32-row x 64-byte units in shared memory (64 B swizzle, conflict-free) and hand them to
 //   TMA stores (cp.async.bulk.tensor ... bulk_group), so HBM sees full-sector row writes and the M/N edges are
 //   clipped by the tensor map:
-//     NONE  (+bias) | GELU (bias, erf GELU, optional pre-activation copy) | QKV (q_bias/0/v_bias, per-head
-//     L2-normalisation of q and k in fp32 + 1/|q|,1/|k| side output) | DGELU (multiply by gelu'(aux));
+//     NONE  (+bias) | GELU (bias, exact-erf GELU, side output gelu'(pre-activation) for the backward) | QKV
+//     (q_bias/0/v_bias, per-head L2-normalisation of q and k in fp32 + 1/|q|,1/|k| side output) | DGELU (multiply
+//     by the saved gelu', whose tile is prefetched by TMA);
 // * either operand may be "MN-major" (stored [K][M] / [K][N]), which is how dgrad (B = W as stored) and wgrad
 //   (A = dY, B = X as stored) run WITHOUT any transposed copy in HBM;
 // * fp32-accurate mode: operands split as hi+lo bf16 pairs, 3 MMAs per k-step (hi.hi + hi.lo + lo.hi);
@@ -48,6 +49,7 @@ constexpr float kInvSqrt2Pi = 0.39894228040143268f;
 struct GemmParams {
   CUtensorMap tmA[2], tmB[2];
   CUtensorMap tmOut, tmAux;                 // store maps: box {64 B of columns, 32 rows}, SWIZZLE_64B
+  CUtensorMap tmAuxIn;                      // load map of aux_in (bf16 MUL epilogue), same box
   int nseg;
   int64_t M, N, K;
   int num_kb, kb_per_split, splits;
@@ -66,9 +68,25 @@ struct GemmParams {
   int64_t m_pad;
 };
 
-__device__ __forceinline__ float gelu_erf(float z) { return 0.5f * z * (1.0f + erff(z * kInvSqrt2)); }
-__device__ __forceinline__ float gelu_grad(float z) {
-  return 0.5f * (1.0f + erff(z * kInvSqrt2)) + z * kInvSqrt2Pi * __expf(-0.5f * z * z);
+// Exact-erf GELU and its derivative from ONE exponential and ONE reciprocal (the libdevice erff + expf pair cost
+// more issue slots than the MMAs of a 128x256 tile at K = 512):
+//   erf(x) = sign(x) (1 - (a1 t + ... + a5 t^5) exp(-x^2)),  t = 1 / (1 + p |x|)      (Abramowitz-Stegun 7.1.26,
+//   |error| <= 1.5e-7 -- fp32 rounding level), and exp(-x^2) with x = z / sqrt(2) is also the Gaussian of gelu'.
+//   h = z Phi(z),   g = gelu'(z) = Phi(z) + z phi(z),   Phi = (1 + erf(z / sqrt 2)) / 2,  phi = exp(-z^2/2) / sqrt(2 pi)
+__device__ __forceinline__ void gelu_pair(float z, float& h, float& g) {
+  const float ax = fabsf(z) * kInvSqrt2;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -0.72134752044448170f));     // exp(-z^2 / 2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float half_erfc = 0.5f * poly * e;                      // (1 - erf|x|) / 2
+  const float Phi = z >= 0.f ? 1.0f - half_erfc : half_erfc;
+  h = z * Phi;
+  g = fmaf(z * kInvSqrt2Pi, e, Phi);
 }
 
 // Per-warp staging ring for the TMA-store epilogue.  A unit is 32 rows x 64 B with the 64-byte swizzle
@@ -78,11 +96,14 @@ struct Stager {
   uint32_t base;       // shared address of this warp's kEpiBufs units
   uint32_t slot;       // units issued so far
   int lane;
+  bool half_ring;      // MUL epilogue: units 2, 3 of the warp receive the prefetched aux tile; stores use units 0, 1
 
   __device__ __forceinline__ uint32_t acquire() {
-    if (lane == 0) ptx::bulk_wait_read<kEpiBufs - 1>();    // the store that last used this unit has read it
+    if (lane == 0) {                                       // the store that last used this unit has read it
+      if (half_ring) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<kEpiBufs - 1>();
+    }
     __syncwarp();
-    return base + (slot % kEpiBufs) * kEpiUnitBytes;
+    return base + (slot % (half_ring ? 2 : kEpiBufs)) * kEpiUnitBytes;
   }
   __device__ __forceinline__ void piece(uint32_t unit, int j, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     const uint32_t addr = unit + (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
@@ -159,26 +180,46 @@ __device__ __forceinline__ void add_bias32(float (&v)[32], const float* __restri
 // `valid_row`: this thread's row exists (row < M); rows beyond M still take part in the staging (the store clips).
 template <typename OutT>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, Stager& st, float (&v)[32], int64_t row, int row0,
-                                               int col0, int nvalid, bool valid_row) {
+                                               int col0, int nvalid, bool valid_row, uint32_t aux_unit) {
   if (p.epilogue == B200SWIN_EPI_NONE) {
     if (p.bias) add_bias32(v, p.bias + col0, nvalid);
     store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
   } else if (p.epilogue == B200SWIN_EPI_GELU) {
     if (p.bias) add_bias32(v, p.bias + col0, nvalid);
-    if (p.aux_out) store_chunk<OutT>(st, &p.tmAux, v, col0, row0, p.N);
+    float g[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) v[c] = gelu_erf(v[c]);
+    for (int c = 0; c < 32; ++c) gelu_pair(v[c], v[c], g[c]);
+    if (p.aux_out) store_chunk<OutT>(st, &p.tmAux, g, col0, row0, p.N);
     store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
   } else if (p.epilogue == B200SWIN_EPI_DGELU) {
-    float z[32];
-    if (valid_row) {
-      load_chunk32<OutT>(reinterpret_cast<const OutT*>(p.aux_in) + row * p.ldo + col0, z, nvalid);
+    if constexpr (sizeof(OutT) == 2) {
+      // the aux chunk (32 rows x 64 B) was prefetched by TMA into `aux_unit` (same swizzle as the store units)
+      const uint32_t rowaddr = aux_unit + (uint32_t)st.lane * 64u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t w0, w1, w2, w3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                     : "r"(rowaddr + (uint32_t)((j ^ ((st.lane >> 1) & 3)) << 4)));
+        const uint32_t ww[4] = {w0, w1, w2, w3};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+          v[8 * j + 2 * e] *= f.x;
+          v[8 * j + 2 * e + 1] *= f.y;
+        }
+      }
     } else {
+      float z[32];
+      if (valid_row) {
+        load_chunk32<OutT>(reinterpret_cast<const OutT*>(p.aux_in) + row * p.ldo + col0, z, nvalid);
+      } else {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) z[c] = 0.f;
+        for (int c = 0; c < 32; ++c) z[c] = 0.f;
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] *= z[c];
     }
-#pragma unroll
-    for (int c = 0; c < 32; ++c) v[c] *= gelu_grad(z[c]);
     store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
   } else {  // B200SWIN_EPI_QKV: one 32-column chunk == one head of q, k or v  (swin_transformer_v2.py:283-293)
     const int part = col0 / p.Cq;
@@ -208,6 +249,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
+  __shared__ __align__(8) uint64_t aux_bar[4][2];          // per epilogue warp: arrival of a prefetched aux unit
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = (ptx::smem_u32(smem_dyn) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024 B alignment
@@ -217,6 +259,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&aux_bar[i >> 1][i & 1], 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&p.tmA[0]);
     ptx::prefetch_tmap(&p.tmB[0]);
@@ -313,9 +356,38 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     // -------------------------------------------------------------------- epilogue warps (TMEM -> smem -> TMA store)
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     Stager st;
-    st.base = smem_base + (uint32_t)STAGES * TL::kStageBytes + (uint32_t)q * (kEpiBufs * kEpiUnitBytes);
+    const uint32_t epi_off = (uint32_t)STAGES * TL::kStageBytes + (uint32_t)q * (kEpiBufs * kEpiUnitBytes);
+    st.base = smem_base + epi_off;
     st.slot = 0;
     st.lane = lane;
+    // bf16 MUL epilogue (dgrad of fc2 times gelu'): the aux chunk of unit k+1 is fetched by TMA into staging units
+    // 2, 3 of this warp while unit k is processed -- coalesced, instead of 32 scattered 64-byte row reads per chunk
+    const bool pf = p.epilogue == B200SWIN_EPI_DGELU && p.out_dtype == B200SWIN_BF16 && !p.partial;
+    st.half_ring = pf;
+    auto slab_exists = [&](int64_t t) { int mb, nb, z; decode(t, mb, nb, z); return mb * BM + q * 32 < p.M; };
+    auto first_valid = [&](int64_t t) { while (t < p.num_tiles && !slab_exists(t)) t += gridDim.x; return t; };
+    auto next_unit = [&](int64_t& t, int& c) {
+      int mb, nb, z;
+      decode(t, mb, nb, z);
+      ++c;
+      if (c == BN / 32 || nb * BN + c * 32 >= p.N) { c = 0; t = first_valid(t + gridDim.x); }
+    };
+    auto prefetch = [&](int64_t t, int c, uint32_t k) {
+      if (lane == 0) {
+        int mb, nb, z;
+        decode(t, mb, nb, z);
+        ptx::mbar_arrive_expect_tx(&aux_bar[q][k & 1], kEpiUnitBytes);
+        ptx::tma_load_2d(smem_al + epi_off + (2 + (k & 1)) * kEpiUnitBytes, &p.tmAuxIn, &aux_bar[q][k & 1], nb * BN + c * 32,
+                         mb * BM + q * 32);
+      }
+    };
+    int64_t pt = first_valid(blockIdx.x);          // prefetch cursor: one unit ahead of the processing loop
+    int pc = 0;
+    uint32_t k = 0;                                // units processed by this warp
+    if (pf && pt < p.num_tiles) {
+      prefetch(pt, pc, 0);
+      next_unit(pt, pc);
+    }
     uint32_t tcount = 0;
     for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
       int mb, nb, z;
@@ -330,6 +402,16 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         for (int c = 0; c < BN / 32; ++c) {
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) break;                  // warp-uniform
+          uint32_t aux_unit = 0;
+          if (pf) {
+            __syncwarp();                          // every lane has finished reading the unit fetched two units ago
+            if (pt < p.num_tiles) {
+              prefetch(pt, pc, k + 1);
+              next_unit(pt, pc);
+            }
+            ptx::mbar_wait(&aux_bar[q][k & 1], (k >> 1) & 1);
+            aux_unit = st.base + (2 + (k & 1)) * kEpiUnitBytes;
+          }
           float v[32];
           {
             uint32_t r[32];
@@ -342,10 +424,11 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           if (p.partial) {
             store_chunk<float>(st, &p.tmOut, v, col0, (int)((int64_t)z * p.m_pad) + m0, p.N);
           } else if (p.out_dtype == B200SWIN_BF16) {
-            epilogue_chunk<__nv_bfloat16>(p, st, v, row, m0, col0, nvalid, row < p.M);
+            epilogue_chunk<__nv_bfloat16>(p, st, v, row, m0, col0, nvalid, row < p.M, aux_unit);
           } else {
-            epilogue_chunk<float>(p, st, v, row, m0, col0, nvalid, row < p.M);
+            epilogue_chunk<float>(p, st, v, row, m0, col0, nvalid, row < p.M, 0u);
           }
+          ++k;
         }
       }
       ptx::tc_fence_before();
@@ -535,6 +618,9 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   } else {
     if ((rc = store_map(&p.tmOut, out, out_dtype, M, N))) return rc;
     if (aux_out && (rc = store_map(&p.tmAux, aux_out, out_dtype, M, N))) return rc;
+    if (epilogue == B200SWIN_EPI_DGELU && out_dtype == B200SWIN_BF16 &&
+        (rc = store_map(&p.tmAuxIn, aux_in, B200SWIN_BF16, M, N)))
+      return rc;
   }
 
   cudaStream_t st = (cudaStream_t)stream;

@@ -329,7 +329,8 @@ def linear(x, weight, bias=None):
 
 
 class _Mlp(torch.autograd.Function):
-    """fc2(GELU(fc1(x))) with the GELU fused into fc1's epilogue and gelu' fused into fc2's dgrad epilogue
+    """fc2(GELU(fc1(x))) with the GELU fused into fc1's epilogue -- which also emits gelu'(pre-activation) for the
+    backward -- and the multiplication by that derivative fused into fc2's dgrad epilogue
     (reference: Mlp.forward, swin_transformer_v2.py:76-89; exact-erf GELU)."""
 
     @staticmethod
