@@ -160,6 +160,19 @@ def peaks():
     return 1400.0, 6650.0, "fallback"
 
 
+def gemm_traffic():
+    """DRAM bytes of one representative launch of the dominant kernel, from the committed ncu --set full capture."""
+    f = os.path.join(ROOT, "profiles", "r01_ncu_gemm_tc_r01.json")
+    try:
+        d = json.load(open(f))
+        rd, wr = float(d["dram_read"].split()[0]), float(d["dram_write"].split()[0])      # Mbyte
+        M, N, K = 43200, 512, 2048
+        return {"launch": "gemm_tc_kernel M=43200 N=512 K=2048 (stage-2 fc2 forward)", "dram_bytes": (rd + wr) * 1e6,
+                "algorithmic_bytes": 2.0 * (M * K + N * K + M * N), "source": "profiles/r01_ncu_gemm_tc_r01.json"}
+    except Exception:
+        return None
+
+
 def run_b200(args):
     # Everything -- eager warm-up, the eager (roofline) pass, the graph capture and its replays -- runs on ONE
     # non-default stream: autograd binds each parameter's gradient accumulation to the stream of its first backward,
@@ -341,7 +354,7 @@ def _run_b200(args, stream):
             "launch_calls": calls,
             "eager_ms_per_step": ms_eager / args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf_peak, "traffic": None, "kernel": "gemm_tc_kernel (all launches)",
+                         "frac": achieved / tf_peak, "traffic": gemm_traffic(), "kernel": "gemm_tc_kernel (all launches)",
                          "launches": n_gemm, "kernel_ms_per_step": gemm_ms / args.steps, "peak_source": how,
                          "timed_in": "eager pass of the same K steps (CUDA events around every launch)"},
             "model_flops": {"encoder_fwd_gflop_per_frame": (gemm_f + attn_f) / 1e9,
