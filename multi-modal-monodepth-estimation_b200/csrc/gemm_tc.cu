@@ -9,13 +9,13 @@
 // * one elected thread issues tcgen05.mma (M=128, N=128|256, K=16 per instruction) into one of TWO TMEM
 //   accumulators; tcgen05.commit releases smem stages and signals the epilogue, which drains accumulator i
 //   while the tensor pipe fills accumulator i^1;
-// * 4 epilogue warps read the accumulator with tcgen05.ld (one row per thread), apply the fused epilogue in
+// * 16 epilogue warps read the accumulator with tcgen05.ld (one row per thread), apply the fused epilogue in
 //   registers, stage 32-row x 64-byte units in shared memory (64 B swizzle, conflict-free) and hand them to
 //   TMA stores (cp.async.bulk.tensor ... bulk_group), so HBM sees full-sector row writes and the M/N edges are
 //   clipped by the tensor map:
 //     NONE  (+bias) | GELU (bias, exact-erf GELU, side output gelu'(pre-activation) for the backward) | QKV
 //     (q_bias/0/v_bias, per-head L2-normalisation of q and k in fp32 + 1/|q|,1/|k| side output) | DGELU (multiply
-//     by the saved gelu', whose tile is prefetched by TMA);
+//     by the saved gelu', read straight from global memory while the accumulator load is in flight);
 // * either operand may be "MN-major" (stored [K][M] / [K][N]), which is how dgrad (B = W as stored) and wgrad
 //   (A = dY, B = X as stored) run WITHOUT any transposed copy in HBM;
 // * fp32-accurate mode: operands split as hi+lo bf16 pairs, 3 MMAs per k-step (hi.hi + hi.lo + lo.hi);
@@ -28,12 +28,16 @@ namespace b200swin {
 
 namespace {
 constexpr int BM = 128, BK = 64;
-constexpr int kGemmThreads = 192;                       // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+// warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..: epilogue.  SIXTEEN epilogue warps (four per TMEM lane quarter,
+// i.e. four per SM sub-partition, each owning every fourth 32-column chunk of the tile): with one warp per
+// sub-partition the epilogue ran at ~0.3 instructions per cycle (MUFU, tcgen05.ld and staging latencies fully
+// exposed) and took 5x the MMA time of a K = 512 tile; four warps hide each other's latencies.
+constexpr int kEpiWarps = 16, kEpiSub = kEpiWarps / 4;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = BM * BK * 2;
-// epilogue staging: per epilogue warp a ring of kEpiBufs units of 32 rows x 64 B (SWIZZLE_64B)
-constexpr int kEpiBufs = 4;
+// epilogue staging: one unit of 32 rows x 64 B (SWIZZLE_64B) per epilogue warp
 constexpr uint32_t kEpiUnitBytes = 32 * 64;
-constexpr uint32_t kEpiSmemBytes = 4 * kEpiBufs * kEpiUnitBytes;    // 32 KB
+constexpr uint32_t kEpiSmemBytes = kEpiWarps * kEpiUnitBytes;       // 32 KB
 template <int BN>
 struct Tile {
   static constexpr uint32_t kBBytes = BN * BK * 2;
@@ -49,7 +53,6 @@ constexpr float kInvSqrt2Pi = 0.39894228040143268f;
 struct GemmParams {
   CUtensorMap tmA[2], tmB[2];
   CUtensorMap tmOut, tmAux;                 // store maps: box {64 B of columns, 32 rows}, SWIZZLE_64B
-  CUtensorMap tmAuxIn;                      // load map of aux_in (bf16 MUL epilogue), same box
   int nseg;
   int64_t M, N, K;
   int num_kb, kb_per_split, splits;
@@ -89,21 +92,18 @@ __device__ __forceinline__ void gelu_pair(float z, float& h, float& g) {
   g = fmaf(z * kInvSqrt2Pi, e, Phi);
 }
 
-// Per-warp staging ring for the TMA-store epilogue.  A unit is 32 rows x 64 B with the 64-byte swizzle
-// (16-byte piece j of row r sits at r*64 + ((j ^ ((r >> 1) & 3)) << 4)): eight consecutive rows hit eight distinct
-// 16-byte bank groups, so the st.shared.v4 of a warp is conflict-free.
+// Per-warp staging unit for the TMA-store epilogue: 32 rows x 64 B with the 64-byte swizzle (16-byte piece j of
+// row r sits at r*64 + ((j ^ ((r >> 1) & 3)) << 4)): eight consecutive rows hit eight distinct 16-byte bank groups,
+// so the st.shared.v4 of a warp is conflict-free.  While the TMA engine reads the unit of one warp the other three
+// warps of the sub-partition compute.
 struct Stager {
-  uint32_t base;       // shared address of this warp's kEpiBufs units
-  uint32_t slot;       // units issued so far
+  uint32_t base;       // shared address of this warp's unit
   int lane;
-  bool half_ring;      // MUL epilogue: units 2, 3 of the warp receive the prefetched aux tile; stores use units 0, 1
 
   __device__ __forceinline__ uint32_t acquire() {
-    if (lane == 0) {                                       // the store that last used this unit has read it
-      if (half_ring) ptx::bulk_wait_read<1>(); else ptx::bulk_wait_read<kEpiBufs - 1>();
-    }
+    if (lane == 0) ptx::bulk_wait_read<0>();               // the store that last used the unit has read it
     __syncwarp();
-    return base + (slot % (half_ring ? 2 : kEpiBufs)) * kEpiUnitBytes;
+    return base;
   }
   __device__ __forceinline__ void piece(uint32_t unit, int j, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     const uint32_t addr = unit + (uint32_t)lane * 64u + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4);
@@ -116,7 +116,6 @@ struct Stager {
       ptx::tma_store_2d(tm, unit, c0, c1);
       ptx::bulk_commit();
     }
-    ++slot;
   }
 };
 
@@ -180,7 +179,7 @@ __device__ __forceinline__ void add_bias32(float (&v)[32], const float* __restri
 // `valid_row`: this thread's row exists (row < M); rows beyond M still take part in the staging (the store clips).
 template <typename OutT>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, Stager& st, float (&v)[32], int64_t row, int row0,
-                                               int col0, int nvalid, bool valid_row, uint32_t aux_unit) {
+                                               int col0, int nvalid, bool valid_row, const uint4 (&aux)[4]) {
   if (p.epilogue == B200SWIN_EPI_NONE) {
     if (p.bias) add_bias32(v, p.bias + col0, nvalid);
     store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
@@ -193,15 +192,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, Stager& st, 
     store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
   } else if (p.epilogue == B200SWIN_EPI_DGELU) {
     if constexpr (sizeof(OutT) == 2) {
-      // the aux chunk (32 rows x 64 B) was prefetched by TMA into `aux_unit` (same swizzle as the store units)
-      const uint32_t rowaddr = aux_unit + (uint32_t)st.lane * 64u;
+      // this row's 64 bytes of gelu' were requested (4 x ld.global.v4) before the accumulator was read
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint32_t w0, w1, w2, w3;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                     : "r"(rowaddr + (uint32_t)((j ^ ((st.lane >> 1) & 3)) << 4)));
-        const uint32_t ww[4] = {w0, w1, w2, w3};
+        const uint32_t ww[4] = {aux[j].x, aux[j].y, aux[j].z, aux[j].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
@@ -249,7 +243,6 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
-  __shared__ __align__(8) uint64_t aux_bar[4][2];          // per epilogue warp: arrival of a prefetched aux unit
   __shared__ uint32_t tmem_slot;
 
   const uint32_t smem_base = (ptx::smem_u32(smem_dyn) + 1023u) & ~1023u;      // SWIZZLE_128B needs 1024 B alignment
@@ -258,8 +251,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
-    for (int i = 0; i < 8; ++i) ptx::mbar_init(&aux_bar[i >> 1][i & 1], 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kEpiWarps); }
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&p.tmA[0]);
     ptx::prefetch_tmap(&p.tmB[0]);
@@ -355,39 +347,11 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   } else {
     // -------------------------------------------------------------------- epilogue warps (TMEM -> smem -> TMA store)
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int sub = (warp - 2) >> 2;             // which of the quarter's four warps: chunks sub, sub + 4, ...
     Stager st;
-    const uint32_t epi_off = (uint32_t)STAGES * TL::kStageBytes + (uint32_t)q * (kEpiBufs * kEpiUnitBytes);
-    st.base = smem_base + epi_off;
-    st.slot = 0;
+    st.base = smem_base + (uint32_t)STAGES * TL::kStageBytes + (uint32_t)(warp - 2) * kEpiUnitBytes;
     st.lane = lane;
-    // bf16 MUL epilogue (dgrad of fc2 times gelu'): the aux chunk of unit k+1 is fetched by TMA into staging units
-    // 2, 3 of this warp while unit k is processed -- coalesced, instead of 32 scattered 64-byte row reads per chunk
-    const bool pf = p.epilogue == B200SWIN_EPI_DGELU && p.out_dtype == B200SWIN_BF16 && !p.partial;
-    st.half_ring = pf;
-    auto slab_exists = [&](int64_t t) { int mb, nb, z; decode(t, mb, nb, z); return mb * BM + q * 32 < p.M; };
-    auto first_valid = [&](int64_t t) { while (t < p.num_tiles && !slab_exists(t)) t += gridDim.x; return t; };
-    auto next_unit = [&](int64_t& t, int& c) {
-      int mb, nb, z;
-      decode(t, mb, nb, z);
-      ++c;
-      if (c == BN / 32 || nb * BN + c * 32 >= p.N) { c = 0; t = first_valid(t + gridDim.x); }
-    };
-    auto prefetch = [&](int64_t t, int c, uint32_t k) {
-      if (lane == 0) {
-        int mb, nb, z;
-        decode(t, mb, nb, z);
-        ptx::mbar_arrive_expect_tx(&aux_bar[q][k & 1], kEpiUnitBytes);
-        ptx::tma_load_2d(smem_al + epi_off + (2 + (k & 1)) * kEpiUnitBytes, &p.tmAuxIn, &aux_bar[q][k & 1], nb * BN + c * 32,
-                         mb * BM + q * 32);
-      }
-    };
-    int64_t pt = first_valid(blockIdx.x);          // prefetch cursor: one unit ahead of the processing loop
-    int pc = 0;
-    uint32_t k = 0;                                // units processed by this warp
-    if (pf && pt < p.num_tiles) {
-      prefetch(pt, pc, 0);
-      next_unit(pt, pc);
-    }
+    const bool aux_bf16 = p.epilogue == B200SWIN_EPI_DGELU && p.out_dtype == B200SWIN_BF16 && !p.partial;
     uint32_t tcount = 0;
     for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
       int mb, nb, z;
@@ -399,41 +363,37 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       ptx::tc_fence_after();
       if (m0 < p.M) {                              // warp-uniform: this 32-row slab exists
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = sub; c < BN / 32; c += kEpiSub) {
           const int col0 = n0 + c * 32;
           if (col0 >= p.N) break;                  // warp-uniform
-          uint32_t aux_unit = 0;
-          if (pf) {
-            __syncwarp();                          // every lane has finished reading the unit fetched two units ago
-            if (pt < p.num_tiles) {
-              prefetch(pt, pc, k + 1);
-              next_unit(pt, pc);
-            }
-            ptx::mbar_wait(&aux_bar[q][k & 1], (k >> 1) & 1);
-            aux_unit = st.base + (2 + (k & 1)) * kEpiUnitBytes;
-          }
-          float v[32];
-          {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          }
           const int nvalid = (int)min((int64_t)32, p.N - col0);
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
+          uint4 aux[4];
+          if (aux_bf16) {
+            // bf16 MUL epilogue (dgrad of fc2 times gelu'): this row's 64 bytes, in flight together with the tcgen05.ld
+            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux_in) +
+                                                             row * p.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              aux[j] = (row < p.M && 8 * j < nvalid) ? __ldg(ap + j) : make_uint4(0u, 0u, 0u, 0u);
+          }
+          ptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           if (p.partial) {
             store_chunk<float>(st, &p.tmOut, v, col0, (int)((int64_t)z * p.m_pad) + m0, p.N);
           } else if (p.out_dtype == B200SWIN_BF16) {
-            epilogue_chunk<__nv_bfloat16>(p, st, v, row, m0, col0, nvalid, row < p.M, aux_unit);
+            epilogue_chunk<__nv_bfloat16>(p, st, v, row, m0, col0, nvalid, row < p.M, aux);
           } else {
-            epilogue_chunk<float>(p, st, v, row, m0, col0, nvalid, row < p.M, 0u);
+            epilogue_chunk<float>(p, st, v, row, m0, col0, nvalid, row < p.M, aux);
           }
-          ++k;
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);    // 4 arrivals (one per epilogue warp) free the accumulator
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);    // one arrival per epilogue warp frees the accumulator
     }
     if (lane == 0) ptx::bulk_wait<0>();            // all stores of this warp have landed before the CTA retires
   }
@@ -618,9 +578,6 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   } else {
     if ((rc = store_map(&p.tmOut, out, out_dtype, M, N))) return rc;
     if (aux_out && (rc = store_map(&p.tmAux, aux_out, out_dtype, M, N))) return rc;
-    if (epilogue == B200SWIN_EPI_DGELU && out_dtype == B200SWIN_BF16 &&
-        (rc = store_map(&p.tmAuxIn, aux_in, B200SWIN_BF16, M, N)))
-      return rc;
   }
 
   cudaStream_t st = (cudaStream_t)stream;

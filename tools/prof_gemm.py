@@ -50,6 +50,20 @@ for si, (T, C, nblk) in enumerate(stages):
             "wgrad": lambda: ops.gemm(ops.Operand(dy), ops.Operand(x), N, K, T, a_mn=True, b_mn=True,
                                       out_dtype=torch.float32, splits=splits),
         }
+        if name == "fc1":
+            z = torch.empty(T, N, device=dev, dtype=torch.bfloat16)
+            bias = torch.randn(N, device=dev)
+            cases["fwd+gelu"] = lambda: ops.gemm(ops.Operand(x), ops.Operand(w), T, N, K, epilogue=L.EPI_GELU, bias=bias,
+                                                 aux_out=z)
+        if name == "fc2":
+            gd = torch.randn(T, K, device=dev).bfloat16()
+            cases["dgrad*g'"] = lambda: ops.gemm(ops.Operand(dy), ops.Operand(w), T, K, N, b_mn=True,
+                                                 epilogue=L.EPI_DGELU, aux_in=gd)
+        if name == "qkv":
+            inv = torch.empty(T, 2, C // 32, device=dev)
+            qb, vb = torch.randn(C, device=dev), torch.randn(C, device=dev)
+            cases["fwd+norm"] = lambda: ops.gemm(ops.Operand(x), ops.Operand(w), T, N, K, epilogue=L.EPI_QKV, bias=qb,
+                                                 bias2=vb, inv_norm=inv, nH=C // 32)
         for kind, fn in cases.items():
             if a.only and a.only not in f"{name}.{kind}":
                 continue

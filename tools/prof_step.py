@@ -28,4 +28,10 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
     step()
     torch.cuda.synchronize()
-print(prof.key_averages(group_by_input_shape=True).table(sort_by="self_cuda_time_total", row_limit=45, max_name_column_width=60, max_shapes_column_width=70))
+ka = prof.key_averages(group_by_input_shape=True)
+rows = [(e.self_device_time_total, e.count, e.key, str(e.input_shapes)[:150]) for e in ka if e.key.startswith("aten::") and e.self_device_time_total > 0]
+rows.sort(reverse=True)
+tot = sum(r[0] for r in rows)
+print(f"aten ops with GPU time: {tot/1e3:.2f} ms total")
+for t, n, k, sh in rows[:40]:
+    print(f"{t/1e3:8.3f} ms  x{n:4d}  {k:32s} {sh}")
