@@ -92,6 +92,37 @@ __device__ __forceinline__ void gelu_pair(float z, float& h, float& g) {
   g = fmaf(z * kInvSqrt2Pi, e, Phi);
 }
 
+// bf16 epilogue: two elements at a time on the packed fp32x2 instructions of sm_100 (FFMA2 / FMUL2: one issue slot per
+// two results) and with ONE MUFU operation per element instead of two -- at K = 128 / 256 the two MUFU operations per
+// output (16 per clock and SM) cost as much time as the HBM traffic of the whole GEMM.  The reciprocal of the
+// Abramowitz-Stegun form is replaced by a polynomial for the scaled complementary error function:
+//   (1 - erf(a / sqrt 2)) / 2 = F(a) exp(-a^2 / 2),   F(a) = erfcx(a / sqrt 2) / 2 ~ P8(2 a / 4.5 - 1) on [0, 4.5]
+// (weighted minimax fit, |error of Phi| <= 1.7e-6, of gelu <= 4.7e-6, of gelu' <= 1.8e-6 over all z -- 1/1000 of a
+// bf16 ulp at 1; beyond a = 4.5 the Gaussian factor is below 4e-5 and a clamped F is exact to 1e-6).
+// Phi = 1/2 + sign(z) (1/2 - F e),  gelu = z Phi,  gelu' = Phi + z e / sqrt(2 pi).
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ void gelu_pair2(float2 z, float2& h, float2& g) {
+  const float2 ac = make_float2(fminf(fabsf(z.x), 4.5f), fminf(fabsf(z.y), 4.5f));
+  const float2 t = __ffma2_rn(ac, splat2(2.0f / 4.5f), splat2(-1.0f));
+  const float2 w = __fmul2_rn(__fmul2_rn(z, z), splat2(-0.72134752044448170f));
+  float2 e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(w.x));                              // exp(-z^2 / 2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(w.y));
+  float2 F = __ffma2_rn(splat2(1.882177644e-02f), t, splat2(2.564300909e-03f));
+  F = __ffma2_rn(F, t, splat2(-2.922779805e-03f));
+  F = __ffma2_rn(F, t, splat2(-3.627864966e-02f));
+  F = __ffma2_rn(F, t, splat2(3.699574419e-02f));
+  F = __ffma2_rn(F, t, splat2(-5.326356786e-02f));
+  F = __ffma2_rn(F, t, splat2(8.664873954e-02f));
+  F = __ffma2_rn(F, t, splat2(-1.198449042e-01f));
+  F = __ffma2_rn(F, t, splat2(1.536320908e-01f));
+  const float2 d = __ffma2_rn(__fmul2_rn(F, e), splat2(-1.0f), splat2(0.5f));
+  const float2 sg = make_float2(copysignf(1.0f, z.x), copysignf(1.0f, z.y));
+  const float2 Phi = __ffma2_rn(sg, d, splat2(0.5f));
+  h = __fmul2_rn(z, Phi);
+  g = __ffma2_rn(__fmul2_rn(z, splat2(kInvSqrt2Pi)), e, Phi);
+}
+
 // Per-warp staging unit for the TMA-store epilogue: 32 rows x 64 B with the 64-byte swizzle (16-byte piece j of
 // row r sits at r*64 + ((j ^ ((r >> 1) & 3)) << 4)): eight consecutive rows hit eight distinct 16-byte bank groups,
 // so the st.shared.v4 of a warp is conflict-free.  While the TMA engine reads the unit of one warp the other three
@@ -177,20 +208,29 @@ __device__ __forceinline__ void add_bias32(float (&v)[32], const float* __restri
 }
 
 // `valid_row`: this thread's row exists (row < M); rows beyond M still take part in the staging (the store clips).
-template <typename OutT>
+template <int EPI, typename OutT>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, Stager& st, float (&v)[32], int64_t row, int row0,
                                                int col0, int nvalid, bool valid_row, const uint4 (&aux)[4]) {
-  if (p.epilogue == B200SWIN_EPI_NONE) {
+  if constexpr (EPI == B200SWIN_EPI_NONE) {
     if (p.bias) add_bias32(v, p.bias + col0, nvalid);
     store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
-  } else if (p.epilogue == B200SWIN_EPI_GELU) {
+  } else if constexpr (EPI == B200SWIN_EPI_GELU) {
     if (p.bias) add_bias32(v, p.bias + col0, nvalid);
     float g[32];
+    if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c) gelu_pair(v[c], v[c], g[c]);
+      for (int c = 0; c < 32; c += 2) {
+        float2 h2, g2;
+        gelu_pair2(make_float2(v[c], v[c + 1]), h2, g2);
+        v[c] = h2.x; v[c + 1] = h2.y; g[c] = g2.x; g[c + 1] = g2.y;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) gelu_pair(v[c], v[c], g[c]);
+    }
     if (p.aux_out) store_chunk<OutT>(st, &p.tmAux, g, col0, row0, p.N);
     store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
-  } else if (p.epilogue == B200SWIN_EPI_DGELU) {
+  } else if constexpr (EPI == B200SWIN_EPI_DGELU) {
     if constexpr (sizeof(OutT) == 2) {
       // this row's 64 bytes of gelu' were requested (4 x ld.global.v4) before the accumulator was read
 #pragma unroll
@@ -233,7 +273,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, Stager& st, 
   }
 }
 
-template <bool A_MN, bool B_MN, int BN>
+// EPI / OUT_BF16 are template parameters so that every launch carries only its own epilogue (registers, code size);
+// split-K launches (p.partial) are EPI_NONE with fp32 stores.
+template <bool A_MN, bool B_MN, int BN, int EPI, bool OUT_BF16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using TL = Tile<BN>;
@@ -351,7 +393,26 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     Stager st;
     st.base = smem_base + (uint32_t)STAGES * TL::kStageBytes + (uint32_t)(warp - 2) * kEpiUnitBytes;
     st.lane = lane;
-    const bool aux_bf16 = p.epilogue == B200SWIN_EPI_DGELU && p.out_dtype == B200SWIN_BF16 && !p.partial;
+    constexpr bool aux_bf16 = EPI == B200SWIN_EPI_DGELU && OUT_BF16;
+    // bf16 MUL epilogue (dgrad of fc2 times gelu'): every thread reads its row's 64 bytes of gelu' straight from global
+    // memory, ONE UNIT AHEAD (the tile schedule is static), so the HBM latency hides behind the previous unit
+    uint4 aux_next[4];
+    auto aux_fetch = [&](int64_t tt, int cc) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) aux_next[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (tt >= p.num_tiles) return;
+      int mb, nb, z;
+      decode(tt, mb, nb, z);
+      const int64_t rr = (int64_t)mb * BM + q * 32 + lane;
+      const int64_t cc0 = (int64_t)nb * BN + cc * 32;
+      if (rr < p.M && cc0 < p.N) {
+        const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + rr * p.ldo + cc0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (cc0 + 8 * j < p.N) aux_next[j] = __ldg(ap + j);
+      }
+    };
+    if constexpr (aux_bf16) aux_fetch(blockIdx.x, sub);
     uint32_t tcount = 0;
     for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
       int mb, nb, z;
@@ -361,33 +422,30 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       const uint32_t acc = tcount & 1;
       ptx::mbar_wait(&acc_full[acc], (tcount >> 1) & 1);
       ptx::tc_fence_after();
-      if (m0 < p.M) {                              // warp-uniform: this 32-row slab exists
 #pragma unroll 1
-        for (int c = sub; c < BN / 32; c += kEpiSub) {
-          const int col0 = n0 + c * 32;
-          if (col0 >= p.N) break;                  // warp-uniform
+      for (int c = sub; c < BN / 32; c += kEpiSub) {
+        const int col0 = n0 + c * 32;
+        uint4 aux[4];
+        if constexpr (aux_bf16) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) aux[j] = aux_next[j];
+          if (c + kEpiSub < BN / 32) aux_fetch(t, c + kEpiSub); else aux_fetch(t + gridDim.x, sub);
+        }
+        if (m0 < p.M && col0 < p.N) {              // warp-uniform: this 32 x 32 chunk exists
           const int nvalid = (int)min((int64_t)32, p.N - col0);
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)(c * 32), r);
-          uint4 aux[4];
-          if (aux_bf16) {
-            // bf16 MUL epilogue (dgrad of fc2 times gelu'): this row's 64 bytes, in flight together with the tcgen05.ld
-            const uint4* ap = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux_in) +
-                                                             row * p.ldo + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              aux[j] = (row < p.M && 8 * j < nvalid) ? __ldg(ap + j) : make_uint4(0u, 0u, 0u, 0u);
-          }
           ptx::tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (p.partial) {
-            store_chunk<float>(st, &p.tmOut, v, col0, (int)((int64_t)z * p.m_pad) + m0, p.N);
-          } else if (p.out_dtype == B200SWIN_BF16) {
-            epilogue_chunk<__nv_bfloat16>(p, st, v, row, m0, col0, nvalid, row < p.M, aux);
+          if constexpr (OUT_BF16) {
+            epilogue_chunk<EPI, __nv_bfloat16>(p, st, v, row, m0, col0, nvalid, row < p.M, aux);
           } else {
-            epilogue_chunk<float>(p, st, v, row, m0, col0, nvalid, row < p.M, aux);
+            if (EPI == B200SWIN_EPI_NONE && p.partial)
+              store_chunk<float>(st, &p.tmOut, v, col0, (int)((int64_t)z * p.m_pad) + m0, p.N);
+            else
+              epilogue_chunk<EPI, float>(p, st, v, row, m0, col0, nvalid, row < p.M, aux);
           }
         }
       }
@@ -585,18 +643,34 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   p.n_tiles = (int)((N + bn - 1) / bn);
   p.num_tiles = (int64_t)p.m_tiles * p.n_tiles * splits;
   const unsigned grid = (unsigned)(p.num_tiles < sm_count() ? p.num_tiles : sm_count());
-#define LAUNCH(AM, BMN, BNV)                                                                                  \
-  do {                                                                                                        \
-    BSW_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AM, BMN, BNV>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                  (int)Tile<BNV>::kSmemBytes));                                               \
-    gemm_tc_kernel<AM, BMN, BNV><<<grid, kGemmThreads, Tile<BNV>::kSmemBytes, st>>>(p);                       \
+  const bool out_bf16 = out_dtype == B200SWIN_BF16 && splits == 1;     // split-K partials are fp32
+#define LAUNCH(AM, BMN, BNV, EPI, OB)                                                                              \
+  do {                                                                                                             \
+    BSW_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AM, BMN, BNV, EPI, OB>,                                           \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<BNV>::kSmemBytes));       \
+    gemm_tc_kernel<AM, BMN, BNV, EPI, OB><<<grid, kGemmThreads, Tile<BNV>::kSmemBytes, st>>>(p);                   \
   } while (0)
-#define LAUNCH_BN(AM, BMN) do { if (bn == 256) LAUNCH(AM, BMN, 256); else LAUNCH(AM, BMN, 128); } while (0)
-  if (a_mn_major && b_mn_major) LAUNCH_BN(true, true);
-  else if (a_mn_major) LAUNCH_BN(true, false);
-  else if (b_mn_major) LAUNCH_BN(false, true);
-  else LAUNCH_BN(false, false);
+#define LAUNCH_OB(AM, BMN, BNV, EPI) do { if (out_bf16) LAUNCH(AM, BMN, BNV, EPI, true); else LAUNCH(AM, BMN, BNV, EPI, false); } while (0)
+#define LAUNCH_BN(AM, BMN, EPI) do { if (bn == 256) LAUNCH_OB(AM, BMN, 256, EPI); else LAUNCH_OB(AM, BMN, 128, EPI); } while (0)
+  // instantiated combinations: the plain epilogue for every operand layout; GELU and QKV for the forward layout
+  // (both K-major); DGELU for the dgrad layout (B read MN-major)
+  if (epilogue == B200SWIN_EPI_NONE) {
+    if (a_mn_major && b_mn_major) LAUNCH_BN(true, true, B200SWIN_EPI_NONE);
+    else if (a_mn_major) LAUNCH_BN(true, false, B200SWIN_EPI_NONE);
+    else if (b_mn_major) LAUNCH_BN(false, true, B200SWIN_EPI_NONE);
+    else LAUNCH_BN(false, false, B200SWIN_EPI_NONE);
+  } else if (epilogue == B200SWIN_EPI_GELU) {
+    BSW_REQUIRE(!a_mn_major && !b_mn_major, "gemm: the GELU epilogue is built for K-major operands only");
+    LAUNCH_BN(false, false, B200SWIN_EPI_GELU);
+  } else if (epilogue == B200SWIN_EPI_QKV) {
+    BSW_REQUIRE(!a_mn_major && !b_mn_major, "gemm: the QKV epilogue is built for K-major operands only");
+    LAUNCH_BN(false, false, B200SWIN_EPI_QKV);
+  } else {
+    BSW_REQUIRE(!a_mn_major && b_mn_major, "gemm: the DGELU epilogue is built for the dgrad layout (B MN-major) only");
+    LAUNCH_BN(false, true, B200SWIN_EPI_DGELU);
+  }
 #undef LAUNCH_BN
+#undef LAUNCH_OB
 #undef LAUNCH
   BSW_LAUNCH_CHECK();
   if (splits > 1) {

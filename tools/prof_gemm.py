@@ -55,6 +55,8 @@ for si, (T, C, nblk) in enumerate(stages):
             bias = torch.randn(N, device=dev)
             cases["fwd+gelu"] = lambda: ops.gemm(ops.Operand(x), ops.Operand(w), T, N, K, epilogue=L.EPI_GELU, bias=bias,
                                                  aux_out=z)
+            cases["fwd+gelu-noaux"] = lambda: ops.gemm(ops.Operand(x), ops.Operand(w), T, N, K, epilogue=L.EPI_GELU,
+                                                       bias=bias)
         if name == "fc2":
             gd = torch.randn(T, K, device=dev).bfloat16()
             cases["dgrad*g'"] = lambda: ops.gemm(ops.Operand(dy), ops.Operand(w), T, K, N, b_mn=True,
