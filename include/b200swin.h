@@ -75,7 +75,9 @@ int b200swin_shift_mask(float* out, int H, int W, int ws, int shift, void* strea
  *   y[r,:] = residual[r,:] + row_scale[r / rows_per_scale] * (LN(x[r,:]) * gamma + beta)
  * residual and row_scale may be NULL.  x,residual,y,dy,dx have `dtype`; gamma,beta,mean,rstd and
  * the gradients of gamma/beta are float32.  C must be a multiple of 4.
- * bwd: dx, plus dgamma/dbeta [C] reduced deterministically through `workspace`.
+ * bwd: dx, plus dgamma/dbeta [C] reduced deterministically through `workspace`; dcolsum (optional, NULL to
+ * skip; bf16 tensors with C % 8 == 0 and C <= 1536 only) receives the fp32 column sums of dx, i.e. the bias
+ * gradient of the Linear whose output was normalised (proj / fc2), saving a separate pass over dx.
  * The gradient of `residual` is dy itself (the caller aliases it).
  * ------------------------------------------------------------------------------------------ */
 int b200swin_ln_fwd(const void* x, const void* residual, const float* gamma, const float* beta,
@@ -84,7 +86,8 @@ int b200swin_ln_fwd(const void* x, const void* residual, const float* gamma, con
 size_t b200swin_ln_bwd_workspace_bytes(int64_t rows, int C);
 int b200swin_ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                     const float* row_scale, int64_t rows_per_scale, void* dx, float* dgamma, float* dbeta,
-                    int64_t rows, int C, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+                    float* dcolsum, int64_t rows, int C, int dtype, void* workspace, size_t workspace_bytes,
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Attention core.  Replaces, for attn_type='cosine_mh', the body of WindowAttention.forward between

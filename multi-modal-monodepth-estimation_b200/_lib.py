@@ -35,7 +35,7 @@ SIGNATURES = {
     "b200swin_shift_mask": (I, [P, I, I, I, I, P]),
     "b200swin_ln_fwd": (I, [P, P, P, P, P, L, P, P, P, L, I, F, I, P]),
     "b200swin_ln_bwd_workspace_bytes": (Z, [L, I]),
-    "b200swin_ln_bwd": (I, [P, P, P, P, P, P, L, P, P, P, L, I, I, P, Z, P]),
+    "b200swin_ln_bwd": (I, [P, P, P, P, P, P, L, P, P, P, P, L, I, I, P, Z, P]),
     "b200swin_attn_fwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P]),
     "b200swin_attn_bwd_workspace_bytes": (Z, [I, I, I, I, I, I, I]),
     "b200swin_attn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, I, I, P, Z, P]),

@@ -122,11 +122,19 @@ def shift_mask(H, W, ws, shift, device):
 
 
 # ------------------------------------------------------------------------------ LayerNorm (+residual)
+def ln_colsum_supported(dtype: torch.dtype, C: int) -> bool:
+    """Whether the LayerNorm backward can also emit the column sums of dx (bf16 streaming kernels only)."""
+    return dtype == torch.bfloat16 and C % 8 == 0 and C <= 1536
+
+
 class _LayerNormResidual(torch.autograd.Function):
-    """y = residual + row_scale[b] * (LN(x) * gamma + beta); residual / row_scale optional."""
+    """y = residual + row_scale[b] * (LN(x) * gamma + beta); residual / row_scale optional.
+    `producer_bias` is the bias of the Linear that produced x: it is NOT used in the forward (the GEMM epilogue
+    already added it) -- it is an input only so that its gradient, the column sums of dx, can be returned from the
+    LayerNorm backward kernel, which has dx in registers anyway (the caller passes bias.detach() to the Linear)."""
 
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, row_scale, rows_per_scale, eps):
+    def forward(ctx, x, residual, gamma, beta, row_scale, rows_per_scale, eps, producer_bias=None):
         L.require_cuda(x, residual, gamma, beta, row_scale)
         lib = L.load()
         C = x.shape[-1]
@@ -150,6 +158,11 @@ class _LayerNormResidual(torch.autograd.Function):
         ctx.has_res = residual is not None
         ctx.rows_per_scale = rows_per_scale
         ctx.gdtype, ctx.bdtype = gamma.dtype, beta.dtype
+        ctx.pbdtype = None
+        if producer_bias is not None:
+            if not ln_colsum_supported(xc.dtype, C):
+                raise RuntimeError("layer_norm_residual: producer_bias needs bf16 activations with C % 8 == 0, C <= 1536")
+            ctx.pbdtype = producer_bias.dtype
         return y.view(x.shape)
 
     @staticmethod
@@ -163,19 +176,21 @@ class _LayerNormResidual(torch.autograd.Function):
             dyc = dyc.to(xc.dtype)
         with torch.cuda.device_of(xc):
             dx = torch.empty_like(xc)
-            dgb = torch.empty((2, C), dtype=torch.float32, device=xc.device)
+            dgb = torch.empty((3, C), dtype=torch.float32, device=xc.device)
             ws_bytes = lib.b200swin_ln_bwd_workspace_bytes(rows, C)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xc.device)
+            want_cs = ctx.pbdtype is not None and ctx.needs_input_grad[7]
             L.check(lib.b200swin_ln_bwd(dyc.data_ptr(), xc.data_ptr(), g32.data_ptr(), stats[0].data_ptr(),
                                         stats[1].data_ptr(), L.ptr(rs), ctx.rows_per_scale, dx.data_ptr(),
-                                        dgb[0].data_ptr(), dgb[1].data_ptr(), rows, C, L.dtype_code(xc),
-                                        ws.data_ptr(), ws_bytes, L.stream_of(xc)), "ln_bwd")
+                                        dgb[0].data_ptr(), dgb[1].data_ptr(), dgb[2].data_ptr() if want_cs else 0,
+                                        rows, C, L.dtype_code(xc), ws.data_ptr(), ws_bytes, L.stream_of(xc)), "ln_bwd")
         dres = dyc.view(dy.shape) if ctx.has_res else None
-        return dx, dres, dgb[0].to(ctx.gdtype), dgb[1].to(ctx.bdtype), None, None, None
+        dpb = dgb[2].to(ctx.pbdtype) if want_cs else None
+        return dx, dres, dgb[0].to(ctx.gdtype), dgb[1].to(ctx.bdtype), None, None, None, dpb
 
 
-def layer_norm_residual(x, gamma, beta, eps, residual=None, row_scale=None, rows_per_scale=1):
-    return _LayerNormResidual.apply(x, residual, gamma, beta, row_scale, int(rows_per_scale), float(eps))
+def layer_norm_residual(x, gamma, beta, eps, residual=None, row_scale=None, rows_per_scale=1, producer_bias=None):
+    return _LayerNormResidual.apply(x, residual, gamma, beta, row_scale, int(rows_per_scale), float(eps), producer_bias)
 
 
 # ------------------------------------------------------------------------------ dense contractions
@@ -367,11 +382,11 @@ class _Mlp(torch.autograd.Function):
         dy2 = dy2.contiguous()
         dyo = stage_operand(dy2, exact)
         dw2 = _wgrad(dyo, Operand(hhi, hlo), M, Co, Hd).to(w2.dtype)
-        db2 = colsum(dy2).to(ctx.bd[1]) if ctx.bd[1] is not None else None
+        db2 = colsum(dy2).to(ctx.bd[1]) if (ctx.bd[1] is not None and ctx.needs_input_grad[4]) else None
         dz = gemm(dyo, stage_weight(w2, exact), M, Hd, Co, b_mn=True, epilogue=L.EPI_DGELU, aux_in=z, out_dtype=ctx.cd)
         dzo = stage_operand(dz, exact)
         dw1 = _wgrad(dzo, Operand(xhi, xlo), M, Hd, C).to(w1.dtype)
-        db1 = colsum(dz).to(ctx.bd[0]) if ctx.bd[0] is not None else None
+        db1 = colsum(dz).to(ctx.bd[0]) if (ctx.bd[0] is not None and ctx.needs_input_grad[2]) else None
         dx = None
         if ctx.needs_input_grad[0]:
             dx = gemm(dzo, stage_weight(w1, exact), M, C, Hd, b_mn=True, out_dtype=ctx.cd).view(ctx.xshape)

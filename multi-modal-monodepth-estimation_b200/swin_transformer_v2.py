@@ -98,8 +98,10 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
         self.norm = None
 
-    def forward(self, x, H=None, W=None):
-        return ops.mlp(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
+    def forward(self, x, H=None, W=None, fc2_bias_grad_elsewhere=False):
+        # fc2_bias_grad_elsewhere: the caller's LayerNorm backward returns fc2.bias' gradient (ops.layer_norm_residual)
+        b2 = self.fc2.bias.detach() if (fc2_bias_grad_elsewhere and self.fc2.bias is not None) else self.fc2.bias
+        return ops.mlp(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, b2)
 
 
 def window_partition(x, window_size):
@@ -213,15 +215,17 @@ class WindowAttention(nn.Module):
             qpad = F.normalize(self.q_bias.float().view(self.num_heads, -1), dim=-1).reshape(-1)
         return qpad, self.v_bias
 
-    def attend(self, x, B, H, W, shift, mask=None):
+    def attend(self, x, B, H, W, shift, mask=None, proj_bias_grad_elsewhere=False):
         """x: [B, H*W, C] natural order -> [B, H*W, C]: qkv GEMM, windowed attention over the (padded,
-        rolled) grid, proj GEMM."""
+        rolled) grid, proj GEMM.  proj_bias_grad_elsewhere: the caller's LayerNorm backward returns proj.bias'
+        gradient (ops.layer_norm_residual(..., producer_bias=...))."""
         C, nH, ws = self.dim, self.num_heads, self.window_size[0]
         qkv, inv_norm = ops.qkv_project(x, self.qkv.weight, self.q_bias, self.v_bias, nH)
         qpad, vpad = self._pads(H % ws != 0 or W % ws != 0)
         o = ops.attention_core(qkv.view(B, H, W, 3 * C), inv_norm, self._bias_table(), self._scale(), qpad, vpad, mask,
                                B, H, W, C, nH, ws, shift)
-        return ops.linear(o.view(B, H * W, C), self.proj.weight, self.proj.bias)
+        pb = self.proj.bias.detach() if (proj_bias_grad_elsewhere and self.proj.bias is not None) else self.proj.bias
+        return ops.linear(o.view(B, H * W, C), self.proj.weight, pb)
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C) window-major; mask: (nW, N, N) additive or None  (reference :275-336)."""
@@ -262,7 +266,7 @@ class _SwinBlockBase(nn.Module):
         self.H = None
         self.W = None
 
-    def _attention(self, x, mask_matrix):
+    def _attention(self, x, mask_matrix, proj_bias_grad_elsewhere=False):
         """Attention half: shifted-window attention on natural-order tokens.  With the ShiftMask handle (or
         no shift) everything is fused; an explicit mask tensor takes the general window-major route."""
         H, W = self.H, self.W
@@ -270,9 +274,10 @@ class _SwinBlockBase(nn.Module):
         assert L == H * W, f"input feature has wrong size, with L = {L}, H = {H}, W = {W}"
         if self.shift_size > 0 and torch.is_tensor(mask_matrix):
             xw = ops.window_gather(x.view(B, H, W, C), self.window_size, self.shift_size)
-            aw = self.attn(xw, mask=mask_matrix)
+            aw = self.attn.attend(xw, xw.shape[0], self.window_size, self.window_size, 0, mask_matrix,
+                                  proj_bias_grad_elsewhere)
             return ops.window_scatter(aw, B, H, W, self.window_size, self.shift_size).view(B, L, C)
-        return self.attn.attend(x, B, H, W, self.shift_size)
+        return self.attn.attend(x, B, H, W, self.shift_size, None, proj_bias_grad_elsewhere)
 
     def _drop_scale(self, x):
         return self.drop_path.sample_scale(x) if isinstance(self.drop_path, DropPath) else None
@@ -294,12 +299,17 @@ class SwinTransformerBlockPost(_SwinBlockBase):
 
     def forward(self, x, mask_matrix):
         L = x.shape[1]
-        a = self._attention(x, mask_matrix)
+        # bf16 path: the bias gradients of proj and fc2 are the column sums of the LayerNorm backward's dx and come
+        # out of that kernel (no separate pass over dx)
+        fuse = torch.is_grad_enabled() and ops.ln_colsum_supported(ops.compute_dtype(x), self.dim)
+        a = self._attention(x, mask_matrix, fuse)
         x = ops.layer_norm_residual(a, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=x,
-                                    row_scale=self._drop_scale(x), rows_per_scale=L)
-        m = self.mlp(x, self.H, self.W)
+                                    row_scale=self._drop_scale(x), rows_per_scale=L,
+                                    producer_bias=self.attn.proj.bias if fuse else None)
+        m = self.mlp(x, self.H, self.W, fuse)
         return ops.layer_norm_residual(m, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=x,
-                                       row_scale=self._drop_scale(x), rows_per_scale=L)
+                                       row_scale=self._drop_scale(x), rows_per_scale=L,
+                                       producer_bias=self.mlp.fc2.bias if fuse else None)
 
 
 class SwinTransformerBlockPre(_SwinBlockBase):

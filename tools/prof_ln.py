@@ -1,31 +1,59 @@
-"""LayerNorm+residual fwd/bwd and colsum on the config-2 shapes: ms and achieved GB/s (algorithmic bytes)."""
+"""LayerNorm+residual fwd/bwd and colsum on the config-2 shapes: us per call and achieved GB/s (algorithmic bytes).
+Each op is captured REP times in a CUDA graph (host overhead of the Python wrappers would otherwise dominate the
+20-200 us kernels); every replay starts from a flushed L2."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from b200swin import ops
 dev = "cuda"
-flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+REP = 4
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+stream = torch.cuda.Stream()
+
+
 def timeit(fn, iters=5):
-    fn(); fn()
-    ts = []
-    for _ in range(iters):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+    with torch.cuda.stream(stream):
+        fn(); fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for _ in range(REP):
+                fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / REP)
     return sorted(ts)[len(ts) // 2]
+
+
+tot = 0.0
 for T, C, nblk in [(48 * 14400, 128, 4), (48 * 3600, 256, 4), (48 * 900, 512, 36), (48 * 225, 1024, 4)]:
-    x = torch.randn(T, C, device=dev).bfloat16().requires_grad_(True)
-    r = torch.randn(T, C, device=dev).bfloat16()
+    # REP distinct input sets so that replays inside one graph do not hit L2 (stage 2/3 tensors are smaller than L2)
+    xs = [torch.randn(T, C, device=dev).bfloat16().requires_grad_(True) for _ in range(REP)]
+    rs = [torch.randn(T, C, device=dev).bfloat16() for _ in range(REP)]
+    dys = [torch.randn(T, C, device=dev).bfloat16() for _ in range(REP)]
     g = torch.ones(C, device=dev, requires_grad=True); b = torch.zeros(C, device=dev, requires_grad=True)
-    dy = torch.randn(T, C, device=dev).bfloat16()
-    y = ops.layer_norm_residual(x, g, b, 1e-6, residual=r)
-    tf = timeit(lambda: ops.layer_norm_residual(x, g, b, 1e-6, residual=r))
+    pb = torch.zeros(C, device=dev, requires_grad=True)
+    it = [0]
+    def fw():
+        i = it[0] % REP; it[0] += 1
+        return ops.layer_norm_residual(xs[i], g, b, 1e-6, residual=rs[i], producer_bias=pb)
+    tf = timeit(fw)
+    with torch.cuda.stream(stream):
+        ys = [ops.layer_norm_residual(xs[i], g, b, 1e-6, residual=rs[i], producer_bias=pb) for i in range(REP)]
+        torch.cuda.synchronize()
     def bw():
-        x.grad = None
-        y.backward(dy, retain_graph=True)
+        i = it[0] % REP; it[0] += 1
+        torch.autograd.grad(ys[i], [xs[i], g, b, pb], dys[i], retain_graph=True)
     tb = timeit(bw)
-    tc = timeit(lambda: ops.colsum(dy))
+    def cs():
+        i = it[0] % REP; it[0] += 1
+        ops.colsum(dys[i])
+    tc = timeit(cs)
     by = T * C * 2
-    print(f"T={T} C={C}: ln fwd {tf*1e3:7.1f} us ({3*by/tf/1e6:6.0f} GB/s)  ln bwd {tb*1e3:7.1f} us ({3*by/tb/1e6:6.0f} GB/s)  "
-          f"colsum {tc*1e3:7.1f} us ({by/tc/1e6:6.0f} GB/s)   x{nblk} -> {nblk*(tf+tb)+nblk*tc:.2f} ms/step")
+    tot += nblk * (tf + tb)
+    print(f"T={T} C={C}: ln fwd {tf*1e3:7.1f} us ({3*by/tf/1e6:6.0f} GB/s)  ln bwd(+colsum of dx) {tb*1e3:7.1f} us "
+          f"({3*by/tb/1e6:6.0f} GB/s)  standalone colsum {tc*1e3:7.1f} us ({by/tc/1e6:6.0f} GB/s)   x{nblk} -> {nblk*(tf+tb):.2f} ms/step")
+print(f"LN total {tot:.2f} ms/step")
