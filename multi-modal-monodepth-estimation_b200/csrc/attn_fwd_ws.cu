@@ -36,13 +36,16 @@ namespace b200swin {
 
 namespace {
 constexpr int HD = 32;
-// Warps 0-15: softmax; warps 16-18: gather; warp 19: MMA issuer.  The warp scheduler favours the highest warp id
-// of a sub-partition, so the latency-critical (but nearly idle) issuer and gather warps sit ABOVE the softmax warps:
-// as warp 0 the issuer was starved of issue slots and every MMA hand-off took ~500 cycles.
+// Warps 0-15: softmax; warps 16-17: gather; warp 18: issuer of S = Q K^T; warp 19: issuer of O = P V.  The warp
+// scheduler favours the highest warp id of a sub-partition, so the latency-critical (but nearly idle) issuer and gather
+// warps sit ABOVE the softmax warps: as warp 0 the issuer was starved of issue slots and every MMA hand-off took ~500
+// cycles.  TWO issuer threads: with one, S of a later unit queued behind the blocking wait for P of an earlier one
+// (a convoy that left the softmax warps waiting for S two thirds of the time, tools trace of round 1).
 constexpr int kThreads = 640;
-constexpr int kIssuerWarp = 19;
+constexpr int kIssuerWarp = 19;      // P V issuer (also allocates TMEM)
+constexpr int kSIssuerWarp = 18;     // Q K^T issuer
 constexpr int kSoftmax = 512;
-constexpr int kLoaders = 96;
+constexpr int kLoaders = 64;
 // register budget: 640 threads x 96 at launch = 61440 = 128 x kRegService + 512 x kRegSoftmax
 constexpr int kRegService = 64, kRegSoftmax = 104;
 constexpr int NSTAGE = 4, LAG = 2;
@@ -98,6 +101,19 @@ struct Cfg {
   static_assert(!INPLACE || (OA + HD <= KA && OB + HD <= NPAD), "accumulators must fit behind the packed P");
   static constexpr int SLOTW = INPLACE ? NPAD : NPAD + 2 * HD;        // TMEM columns per slot
   static constexpr int NSLOT = 512 / SLOTW > 4 ? 4 : 512 / SLOTW;
+  // Slot of a unit and how often that slot has been used before.  One tile per item: a plain ring.  Two tiles (12x12):
+  // slots by ROLE -- the main tile of unit group g lives in slot g, every tail in slot 2 -- so that S of a group's
+  // next item is issued as soon as the epilogue of its current main tile has drained the slot, i.e. while the group
+  // is still busy with the tail (with a ring, the next main tile had to wait for the tail's slot).
+  static constexpr bool ROLES = MT == 2 && NSLOT >= 3;
+  __device__ static __forceinline__ int slot_of(int u) {
+    if constexpr (ROLES) return (u & 1) ? 2 : ((u >> 1) & 1);
+    else return u % NSLOT;
+  }
+  __device__ static __forceinline__ uint32_t uses_of(int u) {
+    if constexpr (ROLES) return (u & 1) ? (uint32_t)(u >> 1) : (uint32_t)(u >> 2);
+    else return (uint32_t)(u / NSLOT);
+  }
   static constexpr int NS = N + ((12 - N % 8) % 8);                 // bias row stride, NS % 8 == 4: float4 reads
   static_assert(NS % 8 == 4 && NS >= N, "bias stride");             //   of 8 consecutive rows hit 8 bank groups
   static constexpr uint32_t kRow = NPAD * 64;                       // one [NPAD][64 B] operand tile
@@ -258,22 +274,18 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
 
   if (warp >= 16) {
     reg_dec<kRegService>();
-    if (warp == kIssuerWarp) {
-      // =================================================================================== MMA issuer
+    if (warp == kSIssuerWarp) {
+      // =================================================================================== issuer of S = Q K^T
       if (lane == 0) {
-        // Fixed software pipeline (blocking, hardware-sleep waits -- a polling scheduler costs more issue slots than
-        // the MMAs themselves):  S runs D units ahead of PV, so the softmax warps always find their next S ready.
+        // runs ahead of the softmax as far as free slots (and gathered items) allow; blocking hardware-sleep waits
         constexpr uint32_t idesc_qk = ptx::make_idesc_bf16(128, NPAD, 0, 0);
-        constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, HD, 0, 1);   // A = P (TMEM), B = V MN-major
-        constexpr int D = NSLOT - 1;
         const uint64_t desc_k = ptx::make_smem_desc(0, 16, 512, kSw64);      // K-major Q / K tiles (64 B rows)
-        const uint64_t desc_v = ptx::make_smem_desc(0, 512, 512, kSw64);     // MN-major V tile
         const int U = n * MT;
-        auto issue_s = [&](int u) {
-          const int slot = u % NSLOT;
+        for (int u = 0; u < U; ++u) {
+          const int slot = CF::slot_of(u);
           const int il = u / MT, tile = u - il * MT, stage = il % NSTAGE;
           TR(10, u);
-          ptx::mbar_wait(&slot_free[slot], ((u / NSLOT) & 1) ^ 1);
+          ptx::mbar_wait(&slot_free[slot], (CF::uses_of(u) & 1) ^ 1);
           TR(11, u);
           if (tile == 0) ptx::mbar_wait(&kv_full[stage], (il / NSTAGE) & 1);
           TR(12, u);
@@ -287,14 +299,19 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
           ptx::mma_bf16_ss(t_s, ad + 2, bd + 2, idesc_qk, 1u);               // second k-step: +32 B
           ptx::mma_commit(&s_full[slot]);
           TR(13, u);
-        };
-        for (int u = 0; u < D && u < U; ++u) issue_s(u);
+        }
+      }
+    } else if (warp == kIssuerWarp) {
+      // =================================================================================== issuer of O = P V
+      if (lane == 0) {
+        constexpr uint32_t idesc_pv = ptx::make_idesc_bf16(128, HD, 0, 1);   // A = P (TMEM), B = V MN-major
+        const uint64_t desc_v = ptx::make_smem_desc(0, 512, 512, kSw64);     // MN-major V tile
+        const int U = n * MT;
         for (int u = 0; u < U; ++u) {
-          if (u + D < U) issue_s(u + D);
-          const int slot = u % NSLOT;
+          const int slot = CF::slot_of(u);
           const int il = u / MT, tile = u - il * MT, stage = il % NSTAGE;
           TR(14, u);
-          ptx::mbar_wait(&p_full[slot], (u / NSLOT) & 1);
+          ptx::mbar_wait(&p_full[slot], CF::uses_of(u) & 1);
           TR(15, u);
           ptx::tc_fence_after();
           const uint32_t v_s = base_u32 + (uint32_t)stage * CF::kStage + 2 * CF::kRow;
@@ -308,7 +325,9 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
                              (ks != 0 && ks != CF::KA / 16) ? 1u : 0u);
           }
           ptx::mma_commit(&o_full[slot]);
-          if (tile == MT - 1) ptx::mma_commit(&kv_empty[stage]);             // every MMA reading this stage retired
+          // every MMA reading this stage has retired: the S MMAs of the item (other thread) completed before the
+          // softmax that produced this P could start
+          if (tile == MT - 1) ptx::mma_commit(&kv_empty[stage]);
           TR(16, u);
         }
       }
@@ -426,8 +445,8 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
 #pragma unroll 1
       for (int tile = 0; tile < MT; ++tile) {
         const int u = il * MT + tile;
-        const int slot = u % NSLOT;
-        const uint32_t par = (u / NSLOT) & 1;
+        const int slot = CF::slot_of(u);
+        const uint32_t par = CF::uses_of(u) & 1;
         const bool rot_tile = CF::ROT && tile == MT - 1;
         int r;                                                            // in-window query row of this thread, or -1
         if (rot_tile) r = (q == ((il >> 1) & 3) && lane < CF::TAIL) ? tile * 128 + lane : -1;
