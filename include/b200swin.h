@@ -35,6 +35,7 @@ extern "C" {
 #define B200SWIN_EPI_GELU 1     /* out = gelu_erf(acc + bias); aux (optional) = gelu'(acc+bias) */
 #define B200SWIN_EPI_QKV 2      /* Swin-V2 qkv: + (q_bias,0,v_bias), L2-normalise q,k per head */
 #define B200SWIN_EPI_DGELU 3    /* out = acc * aux_in   (aux_in = the gelu' saved by EPI_GELU) */
+#define B200SWIN_EPI_ADD 4      /* out = acc + aux_in   (dgrad + the gradient of the residual branch) */
 
 int b200swin_version(void);
 const char* b200swin_last_error(void);
@@ -68,6 +69,19 @@ int b200swin_window_gather(const void* x, void* out, int B, int H, int W, int C,
 int b200swin_window_scatter(const void* win, void* out, int B, int H, int W, int C, int ws, int shift,
                             int elem_bytes, void* stream);
 int b200swin_shift_mask(float* out, int H, int W, int ws, int shift, void* stream);
+/* 2x2 patch merging as an index map.  Replaces the pad + four strided slices + cat of PatchMerging.forward
+ * (models/swin_transformer_v2.py:660-672):
+ *   backward = 0:  in = x[B,H,W,C]  ->  out = merged[B, ceil(H/2)*ceil(W/2), 4C],
+ *                  merged[b, i2*W2+j2, k*C+c] = x[b, 2*i2+(k&1), 2*j2+(k>>1), c]  (zero beyond H, W);
+ *   backward = 1:  in = d merged  ->  out = dx[B,H,W,C]  (the adjoint; pad positions dropped).
+ * C*elem_bytes must be a multiple of 16. */
+int b200swin_patch_merge(const void* in, void* out, int B, int H, int W, int C, int elem_bytes, int backward,
+                         void* stream);
+/* Patchify for the stride = kernel patch-embedding conv (PatchEmbed.forward, models/swin_transformer_v2.py:941-957):
+ *   cols[(b,i,j), c*ph*pw + kh*pw + kw] = x[b, c, i*ph+kh, j*pw+kw]   (zero beyond H, W; x is NCHW)
+ * so that conv(x, weight[E,Cin,ph,pw]) = b200swin_gemm_bf16(cols, weight viewed as [E, Cin*ph*pw]) in token layout. */
+int b200swin_patchify(const void* x, int x_dtype, void* cols, int cols_dtype, int B, int Cin, int H, int W, int ph,
+                      int pw, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * LayerNorm (+ DropPath scale + residual).  Replaces LayerNormFP32.forward
@@ -88,6 +102,17 @@ int b200swin_ln_bwd(const void* dy, const void* x, const float* gamma, const flo
                     const float* row_scale, int64_t rows_per_scale, void* dx, float* dgamma, float* dbeta,
                     float* dcolsum, int64_t rows, int C, int dtype, void* workspace, size_t workspace_bytes,
                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Continuous position bias table (cpb_mlp / rpe_mlp of Swin-V2).  Replaces the bias-table branch of
+ * WindowAttention.forward (models/swin_transformer_v2.py:304-313, rpe_output_type='sigmoid'):
+ *   table[T,nH] = 16 * sigmoid( relu(coords[T,2] @ W0[HID,2]^T + b0[HID]) @ W2[nH,HID]^T ),  all float32.
+ * bwd: given dtable (and the saved table) writes dW0, db0, dW2 (deterministic, no atomics).  nH <= 64.
+ * ------------------------------------------------------------------------------------------ */
+int b200swin_cpb_fwd(const float* coords, const float* w0, const float* b0, const float* w2, float* table, int T,
+                     int HID, int nH, void* stream);
+int b200swin_cpb_bwd(const float* coords, const float* w0, const float* b0, const float* w2, const float* table,
+                     const float* dtable, float* dw0, float* db0, float* dw2, int T, int HID, int nH, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Attention core.  Replaces, for attn_type='cosine_mh', the body of WindowAttention.forward between

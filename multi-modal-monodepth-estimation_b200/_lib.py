@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libb200swin.so")
 
 F32, BF16 = 0, 1
-EPI_NONE, EPI_GELU, EPI_QKV, EPI_DGELU = 0, 1, 2, 3
+EPI_NONE, EPI_GELU, EPI_QKV, EPI_DGELU, EPI_ADD = 0, 1, 2, 3, 4
 
 _lock = threading.Lock()
 _lib = None
@@ -33,6 +33,10 @@ SIGNATURES = {
     "b200swin_window_gather": (I, [P, P, I, I, I, I, I, I, I, P]),
     "b200swin_window_scatter": (I, [P, P, I, I, I, I, I, I, I, P]),
     "b200swin_shift_mask": (I, [P, I, I, I, I, P]),
+    "b200swin_patch_merge": (I, [P, P, I, I, I, I, I, I, P]),
+    "b200swin_patchify": (I, [P, I, P, I, I, I, I, I, I, I, P]),
+    "b200swin_cpb_fwd": (I, [P, P, P, P, P, I, I, I, P]),
+    "b200swin_cpb_bwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "b200swin_ln_fwd": (I, [P, P, P, P, P, L, P, P, P, L, I, F, I, P]),
     "b200swin_ln_bwd_workspace_bytes": (Z, [L, I]),
     "b200swin_ln_bwd": (I, [P, P, P, P, P, P, L, P, P, P, P, L, I, I, P, Z, P]),
@@ -77,7 +81,7 @@ class _Instrumented:
 # kernels launched per C-ABI call (for the bench's gpu_launches claim); split-K gemm adds its reduce
 KERNELS_PER_CALL = {
     "b200swin_silog_fwd": 2, "b200swin_silog_bwd": 1, "b200swin_window_gather": 1, "b200swin_window_scatter": 1,
-    "b200swin_shift_mask": 1, "b200swin_ln_fwd": 1, "b200swin_ln_bwd": 2, "b200swin_attn_fwd": 1,
+    "b200swin_shift_mask": 1, "b200swin_patch_merge": 1, "b200swin_patchify": 1, "b200swin_cpb_fwd": 1, "b200swin_cpb_bwd": 1, "b200swin_ln_fwd": 1, "b200swin_ln_bwd": 2, "b200swin_attn_fwd": 1,
     "b200swin_attn_bwd": 2, "b200swin_gemm_bf16": 1, "b200swin_split_bf16": 1, "b200swin_colsum": 2,
 }
 

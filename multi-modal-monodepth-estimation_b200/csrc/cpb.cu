@@ -1,0 +1,118 @@
+// Continuous position bias table of Swin-V2 (cpb_mlp / rpe_mlp), forward + backward.
+// Replaces WindowAttention.forward's bias-table part, models/swin_transformer_v2.py:304-313 with
+// rpe_output_type='sigmoid':
+//     hid   = relu(coords @ W0^T + b0)          coords [T, 2] (log-spaced offsets, T = (2ws-1)^2), W0 [HID, 2], b0 [HID]
+//     table = 16 * sigmoid(hid @ W2^T)          W2 [nH, HID] (no bias)  ->  table [T, nH] fp32
+// A few hundred kFLOP per block -- in PyTorch that is ~5 launches forward and ~10 backward per block, all of them
+// latency-bound; here it is one launch each way.  fp32 throughout (the reference runs this branch in fp32, :50-56).
+//   fwd: one CTA per table row t: the hidden vector goes to shared memory, then one warp per group of heads.
+//   bwd: one CTA per hidden unit k: threads stride over t, recompute hid[t,k], and accumulate
+//        dW2[:,k], dW0[k,:], db0[k] in registers; fixed-order block reduction (deterministic, no atomics).
+#include "common.cuh"
+#include "../../include/b200swin.h"
+
+namespace b200swin {
+
+constexpr int kCpbThreads = 128;
+constexpr int kCpbMaxHeads = 64;
+
+__global__ void __launch_bounds__(kCpbThreads)
+cpb_fwd_kernel(const float* __restrict__ coords, const float* __restrict__ w0, const float* __restrict__ b0,
+               const float* __restrict__ w2, float* __restrict__ table, int T, int HID, int nH) {
+  extern __shared__ float hid[];   // [HID]
+  const int t = blockIdx.x;
+  const float c0 = coords[2 * t], c1 = coords[2 * t + 1];
+  for (int k = threadIdx.x; k < HID; k += kCpbThreads)
+    hid[k] = fmaxf(fmaf(c0, w0[2 * k], fmaf(c1, w0[2 * k + 1], b0[k])), 0.f);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int h = warp; h < nH; h += kCpbThreads / 32) {
+    float s = 0.f;
+    for (int k = lane; k < HID; k += 32) s = fmaf(hid[k], w2[(int64_t)h * HID + k], s);
+    s = warp_sum(s);
+    if (lane == 0) table[(int64_t)t * nH + h] = 16.0f / (1.0f + __expf(-s));
+  }
+}
+
+// dz[t,h] = dtable[t,h] * y (1 - y/16),  y = table[t,h]   (16 sigmoid' = y (1 - y/16))
+__global__ void __launch_bounds__(kCpbThreads)
+cpb_bwd_kernel(const float* __restrict__ coords, const float* __restrict__ w0, const float* __restrict__ b0,
+               const float* __restrict__ w2, const float* __restrict__ table, const float* __restrict__ dtable,
+               float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw2, int T, int HID, int nH) {
+  __shared__ float red[kCpbThreads / 32][kCpbMaxHeads + 3];
+  const int k = blockIdx.x;
+  const float wa = w0[2 * k], wb = w0[2 * k + 1], bb = b0[k];
+  float acc[kCpbMaxHeads];           // dW2[h, k] partial sums (compile-time indexed below)
+#pragma unroll
+  for (int h = 0; h < kCpbMaxHeads; ++h) acc[h] = 0.f;
+  float g0 = 0.f, g1 = 0.f, gb = 0.f;
+  for (int t = threadIdx.x; t < T; t += kCpbThreads) {
+    const float c0 = coords[2 * t], c1 = coords[2 * t + 1];
+    const float pre = fmaf(c0, wa, fmaf(c1, wb, bb));
+    const float hv = fmaxf(pre, 0.f);
+    float dh = 0.f;
+#pragma unroll
+    for (int h = 0; h < kCpbMaxHeads; ++h) {
+      if (h < nH) {
+        const float y = table[(int64_t)t * nH + h];
+        const float dz = dtable[(int64_t)t * nH + h] * y * (1.0f - y * 0.0625f);
+        acc[h] = fmaf(dz, hv, acc[h]);
+        dh = fmaf(dz, w2[(int64_t)h * HID + k], dh);
+      }
+    }
+    if (pre > 0.f) {
+      g0 = fmaf(dh, c0, g0);
+      g1 = fmaf(dh, c1, g1);
+      gb += dh;
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int h = 0; h < kCpbMaxHeads; ++h) {
+    if (h < nH) {
+      const float s = warp_sum(acc[h]);
+      if (lane == 0) red[warp][h] = s;
+    }
+  }
+  g0 = warp_sum(g0); g1 = warp_sum(g1); gb = warp_sum(gb);
+  if (lane == 0) { red[warp][kCpbMaxHeads] = g0; red[warp][kCpbMaxHeads + 1] = g1; red[warp][kCpbMaxHeads + 2] = gb; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kCpbMaxHeads + 3; i += kCpbThreads) {
+    if (i < nH || i >= kCpbMaxHeads) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCpbThreads / 32; ++w) s += red[w][i];
+      if (i < nH) dw2[(int64_t)i * HID + k] = s;
+      else if (i == kCpbMaxHeads) dw0[2 * k] = s;
+      else if (i == kCpbMaxHeads + 1) dw0[2 * k + 1] = s;
+      else db0[k] = s;
+    }
+  }
+}
+
+}  // namespace b200swin
+
+using namespace b200swin;
+
+extern "C" int b200swin_cpb_fwd(const float* coords, const float* w0, const float* b0, const float* w2, float* table,
+                                int T, int HID, int nH, void* stream) {
+  BSW_REQUIRE(coords && w0 && b0 && w2 && table, "cpb_fwd: null pointer");
+  BSW_REQUIRE(T > 0 && HID > 0 && HID <= 8192 && nH > 0 && nH <= kCpbMaxHeads, "cpb_fwd: T=%d HID=%d nH=%d out of range",
+              T, HID, nH);
+  cpb_fwd_kernel<<<T, kCpbThreads, (size_t)HID * sizeof(float), (cudaStream_t)stream>>>(coords, w0, b0, w2, table, T, HID,
+                                                                                     nH);
+  BSW_LAUNCH_CHECK();
+  return B200SWIN_OK;
+}
+
+extern "C" int b200swin_cpb_bwd(const float* coords, const float* w0, const float* b0, const float* w2,
+                                const float* table, const float* dtable, float* dw0, float* db0, float* dw2, int T,
+                                int HID, int nH, void* stream) {
+  BSW_REQUIRE(coords && w0 && b0 && w2 && table && dtable && dw0 && db0 && dw2, "cpb_bwd: null pointer");
+  BSW_REQUIRE(T > 0 && HID > 0 && HID <= 8192 && nH > 0 && nH <= kCpbMaxHeads, "cpb_bwd: T=%d HID=%d nH=%d out of range",
+              T, HID, nH);
+  cpb_bwd_kernel<<<HID, kCpbThreads, 0, (cudaStream_t)stream>>>(coords, w0, b0, w2, table, dtable, dw0, db0, dw2, T, HID,
+                                                                 nH);
+  BSW_LAUNCH_CHECK();
+  return B200SWIN_OK;
+}

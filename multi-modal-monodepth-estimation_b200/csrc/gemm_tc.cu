@@ -230,7 +230,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, Stager& st, 
     }
     if (p.aux_out) store_chunk<OutT>(st, &p.tmAux, g, col0, row0, p.N);
     store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
-  } else if constexpr (EPI == B200SWIN_EPI_DGELU) {
+  } else if constexpr (EPI == B200SWIN_EPI_DGELU || EPI == B200SWIN_EPI_ADD) {
+    constexpr bool MUL = EPI == B200SWIN_EPI_DGELU;
     if constexpr (sizeof(OutT) == 2) {
       // this row's 64 bytes of gelu' were requested (4 x ld.global.v4) before the accumulator was read
 #pragma unroll
@@ -239,8 +240,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, Stager& st, 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
-          v[8 * j + 2 * e] *= f.x;
-          v[8 * j + 2 * e + 1] *= f.y;
+          v[8 * j + 2 * e] = MUL ? v[8 * j + 2 * e] * f.x : v[8 * j + 2 * e] + f.x;
+          v[8 * j + 2 * e + 1] = MUL ? v[8 * j + 2 * e + 1] * f.y : v[8 * j + 2 * e + 1] + f.y;
         }
       }
     } else {
@@ -252,7 +253,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, Stager& st, 
         for (int c = 0; c < 32; ++c) z[c] = 0.f;
       }
 #pragma unroll
-      for (int c = 0; c < 32; ++c) v[c] *= z[c];
+      for (int c = 0; c < 32; ++c) v[c] = MUL ? v[c] * z[c] : v[c] + z[c];
     }
     store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
   } else {  // B200SWIN_EPI_QKV: one 32-column chunk == one head of q, k or v  (swin_transformer_v2.py:283-293)
@@ -393,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     Stager st;
     st.base = smem_base + (uint32_t)STAGES * TL::kStageBytes + (uint32_t)(warp - 2) * kEpiUnitBytes;
     st.lane = lane;
-    constexpr bool aux_bf16 = EPI == B200SWIN_EPI_DGELU && OUT_BF16;
+    constexpr bool aux_bf16 = (EPI == B200SWIN_EPI_DGELU || EPI == B200SWIN_EPI_ADD) && OUT_BF16;
     // bf16 MUL epilogue (dgrad of fc2 times gelu'): every thread reads its row's 64 bytes of gelu' straight from global
     // memory, ONE UNIT AHEAD (the tile schedule is static), so the HBM latency hides behind the previous unit
     uint4 aux_next[4];
@@ -590,7 +591,7 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   BSW_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension exceeds 2^31");
   BSW_REQUIRE((a_lo == nullptr) == (b_lo == nullptr), "gemm: a_lo and b_lo must be given together");
   BSW_REQUIRE(out_dtype == B200SWIN_F32 || out_dtype == B200SWIN_BF16, "gemm: bad out dtype %d", out_dtype);
-  BSW_REQUIRE(epilogue >= B200SWIN_EPI_NONE && epilogue <= B200SWIN_EPI_DGELU, "gemm: bad epilogue %d", epilogue);
+  BSW_REQUIRE(epilogue >= B200SWIN_EPI_NONE && epilogue <= B200SWIN_EPI_ADD, "gemm: bad epilogue %d", epilogue);
   BSW_REQUIRE(N % 8 == 0, "gemm: N must be a multiple of 8 (16-byte rows for the TMA stores)");
   BSW_REQUIRE((a_mn_major ? M : K) % 8 == 0 && (b_mn_major ? N : K) % 8 == 0,
               "gemm: contiguous operand dimension must be a multiple of 8 (16-byte TMA rows)");
@@ -602,7 +603,8 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
     BSW_REQUIRE(splits == 1, "gemm: QKV epilogue cannot be split");
     p.Cq = (int)(N / 3);
   }
-  if (epilogue == B200SWIN_EPI_DGELU) BSW_REQUIRE(aux_in, "gemm: DGELU epilogue needs aux_in");
+  if (epilogue == B200SWIN_EPI_DGELU || epilogue == B200SWIN_EPI_ADD)
+    BSW_REQUIRE(aux_in, "gemm: DGELU / ADD epilogues need aux_in");
   if (splits > 1) {
     BSW_REQUIRE(epilogue == B200SWIN_EPI_NONE, "gemm: split-K supports only the plain epilogue");
     BSW_REQUIRE(workspace && workspace_bytes >= b200swin_gemm_workspace_bytes(M, N, splits),
@@ -665,9 +667,12 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   } else if (epilogue == B200SWIN_EPI_QKV) {
     BSW_REQUIRE(!a_mn_major && !b_mn_major, "gemm: the QKV epilogue is built for K-major operands only");
     LAUNCH_BN(false, false, B200SWIN_EPI_QKV);
-  } else {
+  } else if (epilogue == B200SWIN_EPI_DGELU) {
     BSW_REQUIRE(!a_mn_major && b_mn_major, "gemm: the DGELU epilogue is built for the dgrad layout (B MN-major) only");
     LAUNCH_BN(false, true, B200SWIN_EPI_DGELU);
+  } else {
+    BSW_REQUIRE(!a_mn_major && b_mn_major, "gemm: the ADD epilogue is built for the dgrad layout (B MN-major) only");
+    LAUNCH_BN(false, true, B200SWIN_EPI_ADD);
   }
 #undef LAUNCH_BN
 #undef LAUNCH_OB

@@ -34,6 +34,73 @@ window_move_kernel(const V* __restrict__ src, V* __restrict__ dst, WinGeom g, in
   }
 }
 
+// 2x2 patch merging as an index map (reference PatchMerging.forward, models/swin_transformer_v2.py:660-672: zero-pad H, W
+// to even, cat([x[:,0::2,0::2], x[:,1::2,0::2], x[:,0::2,1::2], x[:,1::2,1::2]], -1)):
+//   merged[b, i2*W2 + j2, k*C + c] = x[b, 2*i2 + (k & 1), 2*j2 + (k >> 1), c]      (zero beyond H, W)
+// kGather: x -> merged;  !kGather: the adjoint (gradient of merged -> gradient of x; pad positions are dropped).
+// One 16-byte vector per thread, indexed over the x-shaped tensor for the scatter and the merged one for the gather,
+// so every store is coalesced and written exactly once.
+template <bool kGather>
+__global__ void __launch_bounds__(256)
+patch_merge_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int H, int W, int H2, int W2,
+                   int row_vecs /* 16-byte vectors per C */, int64_t total) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+    if (kGather) {
+      // v over merged [B, H2, W2, 4, row_vecs]
+      int cv = (int)(v % row_vecs);
+      int64_t t = v / row_vecs;
+      const int k = (int)(t & 3);
+      t >>= 2;
+      const int j2 = (int)(t % W2);
+      t /= W2;
+      const int i2 = (int)(t % H2);
+      const int b = (int)(t / H2);
+      const int i = 2 * i2 + (k & 1), j = 2 * j2 + (k >> 1);
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (i < H && j < W) val = src[(((int64_t)b * H + i) * W + j) * row_vecs + cv];
+      dst[v] = val;
+    } else {
+      // v over x [B, H, W, row_vecs]
+      int cv = (int)(v % row_vecs);
+      int64_t t = v / row_vecs;
+      const int j = (int)(t % W);
+      t /= W;
+      const int i = (int)(t % H);
+      const int b = (int)(t / H);
+      const int k = (i & 1) + 2 * (j & 1);
+      dst[v] = src[((((int64_t)b * H2 + (i >> 1)) * W2 + (j >> 1)) * 4 + k) * row_vecs + cv];
+    }
+  }
+}
+
+// Patchify for the stride = kernel patch-embedding conv (reference PatchEmbed.forward, models/swin_transformer_v2.py:
+// 941-957): the conv IS a GEMM over non-overlapping patches,
+//   cols[(b, i, j), c*ph*pw + kh*pw + kw] = x[b, c, i*ph + kh, j*pw + kw]       (zero beyond H, W: the reference pads)
+// with the conv weight [E, Cin, ph, pw] viewed as [E, Cin*ph*pw].  One thread per (patch, c, kh): pw contiguous pixels.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const TI* __restrict__ x, TO* __restrict__ cols, int B, int Cin, int H, int W, int ph, int pw, int Hp,
+                int Wp, int64_t total) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+    // consecutive threads -> consecutive patches j of the same (b, i, c, kh): coalesced reads of one image row
+    int j = (int)(v % Wp);
+    int64_t t = v / Wp;
+    const int kh = (int)(t % ph);
+    t /= ph;
+    const int c = (int)(t % Cin);
+    t /= Cin;
+    const int i = (int)(t % Hp);
+    const int b = (int)(t / Hp);
+    const int y = i * ph + kh;
+    const TI* src = x + (((int64_t)b * Cin + c) * H + y) * W + (int64_t)j * pw;
+    TO* dst = cols + ((((int64_t)b * Hp + i) * Wp + j) * Cin + c) * (ph * pw) + kh * pw;
+    for (int kw = 0; kw < pw; ++kw) {
+      const float val = (y < H && j * pw + kw < W) ? Io<TI>::ld(src + kw) : 0.f;
+      Io<TO>::st(dst + kw, val);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 shift_mask_kernel(float* __restrict__ out, int Hp, int Wp, int ws, int shift, int nWw, int64_t total) {
   const int N = ws * ws;
@@ -112,6 +179,52 @@ extern "C" int b200swin_shift_mask(float* out, int H, int W, int ws, int shift, 
   int64_t cap = (int64_t)sm_count() * 16;
   shift_mask_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(out, Hp, Wp, ws, shift,
                                                                                        nWw, total);
+  BSW_LAUNCH_CHECK();
+  return B200SWIN_OK;
+}
+
+extern "C" int b200swin_patch_merge(const void* in, void* out, int B, int H, int W, int C, int elem_bytes, int backward,
+                                    void* stream) {
+  BSW_REQUIRE(in && out, "patch_merge: null pointer");
+  BSW_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "patch_merge: non-positive dimension");
+  BSW_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "patch_merge: elem_bytes %d", elem_bytes);
+  const int64_t row_bytes = (int64_t)C * elem_bytes;
+  BSW_REQUIRE(row_bytes % 16 == 0, "patch_merge: C * elem_bytes = %lld must be a multiple of 16", (long long)row_bytes);
+  BSW_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+              "patch_merge: pointers must be 16-byte aligned");
+  const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  const int row_vecs = (int)(row_bytes / 16);
+  const int64_t total = backward ? (int64_t)B * H * W * row_vecs : (int64_t)B * H2 * W2 * 4 * row_vecs;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (backward)
+    patch_merge_kernel<false><<<grid, 256, 0, st>>>((const uint4*)in, (uint4*)out, B, H, W, H2, W2, row_vecs, total);
+  else
+    patch_merge_kernel<true><<<grid, 256, 0, st>>>((const uint4*)in, (uint4*)out, B, H, W, H2, W2, row_vecs, total);
+  BSW_LAUNCH_CHECK();
+  return B200SWIN_OK;
+}
+
+extern "C" int b200swin_patchify(const void* x, int x_dtype, void* cols, int cols_dtype, int B, int Cin, int H, int W,
+                                 int ph, int pw, void* stream) {
+  BSW_REQUIRE(x && cols, "patchify: null pointer");
+  BSW_REQUIRE(B > 0 && Cin > 0 && H > 0 && W > 0 && ph > 0 && pw > 0, "patchify: non-positive dimension");
+  BSW_REQUIRE((x_dtype == B200SWIN_F32 || x_dtype == B200SWIN_BF16) && (cols_dtype == B200SWIN_F32 || cols_dtype == B200SWIN_BF16),
+              "patchify: bad dtype");
+  const int Hp = (H + ph - 1) / ph, Wp = (W + pw - 1) / pw;
+  const int64_t total = (int64_t)B * Hp * Cin * ph * Wp;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PF(TI, TO) patchify_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)x, (TO*)cols, B, Cin, H, W, ph, pw, Hp, Wp, total)
+  if (x_dtype == B200SWIN_F32 && cols_dtype == B200SWIN_BF16) PF(float, __nv_bfloat16);
+  else if (x_dtype == B200SWIN_F32) PF(float, float);
+  else if (cols_dtype == B200SWIN_BF16) PF(__nv_bfloat16, __nv_bfloat16);
+  else PF(__nv_bfloat16, float);
+#undef PF
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
 }

@@ -110,6 +110,58 @@ def window_scatter(win, B, H, W, ws, shift=0):
     return _WindowScatter.apply(win, int(B), int(H), int(W), int(ws), int(shift))
 
 
+class _PatchMerge(torch.autograd.Function):
+    """x[B,H,W,C] -> [B, ceil(H/2)*ceil(W/2), 4C]: zero-pad to even + the four strided slices + cat of
+    PatchMerging.forward (swin_transformer_v2.py:660-672) as ONE gather; backward is the adjoint scatter."""
+
+    @staticmethod
+    def forward(ctx, x):
+        L.require_cuda(x)
+        lib = L.load()
+        B, H, W, C = x.shape
+        xc = x.contiguous()
+        H2, W2 = (H + 1) // 2, (W + 1) // 2
+        with torch.cuda.device_of(xc):
+            out = torch.empty((B, H2 * W2, 4 * C), dtype=x.dtype, device=x.device)
+            L.check(lib.b200swin_patch_merge(xc.data_ptr(), out.data_ptr(), B, H, W, C, xc.element_size(), 0,
+                                             L.stream_of(xc)), "patch_merge")
+        ctx.geom = (B, H, W, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, H, W, C = ctx.geom
+        lib = L.load()
+        gc = g.contiguous()
+        with torch.cuda.device_of(gc):
+            dx = torch.empty((B, H, W, C), dtype=g.dtype, device=g.device)
+            L.check(lib.b200swin_patch_merge(gc.data_ptr(), dx.data_ptr(), B, H, W, C, gc.element_size(), 1,
+                                             L.stream_of(gc)), "patch_merge(bwd)")
+        return dx
+
+
+def patch_merge(x):
+    return _PatchMerge.apply(x)
+
+
+def patchify(x, ph, pw, out_dtype):
+    """x[B,Cin,H,W] (no gradient) -> cols[B*ceil(H/ph)*ceil(W/pw), Cin*ph*pw] in `out_dtype` (see b200swin_patchify)."""
+    L.require_cuda(x)
+    if x.requires_grad and torch.is_grad_enabled():
+        raise RuntimeError("patchify: the input image must not require a gradient")
+    lib = L.load()
+    xc = x.contiguous()
+    if xc.dtype not in (torch.float32, torch.bfloat16):
+        xc = xc.float()
+    B, Cin, H, W = xc.shape
+    Hp, Wp = (H + ph - 1) // ph, (W + pw - 1) // pw
+    with torch.cuda.device_of(xc):
+        cols = torch.empty((B * Hp * Wp, Cin * ph * pw), dtype=out_dtype, device=x.device)
+        L.check(lib.b200swin_patchify(xc.data_ptr(), L.dtype_code(xc), cols.data_ptr(), L.dtype_code(cols), B, Cin, H, W,
+                                      ph, pw, L.stream_of(xc)), "patchify")
+    return cols, Hp, Wp
+
+
 def shift_mask(H, W, ws, shift, device):
     lib = L.load()
     Hp, Wp = (H + ws - 1) // ws * ws, (W + ws - 1) // ws * ws
@@ -294,6 +346,17 @@ def _wgrad(dy_op: Operand, x_op: Operand, M: int, N: int, K: int) -> torch.Tenso
     return gemm(dy_op, x_op, N, K, M, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=splits)
 
 
+def _dgrad_plus(dyo: Operand, wo: Operand, M: int, K: int, N: int, cd, dres):
+    """dX[M,K] = dY . W (W read as stored) + dres, the addition fused into the GEMM epilogue when dres has the
+    output's type and shape."""
+    if dres is None:
+        return gemm(dyo, wo, M, K, N, b_mn=True, out_dtype=cd)
+    r = dres.reshape(M, K)
+    if r.dtype != cd:
+        r = r.to(cd)
+    return gemm(dyo, wo, M, K, N, b_mn=True, epilogue=L.EPI_ADD, aux_in=r.contiguous(), out_dtype=cd)
+
+
 class _Linear(torch.autograd.Function):
     """y = x @ W^T + b on tcgen05 (reference: nn.Linear at swin_transformer_v2.py:334 and others)."""
 
@@ -349,7 +412,10 @@ class _Mlp(torch.autograd.Function):
     (reference: Mlp.forward, swin_transformer_v2.py:76-89; exact-erf GELU)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2):
+    def forward(ctx, x, w1, b1, w2, b2, passthrough=False):
+        # passthrough: also return x itself (as a view).  The caller routes its residual branch through that alias, so
+        # the gradient of the residual arrives HERE and is added in the epilogue of the last dgrad GEMM instead of in
+        # a separate elementwise pass by the autograd engine.
         L.require_cuda(x, w1, b1, w2, b2)
         cd = compute_dtype(x)
         exact = cd == torch.float32
@@ -367,11 +433,15 @@ class _Mlp(torch.autograd.Function):
         ctx.save_for_backward(xo.hi, xo.lo, z, ho.hi, ho.lo, w1, w2)
         ctx.cd, ctx.xdtype, ctx.xshape = cd, x.dtype, x.shape
         ctx.bd = (b1.dtype if b1 is not None else None, b2.dtype if b2 is not None else None)
-        return y.view(*x.shape[:-1], Co)
+        ctx.set_materialize_grads(False)
+        y = y.view(*x.shape[:-1], Co)
+        return (y, x.view_as(x)) if passthrough else y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dres=None):
         xhi, xlo, z, hhi, hlo, w1, w2 = ctx.saved_tensors
+        if dy is None:                                   # only the alias was used downstream
+            return dres, None, None, None, None, None
         exact = ctx.cd == torch.float32
         Hd, C = w1.shape
         Co = w2.shape[0]
@@ -389,14 +459,14 @@ class _Mlp(torch.autograd.Function):
         db1 = colsum(dz).to(ctx.bd[0]) if (ctx.bd[0] is not None and ctx.needs_input_grad[2]) else None
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = gemm(dzo, stage_weight(w1, exact), M, C, Hd, b_mn=True, out_dtype=ctx.cd).view(ctx.xshape)
+            dx = _dgrad_plus(dzo, stage_weight(w1, exact), M, C, Hd, ctx.cd, dres).view(ctx.xshape)
             if dx.dtype != ctx.xdtype:
                 dx = dx.to(ctx.xdtype)
-        return dx, dw1, db1, dw2, db2
+        return dx, dw1, db1, dw2, db2, None
 
 
-def mlp(x, w1, b1, w2, b2):
-    return _Mlp.apply(x, w1, b1, w2, b2)
+def mlp(x, w1, b1, w2, b2, passthrough=False):
+    return _Mlp.apply(x, w1, b1, w2, b2, passthrough)
 
 
 class _QKV(torch.autograd.Function):
@@ -406,7 +476,8 @@ class _QKV(torch.autograd.Function):
     UN-normalised q, k (the attention backward applies the F.normalize backward with inv_norm)."""
 
     @staticmethod
-    def forward(ctx, x, weight, q_bias, v_bias, nH):
+    def forward(ctx, x, weight, q_bias, v_bias, nH, passthrough=False):
+        # passthrough: see _Mlp.forward
         L.require_cuda(x, weight, q_bias, v_bias)
         cd = compute_dtype(x)
         exact = cd == torch.float32
@@ -424,11 +495,14 @@ class _QKV(torch.autograd.Function):
         ctx.has_bias = q_bias is not None
         ctx.bdtype = q_bias.dtype if q_bias is not None else None
         ctx.mark_non_differentiable(inv_norm)
-        return qkv, inv_norm
+        ctx.set_materialize_grads(False)
+        return (qkv, inv_norm, x.view_as(x)) if passthrough else (qkv, inv_norm)
 
     @staticmethod
-    def backward(ctx, dqkv, _):
+    def backward(ctx, dqkv, _, dres=None):
         xhi, xlo, weight = ctx.saved_tensors
+        if dqkv is None:
+            return dres, None, None, None, None, None
         exact = ctx.cd == torch.float32
         N, K = weight.shape
         C = N // 3
@@ -440,7 +514,7 @@ class _QKV(torch.autograd.Function):
         do = stage_operand(d2, exact)
         dx = None
         if ctx.needs_input_grad[0]:
-            dx = gemm(do, stage_weight(weight, exact), M, K, N, b_mn=True, out_dtype=ctx.cd).view(ctx.xshape)
+            dx = _dgrad_plus(do, stage_weight(weight, exact), M, K, N, ctx.cd, dres).view(ctx.xshape)
             if dx.dtype != ctx.xdtype:
                 dx = dx.to(ctx.xdtype)
         dw = _wgrad(do, Operand(xhi, xlo), M, N, K).to(weight.dtype)
@@ -448,11 +522,50 @@ class _QKV(torch.autograd.Function):
         if ctx.has_bias:
             dqb = colsum(d2, 0, C).to(ctx.bdtype)
             dvb = colsum(d2, 2 * C, C).to(ctx.bdtype)
-        return dx, dw, dqb, dvb, None
+        return dx, dw, dqb, dvb, None, None
 
 
-def qkv_project(x, weight, q_bias, v_bias, nH):
-    return _QKV.apply(x, weight, q_bias, v_bias, int(nH))
+def qkv_project(x, weight, q_bias, v_bias, nH, passthrough=False):
+    return _QKV.apply(x, weight, q_bias, v_bias, int(nH), passthrough)
+
+
+# ------------------------------------------------------------------------------ continuous position bias table
+class _CpbTable(torch.autograd.Function):
+    """table16[T,nH] = 16 sigmoid(relu(coords W0^T + b0) W2^T) in one kernel each way
+    (reference: rpe_mlp + sigmoid, swin_transformer_v2.py:304-313)."""
+
+    @staticmethod
+    def forward(ctx, coords, w0, b0, w2):
+        L.require_cuda(coords, w0, b0, w2)
+        lib = L.load()
+        c = coords.reshape(-1, 2).contiguous().float()
+        w0c, b0c, w2c = w0.contiguous().float(), b0.contiguous().float(), w2.contiguous().float()
+        T, HID, nH = c.shape[0], w0c.shape[0], w2c.shape[0]
+        with torch.cuda.device_of(c):
+            table = torch.empty((T, nH), dtype=torch.float32, device=c.device)
+            L.check(lib.b200swin_cpb_fwd(c.data_ptr(), w0c.data_ptr(), b0c.data_ptr(), w2c.data_ptr(), table.data_ptr(),
+                                         T, HID, nH, L.stream_of(c)), "cpb_fwd")
+        ctx.save_for_backward(c, w0c, b0c, w2c, table)
+        ctx.dtypes = (w0.dtype, b0.dtype, w2.dtype)
+        return table
+
+    @staticmethod
+    def backward(ctx, dtable):
+        c, w0c, b0c, w2c, table = ctx.saved_tensors
+        lib = L.load()
+        T, HID, nH = c.shape[0], w0c.shape[0], w2c.shape[0]
+        dt = dtable.contiguous().float()
+        with torch.cuda.device_of(c):
+            dw0, db0, dw2 = torch.empty_like(w0c), torch.empty_like(b0c), torch.empty_like(w2c)
+            L.check(lib.b200swin_cpb_bwd(c.data_ptr(), w0c.data_ptr(), b0c.data_ptr(), w2c.data_ptr(), table.data_ptr(),
+                                         dt.data_ptr(), dw0.data_ptr(), db0.data_ptr(), dw2.data_ptr(), T, HID, nH,
+                                         L.stream_of(c)), "cpb_bwd")
+        d0, d1, d2 = ctx.dtypes
+        return None, dw0.to(d0), db0.to(d1), dw2.to(d2)
+
+
+def cpb_table(coords, w0, b0, w2):
+    return _CpbTable.apply(coords, w0, b0, w2)
 
 
 # ------------------------------------------------------------------------------ attention core

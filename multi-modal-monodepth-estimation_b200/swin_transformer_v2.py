@@ -98,10 +98,11 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
         self.norm = None
 
-    def forward(self, x, H=None, W=None, fc2_bias_grad_elsewhere=False):
+    def forward(self, x, H=None, W=None, fc2_bias_grad_elsewhere=False, passthrough=False):
         # fc2_bias_grad_elsewhere: the caller's LayerNorm backward returns fc2.bias' gradient (ops.layer_norm_residual)
+        # passthrough: also return an alias of x for the caller's residual branch (ops._Mlp.forward)
         b2 = self.fc2.bias.detach() if (fc2_bias_grad_elsewhere and self.fc2.bias is not None) else self.fc2.bias
-        return ops.mlp(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, b2)
+        return ops.mlp(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, b2, passthrough)
 
 
 def window_partition(x, window_size):
@@ -198,6 +199,11 @@ class WindowAttention(nn.Module):
     # -- small host-side pieces (a few kFLOP; autograd carries their gradients) ---------------------
     def _bias_table(self):
         """[(2ws-1)^2, nH] fp32: rpe_mlp(coords) then 16*sigmoid (reference :304-313)."""
+        l0, l2 = self.rpe_mlp[0], self.rpe_mlp[2]
+        if (self.rpe_output_type == 'sigmoid' and self.relative_coords_table.is_cuda and l2.bias is None
+                and self.num_heads <= 64):
+            # one kernel forward, one backward (the PyTorch graph below is ~15 latency-bound launches per block)
+            return ops.cpb_table(self.relative_coords_table, l0.weight, l0.bias, l2.weight)
         with torch.autocast('cuda', enabled=False):
             t = self.rpe_mlp(self.relative_coords_table.float()).view(-1, self.num_heads)
             if self.rpe_output_type == 'sigmoid':
@@ -215,17 +221,22 @@ class WindowAttention(nn.Module):
             qpad = F.normalize(self.q_bias.float().view(self.num_heads, -1), dim=-1).reshape(-1)
         return qpad, self.v_bias
 
-    def attend(self, x, B, H, W, shift, mask=None, proj_bias_grad_elsewhere=False):
+    def attend(self, x, B, H, W, shift, mask=None, proj_bias_grad_elsewhere=False, passthrough=False):
         """x: [B, H*W, C] natural order -> [B, H*W, C]: qkv GEMM, windowed attention over the (padded,
         rolled) grid, proj GEMM.  proj_bias_grad_elsewhere: the caller's LayerNorm backward returns proj.bias'
         gradient (ops.layer_norm_residual(..., producer_bias=...))."""
         C, nH, ws = self.dim, self.num_heads, self.window_size[0]
-        qkv, inv_norm = ops.qkv_project(x, self.qkv.weight, self.q_bias, self.v_bias, nH)
+        x_alias = None
+        if passthrough:        # alias of x for the caller's residual branch: its gradient is added in the qkv dgrad epilogue
+            qkv, inv_norm, x_alias = ops.qkv_project(x, self.qkv.weight, self.q_bias, self.v_bias, nH, True)
+        else:
+            qkv, inv_norm = ops.qkv_project(x, self.qkv.weight, self.q_bias, self.v_bias, nH)
         qpad, vpad = self._pads(H % ws != 0 or W % ws != 0)
         o = ops.attention_core(qkv.view(B, H, W, 3 * C), inv_norm, self._bias_table(), self._scale(), qpad, vpad, mask,
                                B, H, W, C, nH, ws, shift)
         pb = self.proj.bias.detach() if (proj_bias_grad_elsewhere and self.proj.bias is not None) else self.proj.bias
-        return ops.linear(o.view(B, H * W, C), self.proj.weight, pb)
+        y = ops.linear(o.view(B, H * W, C), self.proj.weight, pb)
+        return (y, x_alias) if passthrough else y
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C) window-major; mask: (nW, N, N) additive or None  (reference :275-336)."""
@@ -302,12 +313,19 @@ class SwinTransformerBlockPost(_SwinBlockBase):
         # bf16 path: the bias gradients of proj and fc2 are the column sums of the LayerNorm backward's dx and come
         # out of that kernel (no separate pass over dx)
         fuse = torch.is_grad_enabled() and ops.ln_colsum_supported(ops.compute_dtype(x), self.dim)
-        a = self._attention(x, mask_matrix, fuse)
-        x = ops.layer_norm_residual(a, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=x,
+        # the residual branches run through aliases of x handed back by the qkv / MLP functions, so that the residual
+        # gradients are added inside the dgrad GEMM epilogues (no elementwise gradient-accumulation passes)
+        direct = not (self.shift_size > 0 and torch.is_tensor(mask_matrix))
+        if direct:
+            assert L == self.H * self.W, f"input feature has wrong size, with L = {L}, H = {self.H}, W = {self.W}"
+            a, xr = self.attn.attend(x, x.shape[0], self.H, self.W, self.shift_size, None, fuse, True)
+        else:
+            a, xr = self._attention(x, mask_matrix, fuse), x
+        x = ops.layer_norm_residual(a, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=xr,
                                     row_scale=self._drop_scale(x), rows_per_scale=L,
                                     producer_bias=self.attn.proj.bias if fuse else None)
-        m = self.mlp(x, self.H, self.W, fuse)
-        return ops.layer_norm_residual(m, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=x,
+        m, xr = self.mlp(x, self.H, self.W, fuse, True)
+        return ops.layer_norm_residual(m, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=xr,
                                        row_scale=self._drop_scale(x), rows_per_scale=L,
                                        producer_bias=self.mlp.fc2.bias if fuse else None)
 
@@ -341,8 +359,8 @@ class SwinTransformerBlockPre(_SwinBlockBase):
 
 class PatchMerging(nn.Module):
     """2x2 patch merging (reference :633-678): strided gather + Linear(4C, 2C, no bias) + LayerNorm.
-    The gather is index plumbing on views (stage glue); the contraction and the norm run
-    in the b200swin kernels."""
+    The pad + gather is one index-map kernel (and its adjoint in the backward); the contraction and the norm run in
+    the b200swin GEMM / LayerNorm kernels."""
 
     def __init__(self, dim, norm_layer=nn.LayerNorm, postnorm=True):
         super().__init__()
@@ -354,11 +372,7 @@ class PatchMerging(nn.Module):
     def forward(self, x, H, W):
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
-        x = x.view(B, H, W, C)
-        if H % 2 == 1 or W % 2 == 1:
-            x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
-        x = torch.cat([x[:, 0::2, 0::2, :], x[:, 1::2, 0::2, :], x[:, 0::2, 1::2, :], x[:, 1::2, 1::2, :]], -1)
-        x = x.view(B, -1, 4 * C)
+        x = ops.patch_merge(x.view(B, H, W, C))          # pad to even + 2x2 gather in one kernel: [B, H2*W2, 4C]
         if self.postnorm:
             x = ops.linear(x, self.reduction.weight, None)
             return ops.layer_norm_residual(x, self.norm.weight, self.norm.bias, self.norm.eps)
@@ -425,8 +439,10 @@ class BasicLayer(nn.Module):
 
 
 class PatchEmbed(nn.Module):
-    """4x4 stride-4 conv patch embedding + LayerNorm (reference :918-957).  The conv is stage glue outside the
-    hot path and runs through torch/cuDNN; the norm runs in the b200swin kernel."""
+    """4x4 stride-4 conv patch embedding + LayerNorm (reference :918-957).  A conv whose stride equals its kernel is a
+    GEMM over non-overlapping patches: one patchify kernel (NCHW image -> [patches, Cin*ph*pw]) feeds the b200swin GEMM
+    with the conv weight viewed as [E, Cin*ph*pw]; the result is already in token layout for the norm and the blocks
+    (no NCHW <-> NHWC transposes, no cuDNN)."""
 
     def __init__(self, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
         super().__init__()
@@ -436,20 +452,32 @@ class PatchEmbed(nn.Module):
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=self.patch_size, stride=self.patch_size)
         self.norm = norm_layer(embed_dim) if norm_layer is not None else None
 
-    def forward(self, x):
-        _, _, H, W = x.size()
+    def forward_tokens(self, x):
+        """x[B,Cin,H,W] -> (tokens [B, Wh*Ww, E], Wh, Ww)."""
+        B = x.shape[0]
         ph, pw = self.patch_size
-        if W % pw != 0:
-            x = F.pad(x, (0, pw - W % pw))
-        if H % ph != 0:
-            x = F.pad(x, (0, 0, 0, ph - H % ph))
-        x = self.proj(x)
+        K = self.in_chans * ph * pw
+        if K % 8 == 0 and self.embed_dim % 8 == 0 and not (x.requires_grad and torch.is_grad_enabled()):
+            cols, Wh, Ww = ops.patchify(x, ph, pw, ops.compute_dtype(x))
+            t = ops.linear(cols, self.proj.weight.view(self.embed_dim, K), self.proj.bias).view(B, Wh * Ww, self.embed_dim)
+        else:
+            # general case (input gradient wanted, or rows that are not 16-byte multiples): cuDNN conv + transpose
+            _, _, H, W = x.size()
+            if W % pw != 0:
+                x = F.pad(x, (0, pw - W % pw))
+            if H % ph != 0:
+                x = F.pad(x, (0, 0, 0, ph - H % ph))
+            y = self.proj(x)
+            Wh, Ww = y.size(2), y.size(3)
+            t = y.flatten(2).transpose(1, 2).contiguous()
         if self.norm is not None:
-            Wh, Ww = x.size(2), x.size(3)
-            t = x.flatten(2).transpose(1, 2).contiguous()
             t = ops.layer_norm_residual(t, self.norm.weight, self.norm.bias, self.norm.eps)
-            x = t.transpose(1, 2).reshape(-1, self.embed_dim, Wh, Ww)
-        return x
+        return t, Wh, Ww
+
+    def forward(self, x):
+        """Reference contract: NCHW feature map [B, E, Wh, Ww]."""
+        t, Wh, Ww = self.forward_tokens(x)
+        return t.transpose(1, 2).reshape(-1, self.embed_dim, Wh, Ww)
 
 
 class SwinTransformerV2(nn.Module):
@@ -579,9 +607,7 @@ class SwinTransformerV2(nn.Module):
             raise TypeError('pretrained must be a str or None')
 
     def forward(self, x):
-        x = self.patch_embed(x)
-        Wh, Ww = x.size(2), x.size(3)
-        x = x.flatten(2).transpose(1, 2).contiguous()
+        x, Wh, Ww = self.patch_embed.forward_tokens(x)
         outs = []
         for i in range(self.num_layers):
             x_out, H, W, x, Wh, Ww = self.layers[i](x, Wh, Ww)

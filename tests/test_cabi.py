@@ -30,7 +30,8 @@ def lib():
 def test_header_declares_expected_entry_points():
     syms = declared_symbols()
     for must in ["b200swin_version", "b200swin_last_error", "b200swin_silog_fwd", "b200swin_silog_bwd",
-                 "b200swin_window_gather", "b200swin_window_scatter", "b200swin_shift_mask",
+                 "b200swin_window_gather", "b200swin_window_scatter", "b200swin_shift_mask", "b200swin_patch_merge", "b200swin_patchify",
+                 "b200swin_cpb_fwd", "b200swin_cpb_bwd",
                  "b200swin_ln_fwd", "b200swin_ln_bwd"]:
         assert must in syms
 
