@@ -260,35 +260,35 @@ __device__ __forceinline__ void bwd_main(uint32_t t_row, uint32_t s_col, uint32_
     const int slot0 = c0 >> 3, r7 = row_local & 7;
     unsigned char* prow = Pp + row_local * 128;
     unsigned char* drow = dSp + row_local * 128;
-    uint32_t svb[2][4], dvb[2][4];
-    tmem_ld4(s_base, svb[0]);
-    tmem_ld4(dp_base, dvb[0]);
+    // eight keys per step (one 16-byte panel slot), the TMEM loads of step cc + 1 in flight during the math of step cc
+    static_assert(NC % 8 == 0, "key ranges are whole 16-byte panel slots");
+    uint32_t svb[2][8], dvb[2][8];
+    tmem_ld8(s_base, svb[0]);
+    tmem_ld8(dp_base, dvb[0]);
 #pragma unroll
-    for (int cc = 0; cc < NC / 4; ++cc) {
+    for (int cc = 0; cc < NC / 8; ++cc) {
       ptx::tmem_ld_wait();                                 // step cc has landed ...
-      if (cc + 1 < NC / 4) {                               // ... step cc + 1 flies while step cc is computed
-        tmem_ld4(s_base + (cc + 1) * 4, svb[(cc + 1) & 1]);
-        tmem_ld4(dp_base + (cc + 1) * 4, dvb[(cc + 1) & 1]);
+      if (cc + 1 < NC / 8) {                               // ... step cc + 1 flies while step cc is computed
+        tmem_ld8(s_base + (cc + 1) * 8, svb[(cc + 1) & 1]);
+        tmem_ld8(dp_base + (cc + 1) * 8, dvb[(cc + 1) & 1]);
       }
-      const uint32_t(&sv)[4] = svb[cc & 1];
-      const uint32_t(&dv)[4] = dvb[cc & 1];
-      if (cc == NC / 4 - 1) {
+      const uint32_t(&sv)[8] = svb[cc & 1];
+      const uint32_t(&dv)[8] = dvb[cc & 1];
+      if (cc == NC / 8 - 1) {
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(sdp_free);        // this warp no longer needs S / dP of the unit
       }
-      uint32_t pk[2], dk[2];
+      uint32_t pk[4], dk[4];
 #pragma unroll
-      for (int e2 = 0; e2 < 2; ++e2) {
+      for (int e2 = 0; e2 < 4; ++e2) {
         float p2[2], d2[2];
 #pragma unroll
         for (int e1 = 0; e1 < 2; ++e1) {
-          const int e = e2 * 2 + e1, jj = cc * 4 + e;
+          const int e = e2 * 2 + e1, jj = cc * 8 + e;
           float bias;
           bool masked = false, exists = true;
           if constexpr (ROWALIGNED) {
-            constexpr int dummy = 0;
-            (void)dummy;
             const int yj = jj / WS, xj = jj % WS;                       // relative to y0; compile-time
             bias = trow[-(yj * TW + xj)];
             if (MASK) masked = (((by >> yj) | (bx >> xj)) & 1u) != 0;
@@ -313,10 +313,10 @@ __device__ __forceinline__ void bwd_main(uint32_t t_row, uint32_t s_col, uint32_
         dk[e2] = pack_bf16(d2[0], d2[1]);
       }
       if (cc == 0) pds_free_wait();
-      const int slot = slot0 + (cc >> 1);                               // 16-byte slot of keys [8 slot, 8 slot + 8)
-      const uint32_t off = (uint32_t)((slot >> 3) * kPanel + (((slot & 7) ^ r7) << 4) + (cc & 1) * 8);
-      *reinterpret_cast<uint2*>(prow + off) = make_uint2(pk[0], pk[1]);
-      *reinterpret_cast<uint2*>(drow + off) = make_uint2(dk[0], dk[1]);
+      const int slot = slot0 + cc;                                      // 16-byte slot of keys [8 slot, 8 slot + 8)
+      const uint32_t off = (uint32_t)((slot >> 3) * kPanel + (((slot & 7) ^ r7) << 4));
+      *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(drow + off) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
     }
   }
 }

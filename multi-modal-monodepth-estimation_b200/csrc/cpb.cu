@@ -34,36 +34,51 @@ cpb_fwd_kernel(const float* __restrict__ coords, const float* __restrict__ w0, c
   }
 }
 
-// dz[t,h] = dtable[t,h] * y (1 - y/16),  y = table[t,h]   (16 sigmoid' = y (1 - y/16))
+// dz[t,h] = dtable[t,h] * y (1 - y/16),  y = table[t,h]   (16 sigmoid' = y (1 - y/16)).
+// Every CTA needs all of dz: tiles of 128 table rows are read coalesced and staged TRANSPOSED in shared memory
+// ([h][t], row stride 129: conflict-free both ways) -- a thread that walks the heads of its own row straight from
+// global memory touches 32 different sectors per request.
 __global__ void __launch_bounds__(kCpbThreads)
 cpb_bwd_kernel(const float* __restrict__ coords, const float* __restrict__ w0, const float* __restrict__ b0,
                const float* __restrict__ w2, const float* __restrict__ table, const float* __restrict__ dtable,
                float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw2, int T, int HID, int nH) {
   __shared__ float red[kCpbThreads / 32][kCpbMaxHeads + 3];
+  extern __shared__ float sdz[];     // [nH][129]
   const int k = blockIdx.x;
   const float wa = w0[2 * k], wb = w0[2 * k + 1], bb = b0[k];
   float acc[kCpbMaxHeads];           // dW2[h, k] partial sums (compile-time indexed below)
+  float w2k[kCpbMaxHeads];
 #pragma unroll
-  for (int h = 0; h < kCpbMaxHeads; ++h) acc[h] = 0.f;
+  for (int h = 0; h < kCpbMaxHeads; ++h) { acc[h] = 0.f; w2k[h] = h < nH ? w2[(int64_t)h * HID + k] : 0.f; }
   float g0 = 0.f, g1 = 0.f, gb = 0.f;
-  for (int t = threadIdx.x; t < T; t += kCpbThreads) {
-    const float c0 = coords[2 * t], c1 = coords[2 * t + 1];
-    const float pre = fmaf(c0, wa, fmaf(c1, wb, bb));
-    const float hv = fmaxf(pre, 0.f);
-    float dh = 0.f;
-#pragma unroll
-    for (int h = 0; h < kCpbMaxHeads; ++h) {
-      if (h < nH) {
-        const float y = table[(int64_t)t * nH + h];
-        const float dz = dtable[(int64_t)t * nH + h] * y * (1.0f - y * 0.0625f);
-        acc[h] = fmaf(dz, hv, acc[h]);
-        dh = fmaf(dz, w2[(int64_t)h * HID + k], dh);
-      }
+  for (int t0 = 0; t0 < T; t0 += kCpbThreads) {
+    __syncthreads();
+    const int nrow = min(kCpbThreads, T - t0);
+    for (int e = threadIdx.x; e < nrow * nH; e += kCpbThreads) {
+      const int tl = e / nH, h = e - tl * nH;
+      const float y = table[(int64_t)t0 * nH + e];
+      sdz[h * (kCpbThreads + 1) + tl] = dtable[(int64_t)t0 * nH + e] * y * (1.0f - y * 0.0625f);
     }
-    if (pre > 0.f) {
-      g0 = fmaf(dh, c0, g0);
-      g1 = fmaf(dh, c1, g1);
-      gb += dh;
+    __syncthreads();
+    const int t = t0 + threadIdx.x;
+    if (t < T) {
+      const float c0 = coords[2 * t], c1 = coords[2 * t + 1];
+      const float pre = fmaf(c0, wa, fmaf(c1, wb, bb));
+      const float hv = fmaxf(pre, 0.f);
+      float dh = 0.f;
+#pragma unroll
+      for (int h = 0; h < kCpbMaxHeads; ++h) {
+        if (h < nH) {
+          const float dz = sdz[h * (kCpbThreads + 1) + threadIdx.x];
+          acc[h] = fmaf(dz, hv, acc[h]);
+          dh = fmaf(dz, w2k[h], dh);
+        }
+      }
+      if (pre > 0.f) {
+        g0 = fmaf(dh, c0, g0);
+        g1 = fmaf(dh, c1, g1);
+        gb += dh;
+      }
     }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -111,7 +126,7 @@ extern "C" int b200swin_cpb_bwd(const float* coords, const float* w0, const floa
   BSW_REQUIRE(coords && w0 && b0 && w2 && table && dtable && dw0 && db0 && dw2, "cpb_bwd: null pointer");
   BSW_REQUIRE(T > 0 && HID > 0 && HID <= 8192 && nH > 0 && nH <= kCpbMaxHeads, "cpb_bwd: T=%d HID=%d nH=%d out of range",
               T, HID, nH);
-  cpb_bwd_kernel<<<HID, kCpbThreads, 0, (cudaStream_t)stream>>>(coords, w0, b0, w2, table, dtable, dw0, db0, dw2, T, HID,
+  cpb_bwd_kernel<<<HID, kCpbThreads, (size_t)nH * (kCpbThreads + 1) * sizeof(float), (cudaStream_t)stream>>>(coords, w0, b0, w2, table, dtable, dw0, db0, dw2, T, HID,
                                                                  nH);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
