@@ -388,7 +388,7 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
   constexpr int N = CF::N, NPAD = CF::NPAD, MT = CF::MT, NSTAGE = CF::NSTAGE, TW = CF::TW;
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t kv_full[NSTAGE], kv_empty[NSTAGE];
-  __shared__ __align__(8) uint64_t sdp_full, sdp_free, pds_full, pds_free, dq_full[2], dq_free[2], dkv_full, dkv_free;
+  __shared__ __align__(8) uint64_t sdp_full, sdp_free, pds_full[2], pds_free, dq_full[2], dq_free[2], dkv_full, dkv_free;
   __shared__ uint32_t tmem_slot;
   __shared__ float red_s[kComputeWarps];
 
@@ -426,7 +426,11 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
     for (int s = 0; s < NSTAGE; ++s) { ptx::mbar_init(&kv_full[s], kLoaders); ptx::mbar_init(&kv_empty[s], 1 + kComputeWarps); }
     ptx::mbar_init(&sdp_full, 1);
     ptx::mbar_init(&sdp_free, kComputeWarps);
-    ptx::mbar_init(&pds_full, kComputeWarps);
+    // TWO barriers, alternating by unit: a warp that has nothing to write in unit u + 1 (tail units) arrives for it as
+    // soon as S / dP of u + 1 exist -- which only needs every warp's LAST TMEM READ of unit u, not its panel writes.
+    // With one barrier that early arrival was counted towards unit u and the dQ / dK / dV MMAs could start before the
+    // slowest warp had written its rows of P / dS (rare wrong dQ rows; the determinism test caught it).
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(&pds_full[i], kComputeWarps);
     ptx::mbar_init(&pds_free, 1);
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&dq_full[i], 1); ptx::mbar_init(&dq_free[i], 4); }
     ptx::mbar_init(&dkv_full, 1);
@@ -464,7 +468,7 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
           const uint32_t q_s = ring_s + (uint32_t)stage * CF::kStage, g_s = q_s + CF::kRow, k_s = g_s + CF::kRow;
           const int qb = v & 1;
           TR(14, v);
-          ptx::mbar_wait(&pds_full, v & 1);
+          ptx::mbar_wait(&pds_full[v & 1], (v >> 1) & 1);
           TR(15, v);
           ptx::mbar_wait(&dq_free[qb], ((v >> 1) & 1) ^ 1);
           ptx::tc_fence_after();
@@ -853,7 +857,7 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
         }
         ptx::fence_proxy_async_smem();             // panel writes -> visible to tcgen05.mma
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&pds_full);
+        if (lane == 0) ptx::mbar_arrive(&pds_full[u & 1]);
         TR(32, u);
       }
       // epilogues of the previous unit (its MMAs were issued right after this unit's S / dP)

@@ -238,17 +238,54 @@ static int ln_bwd_launch(const void* dy, const void* x, const float* gamma, cons
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// bf16 streaming kernels (C % 8 == 0, C <= 1536): the row stays PACKED (uint4 = 8 bf16) in registers until it is used,
-// every lane moves 16 bytes per load / store, and U passes (a pass = 32 / LPR rows per warp) are requested before
-// the first is reduced, so a warp keeps ~4 KB in flight with 32 registers.  gamma / beta live in shared memory.
+// bf16 streaming kernels (C % 8 == 0, C <= 1536).  HBM-bound, so the design goal is bytes in flight, not math:
+//   * every warp owns a private ring of kRing slots in shared memory; a slot receives one CHUNK of PASSES * (32 / LPR)
+//     consecutive rows of both input tensors -- rows are contiguous in memory, so a chunk is ONE 1-D bulk copy per
+//     tensor (cp.async.bulk, 1.5 - 3 KB), issued by lane 0 and signalled through an mbarrier;
+//   * while a slot is processed the other kRing - 1 slots of the warp are in flight: 16 warps x 2 slots x ~4 KB =
+//     128 KB per SM without a single register holding in-flight data;
+//   * the math reads the slot with conflict-free 16-byte LDS (8 bf16 per lane), keeps statistics in fp32 and writes
+//     the result straight to global memory (16 bytes per lane, coalesced).
 // LPR = lanes per row (16 for C <= 128: two rows per pass), NV = 16-byte chunks per lane and row.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kRing = 3;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ring_mbar_init(uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void ring_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ring_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_addr(bar);
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
-    f[2 * e] = t.x; f[2 * e + 1] = t.y;
+    f[2 * e] = __uint_as_float(w[e] << 16);
+    f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
   }
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
@@ -260,82 +297,144 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
+// the same eight values as four (even, odd) pairs for the packed fp32x2 instructions (FFMA2 / FMUL2 / FADD2)
+__device__ __forceinline__ void unpack8p(const uint4& u, float2 (&f)[4]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) f[e] = make_float2(__uint_as_float(w[e] << 16), __uint_as_float(w[e] & 0xffff0000u));
+}
+__device__ __forceinline__ uint4 pack8p(const float2 (&f)[4]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(f[e].x, f[e].y);
+    w[e] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void lds_f8p(const float* p, float2 (&f)[4]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = make_float2(a.x, a.y); f[1] = make_float2(a.z, a.w); f[2] = make_float2(b.x, b.y); f[3] = make_float2(b.z, b.w);
+}
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+
 template <int LPR>
 __device__ __forceinline__ float row_sum(float v) {
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void lds_f8(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
 
-template <int NV, int LPR, int U>
-__global__ void __launch_bounds__(kLnThreads, NV <= 3 ? 3 : 2)
+// Ring bookkeeping shared by the forward and the backward kernel.  T0 / T1: the two streamed tensors (T1 may be null).
+struct RingWarp {
+  unsigned char* base;       // this warp's kRing slots, each 2 * slot_bytes
+  uint64_t* bars;            // this warp's kRing mbarriers
+  uint32_t slot_bytes;       // bytes of ONE tensor's chunk (full chunk)
+  int64_t rows, chunk_rows, nchunks, first, stride;
+  int C;
+  const __nv_bfloat16* t0;
+  const __nv_bfloat16* t1;
+
+  __device__ __forceinline__ int64_t my_chunks() const { return first < nchunks ? (nchunks - first + stride - 1) / stride : 0; }
+  __device__ __forceinline__ void issue(int64_t it, int lane) const {
+    if (lane != 0) return;
+    const int s = (int)(it % kRing);
+    const int64_t row0 = (first + it * stride) * chunk_rows;
+    const int64_t nr = min(chunk_rows, rows - row0);
+    const uint32_t bytes = (uint32_t)(nr * C * 2);
+    unsigned char* dst = base + (size_t)s * 2 * slot_bytes;
+    ring_expect(&bars[s], t1 ? 2 * bytes : bytes);
+    ring_bulk_load(dst, t0 + row0 * C, bytes, &bars[s]);
+    if (t1) ring_bulk_load(dst + slot_bytes, t1 + row0 * C, bytes, &bars[s]);
+  }
+};
+
+template <int NV, int LPR, int PASSES>
+__global__ void __launch_bounds__(kLnThreads)
 ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual,
                    const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ row_scale, int64_t rows_per_scale, __nv_bfloat16* __restrict__ y,
                    float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int C, float eps) {
-  extern __shared__ float sh[];   // gamma[C] | beta[C]
-  for (int c = threadIdx.x; c < C; c += kLnThreads) { sh[c] = gamma[c]; sh[C + c] = beta[c]; }
-  __syncthreads();
+  extern __shared__ __align__(128) unsigned char smem_ln[];
+  __shared__ __align__(8) uint64_t bars[kLnWarps][kRing];
   constexpr int RPW = 32 / LPR;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lr = lane % LPR, sub = lane / LPR;
-  const int chunks = C >> 3;
+  const int chunks16 = C >> 3;
+  const uint32_t slot_bytes = (uint32_t)(PASSES * RPW) * C * 2;
+  float* gb = reinterpret_cast<float*>(smem_ln);                     // gamma[C] | beta[C]
+  unsigned char* ring0 = smem_ln + (((size_t)2 * C * 4 + 127) & ~(size_t)127);
+  for (int c = threadIdx.x; c < C; c += kLnThreads) { gb[c] = gamma[c]; gb[C + c] = beta[c]; }
+  if (lane == 0)
+    for (int s = 0; s < kRing; ++s) ring_mbar_init(&bars[warp][s]);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  RingWarp rw;
+  rw.base = ring0 + (size_t)warp * kRing * 2 * slot_bytes;
+  rw.bars = bars[warp];
+  rw.slot_bytes = slot_bytes;
+  rw.rows = rows; rw.chunk_rows = PASSES * RPW; rw.C = C;
+  rw.nchunks = (rows + rw.chunk_rows - 1) / rw.chunk_rows;
+  rw.first = (int64_t)blockIdx.x * kLnWarps + warp;
+  rw.stride = (int64_t)gridDim.x * kLnWarps;
+  rw.t0 = x; rw.t1 = residual;
+  const int64_t n = rw.my_chunks();
   const float inv_c = 1.0f / (float)C;
-  const int64_t npass = (rows + RPW - 1) / RPW;
-  const int64_t gwarp = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * kLnWarps;
-  for (int64_t p0 = gwarp * U; p0 < npass; p0 += nwarps * U) {
-    uint4 xv[U][NV], rv[U][NV];
+  for (int64_t it = 0; it < n && it < kRing; ++it) rw.issue(it, lane);
+
+  for (int64_t it = 0; it < n; ++it) {
+    const int s = (int)(it % kRing);
+    ring_wait(&rw.bars[s], (uint32_t)((it / kRing) & 1));
+    const unsigned char* xs = rw.base + (size_t)s * 2 * slot_bytes;
+    const unsigned char* rs = xs + slot_bytes;
+    const int64_t row0 = (rw.first + it * rw.stride) * rw.chunk_rows;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t row = (p0 + u) * RPW + sub;
+    for (int p = 0; p < PASSES; ++p) {
+      const int rl = p * RPW + sub;                                  // row inside the chunk
+      const int64_t row = row0 + rl;
+      if (row0 + p * RPW >= rows) break;                             // warp-uniform
+      const bool live = row < rows;
+      float f[NV][8];
+      float sm = 0.f;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int ch = k * LPR + lr;
-        xv[u][k] = make_uint4(0u, 0u, 0u, 0u);
-        rv[u][k] = make_uint4(0u, 0u, 0u, 0u);
-        if (row < rows && ch < chunks) {
-          xv[u][k] = ldg16(x + row * C + ch * 8);
-          if (residual) rv[u][k] = ldg16(residual + row * C + ch * 8);
-        }
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (live && ch < chunks16) v = *reinterpret_cast<const uint4*>(xs + (size_t)rl * C * 2 + ch * 16);
+        unpack8(v, f[k]);
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) sm += f[k][e] + f[k][e + 1];
       }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if ((p0 + u) * RPW >= rows) break;            // warp-uniform
-      const int64_t row = (p0 + u) * RPW + sub;
-      const bool live = row < rows;
-      float f[NV][8];
-      float s = 0.f;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        unpack8(xv[u][k], f[k]);
-#pragma unroll
-        for (int e = 0; e < 8; e += 2) s += f[k][e] + f[k][e + 1];
-      }
-      const float mean = row_sum<LPR>(s) * inv_c;
+      const float mean = row_sum<LPR>(sm) * inv_c;
       float q = 0.f;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        if (k * LPR + lr < chunks) {
+        if (k * LPR + lr < chunks16) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) { const float d = f[k][e] - mean; q = fmaf(d, d, q); }
         }
       }
       const float rstd = rsqrtf(row_sum<LPR>(q) * inv_c + eps);
       const float sc = (row_scale && live) ? row_scale[row / rows_per_scale] : 1.0f;
-      const float a = rstd * sc, b0 = -mean * a;    // ((x - mean) rstd g + b) sc = (x a + b0) g + b sc
+      const float a = rstd * sc, b0 = -mean * a;    // ((x - mean) rstd g + b) sc + r = (x a + b0) g + (b sc + r)
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int ch = k * LPR + lr;
-        if (live && ch < chunks) {
-          float r[8], o[8];
-          unpack8(rv[u][k], r);
-          const float4 g0 = *reinterpret_cast<const float4*>(sh + ch * 8), g1 = *reinterpret_cast<const float4*>(sh + ch * 8 + 4);
-          const float4 b0v = *reinterpret_cast<const float4*>(sh + C + ch * 8), b1v = *reinterpret_cast<const float4*>(sh + C + ch * 8 + 4);
-          const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float b[8] = {b0v.x, b0v.y, b0v.z, b0v.w, b1v.x, b1v.y, b1v.z, b1v.w};
+        if (live && ch < chunks16) {
+          float r[8], g[8], b[8], o[8];
+          if (residual) {
+            unpack8(*reinterpret_cast<const uint4*>(rs + (size_t)rl * C * 2 + ch * 16), r);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) r[e] = 0.f;
+          }
+          lds_f8(gb + ch * 8, g);
+          lds_f8(gb + C + ch * 8, b);
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] = fmaf(fmaf(f[k][e], a, b0), g[e], fmaf(b[e], sc, r[e]));
           *reinterpret_cast<uint4*>(y + row * C + ch * 8) = pack8(o);
@@ -343,104 +442,129 @@ ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
       }
       if (lr == 0 && live) { mean_out[row] = mean; rstd_out[row] = rstd; }
     }
+    __syncwarp();                                                    // every lane has finished reading the slot
+    if (it + kRing < n) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      rw.issue(it + kRing, lane);
+    }
   }
 }
 
-// Backward.  Phase A accumulates dgamma / dbeta and the two row sums from the packed registers, phase B unpacks again
-// and writes dx (recomputing x_hat costs three FMAs per element and saves 16 * NV live registers).  COLSUM adds the
-// column sums of dx -- the bias gradient of the Linear that produced x (proj / fc2) -- to the partial rows.
-template <int NV, int LPR, int U, bool COLSUM>
-__global__ void __launch_bounds__(kLnThreads, NV <= 3 ? 2 : 1)
+// Backward.  Phase A accumulates dgamma / dbeta and the two row sums, phase B re-reads the slot and writes dx.
+// COLSUM adds the column sums of dx -- the bias gradient of the Linear that produced x (proj / fc2) -- to the partial
+// rows.
+template <int NV, int LPR, int PASSES, bool COLSUM>
+__global__ void __launch_bounds__(kLnThreads)
 ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                    const float* __restrict__ gamma, const float* __restrict__ mean_in,
                    const float* __restrict__ rstd_in, const float* __restrict__ row_scale, int64_t rows_per_scale,
                    __nv_bfloat16* __restrict__ dx, float* __restrict__ part /*[grid][NP][C]*/, int64_t rows, int C) {
   constexpr int NP = COLSUM ? 3 : 2;
-  extern __shared__ float sh[];   // gamma[C] | reduction scratch [NP][C]
-  for (int c = threadIdx.x; c < C; c += kLnThreads) sh[c] = gamma[c];
-  for (int c = threadIdx.x; c < NP * C; c += kLnThreads) sh[C + c] = 0.f;
-  __syncthreads();
+  extern __shared__ __align__(128) unsigned char smem_ln[];
+  __shared__ __align__(8) uint64_t bars[kLnWarps][kRing];
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lr = lane % LPR, sub = lane / LPR;
-  const int chunks = C >> 3;
+  const int chunks16 = C >> 3;
+  const uint32_t slot_bytes = (uint32_t)(PASSES * RPW) * C * 2;
+  float* gm_s = reinterpret_cast<float*>(smem_ln);                   // gamma[C] | reduction scratch [NP][C]
+  float* red = gm_s + C;
+  unsigned char* ring0 = smem_ln + (((size_t)(1 + NP) * C * 4 + 127) & ~(size_t)127);
+  for (int c = threadIdx.x; c < C; c += kLnThreads) gm_s[c] = gamma[c];
+  for (int c = threadIdx.x; c < NP * C; c += kLnThreads) red[c] = 0.f;
+  if (lane == 0)
+    for (int s = 0; s < kRing; ++s) ring_mbar_init(&bars[warp][s]);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+
+  RingWarp rw;
+  rw.base = ring0 + (size_t)warp * kRing * 2 * slot_bytes;
+  rw.bars = bars[warp];
+  rw.slot_bytes = slot_bytes;
+  rw.rows = rows; rw.chunk_rows = PASSES * RPW; rw.C = C;
+  rw.nchunks = (rows + rw.chunk_rows - 1) / rw.chunk_rows;
+  rw.first = (int64_t)blockIdx.x * kLnWarps + warp;
+  rw.stride = (int64_t)gridDim.x * kLnWarps;
+  rw.t0 = x; rw.t1 = dy;
+  const int64_t n = rw.my_chunks();
   const float inv_c = 1.0f / (float)C;
-  const int64_t npass = (rows + RPW - 1) / RPW;
-  const int64_t gwarp = (int64_t)blockIdx.x * kLnWarps + warp;
-  const int64_t nwarps = (int64_t)gridDim.x * kLnWarps;
-  float dg[NV][8], db[NV][8], dc[COLSUM ? NV : 1][8];
+  float2 dg[NV][4], db[NV][4], dc[COLSUM ? NV : 1][4];
 #pragma unroll
   for (int k = 0; k < NV; ++k)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { dg[k][e] = 0.f; db[k][e] = 0.f; if (COLSUM) dc[k][e] = 0.f; }
+    for (int e = 0; e < 4; ++e) { dg[k][e] = f2(0.f); db[k][e] = f2(0.f); if (COLSUM) dc[k][e] = f2(0.f); }
+  for (int64_t it = 0; it < n && it < kRing; ++it) rw.issue(it, lane);
 
-  for (int64_t p0 = gwarp * U; p0 < npass; p0 += nwarps * U) {
-    uint4 xv[U][NV], gv[U][NV];
-    float mean[U], rstd[U];
+  for (int64_t it = 0; it < n; ++it) {
+    const int s = (int)(it % kRing);
+    const int64_t row0 = (rw.first + it * rw.stride) * rw.chunk_rows;
+    // per-row statistics: requested before the wait, they arrive with the slot
+    float mean[PASSES], rstd[PASSES];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t row = (p0 + u) * RPW + sub;
-      mean[u] = row < rows ? mean_in[row] : 0.f;
-      rstd[u] = row < rows ? rstd_in[row] : 0.f;
+    for (int p = 0; p < PASSES; ++p) {
+      const int64_t row = row0 + p * RPW + sub;
+      mean[p] = row < rows ? mean_in[row] : 0.f;
+      rstd[p] = row < rows ? rstd_in[row] : 0.f;
+    }
+    ring_wait(&rw.bars[s], (uint32_t)((it / kRing) & 1));
+    const unsigned char* xs = rw.base + (size_t)s * 2 * slot_bytes;
+    const unsigned char* gs = xs + slot_bytes;
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+      const int rl = p * RPW + sub;
+      const int64_t row = row0 + rl;
+      if (row0 + p * RPW >= rows) break;                             // warp-uniform
+      const bool live = row < rows;
+      const float sc = (row_scale && live) ? row_scale[row / rows_per_scale] : 1.0f;
+      const float a = rstd[p], b0 = -mean[p] * rstd[p];             // x_hat = x a + b0
+      // packed fp32x2 math (the kernel is issue-bound once the loads are decoupled): pairs (even, odd column)
+      const float2 a2 = f2(a), b2 = f2(b0), sc2 = f2(sc);
+      float2 s1 = f2(0.f), s2 = f2(0.f);
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int ch = k * LPR + lr;
-        xv[u][k] = make_uint4(0u, 0u, 0u, 0u);
-        gv[u][k] = make_uint4(0u, 0u, 0u, 0u);
-        if (row < rows && ch < chunks) {
-          xv[u][k] = ldg16(x + row * C + ch * 8);
-          gv[u][k] = ldg16(dy + row * C + ch * 8);
+        if (live && ch < chunks16) {
+          float2 xf[4], gf[4], gm[4];
+          unpack8p(*reinterpret_cast<const uint4*>(xs + (size_t)rl * C * 2 + ch * 16), xf);
+          unpack8p(*reinterpret_cast<const uint4*>(gs + (size_t)rl * C * 2 + ch * 16), gf);
+          lds_f8p(gm_s + ch * 8, gm);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 xh = __ffma2_rn(xf[e], a2, b2);
+            const float2 g = __fmul2_rn(gf[e], sc2);
+            dg[k][e] = __ffma2_rn(g, xh, dg[k][e]);
+            db[k][e] = __fadd2_rn(db[k][e], g);
+            const float2 gg = __fmul2_rn(g, gm[e]);
+            s1 = __fadd2_rn(s1, gg);
+            s2 = __ffma2_rn(gg, xh, s2);
+          }
+        }
+      }
+      const float m1 = row_sum<LPR>(s1.x + s1.y) * inv_c, m2 = row_sum<LPR>(s2.x + s2.y) * inv_c;
+      const float2 nm1 = f2(-m1), nm2 = f2(-m2);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int ch = k * LPR + lr;
+        if (live && ch < chunks16) {
+          float2 xf[4], gf[4], gm[4], o[4];
+          unpack8p(*reinterpret_cast<const uint4*>(xs + (size_t)rl * C * 2 + ch * 16), xf);
+          unpack8p(*reinterpret_cast<const uint4*>(gs + (size_t)rl * C * 2 + ch * 16), gf);
+          lds_f8p(gm_s + ch * 8, gm);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 xh = __ffma2_rn(xf[e], a2, b2);
+            const float2 gg = __fmul2_rn(__fmul2_rn(gf[e], sc2), gm[e]);
+            o[e] = __fmul2_rn(a2, __fadd2_rn(__ffma2_rn(xh, nm2, gg), nm1));
+            if (COLSUM) dc[k][e] = __fadd2_rn(dc[k][e], o[e]);
+          }
+          *reinterpret_cast<uint4*>(dx + row * C + ch * 8) = pack8p(o);
         }
       }
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if ((p0 + u) * RPW >= rows) break;            // warp-uniform
-      const int64_t row = (p0 + u) * RPW + sub;
-      const bool live = row < rows;
-      const float sc = (row_scale && live) ? row_scale[row / rows_per_scale] : 1.0f;
-      const float a = rstd[u], b0 = -mean[u] * rstd[u];             // x_hat = x a + b0
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const int ch = k * LPR + lr;
-        if (ch < chunks) {                          // dead rows carry zeros
-          float xf[8], gf[8];
-          unpack8(xv[u][k], xf);
-          unpack8(gv[u][k], gf);
-          const float4 g0 = *reinterpret_cast<const float4*>(sh + ch * 8), g1 = *reinterpret_cast<const float4*>(sh + ch * 8 + 4);
-          const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float xh = live ? fmaf(xf[e], a, b0) : 0.f;
-            const float g = gf[e] * sc;
-            dg[k][e] = fmaf(g, xh, dg[k][e]);
-            db[k][e] += g;
-            const float gg = g * gm[e];
-            s1 += gg;
-            s2 = fmaf(gg, xh, s2);
-          }
-        }
-      }
-      const float m1 = row_sum<LPR>(s1) * inv_c, m2 = row_sum<LPR>(s2) * inv_c;
-#pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const int ch = k * LPR + lr;
-        if (live && ch < chunks) {
-          float xf[8], gf[8], o[8];
-          unpack8(xv[u][k], xf);
-          unpack8(gv[u][k], gf);
-          const float4 g0 = *reinterpret_cast<const float4*>(sh + ch * 8), g1 = *reinterpret_cast<const float4*>(sh + ch * 8 + 4);
-          const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float xh = fmaf(xf[e], a, b0);
-            o[e] = a * (gf[e] * sc * gm[e] - m1 - xh * m2);
-            if (COLSUM) dc[k][e] += o[e];
-          }
-          *reinterpret_cast<uint4*>(dx + row * C + ch * 8) = pack8(o);
-        }
-      }
+    __syncwarp();
+    if (it + kRing < n) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      rw.issue(it + kRing, lane);
     }
   }
   // two rows per pass: lanes l and l + 16 own the same columns
@@ -448,25 +572,34 @@ ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
 #pragma unroll
     for (int k = 0; k < NV; ++k)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        dg[k][e] += __shfl_xor_sync(0xffffffffu, dg[k][e], 16);
-        db[k][e] += __shfl_xor_sync(0xffffffffu, db[k][e], 16);
-        if (COLSUM) dc[k][e] += __shfl_xor_sync(0xffffffffu, dc[k][e], 16);
+      for (int e = 0; e < 4; ++e) {
+        dg[k][e].x += __shfl_xor_sync(0xffffffffu, dg[k][e].x, 16);
+        dg[k][e].y += __shfl_xor_sync(0xffffffffu, dg[k][e].y, 16);
+        db[k][e].x += __shfl_xor_sync(0xffffffffu, db[k][e].x, 16);
+        db[k][e].y += __shfl_xor_sync(0xffffffffu, db[k][e].y, 16);
+        if (COLSUM) {
+          dc[k][e].x += __shfl_xor_sync(0xffffffffu, dc[k][e].x, 16);
+          dc[k][e].y += __shfl_xor_sync(0xffffffffu, dc[k][e].y, 16);
+        }
       }
   }
   // fixed-order cross-warp reduction in shared memory -> one partial row set per block
-  float* red = sh + C;
   for (int w = 0; w < kLnWarps; ++w) {
     if (warp == w && sub == 0) {
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int ch = k * LPR + lr;
-        if (ch < chunks) {
+        if (ch < chunks16) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            red[ch * 8 + e] += dg[k][e];
-            red[C + ch * 8 + e] += db[k][e];
-            if (COLSUM) red[2 * C + ch * 8 + e] += dc[k][e];
+          for (int e = 0; e < 4; ++e) {
+            red[ch * 8 + 2 * e] += dg[k][e].x;
+            red[ch * 8 + 2 * e + 1] += dg[k][e].y;
+            red[C + ch * 8 + 2 * e] += db[k][e].x;
+            red[C + ch * 8 + 2 * e + 1] += db[k][e].y;
+            if (COLSUM) {
+              red[2 * C + ch * 8 + 2 * e] += dc[k][e].x;
+              red[2 * C + ch * 8 + 2 * e + 1] += dc[k][e].y;
+            }
           }
         }
       }
@@ -497,14 +630,8 @@ ln_param_reduce3_kernel(const float* __restrict__ part, int nparts, int C, int N
 }
 
 static bool ln_fast_ok(int C, int dtype) { return dtype == B200SWIN_BF16 && C % 8 == 0 && C <= 1536; }
-static int ln_fast_bwd_grid(int64_t rows, int C) {
-  int64_t blocks = (rows + 4 * kLnWarps - 1) / (4 * kLnWarps);
-  int64_t cap = (int64_t)sm_count() * (C <= 768 ? 2 : 1);         // exactly the resident blocks
-  if (blocks < 1) blocks = 1;
-  return (int)(blocks < cap ? blocks : cap);
-}
 
-// (NV, LPR, U) by row width: ~4 KB (two tensors) in flight per warp
+// (NV, LPR, PASSES) by row width: chunks of 1.5 - 3 KB per tensor
 #define LN_FAST_DISPATCH(C, X)                   \
   do {                                           \
     if ((C) <= 128) X(1, 16, 4);                 \
@@ -515,17 +642,35 @@ static int ln_fast_bwd_grid(int64_t rows, int C) {
     else X(6, 32, 1);                            \
   } while (0)
 
+static int ln_chunk_rows(int C) { return C <= 128 ? 8 : C <= 256 ? 4 : C <= 512 ? 2 : 1; }
+static size_t ln_ring_bytes(int C) { return (size_t)kLnWarps * kRing * 2 * (size_t)ln_chunk_rows(C) * C * 2; }
+static size_t ln_fwd_smem(int C) { return (((size_t)2 * C * 4 + 127) & ~(size_t)127) + ln_ring_bytes(C); }
+static size_t ln_bwd_smem(int C, int NP) { return (((size_t)(1 + NP) * C * 4 + 127) & ~(size_t)127) + ln_ring_bytes(C); }
+static int ln_blocks_per_sm(size_t smem) {
+  const size_t avail = 227 * 1024;
+  int b = (int)(avail / (smem + 1024));
+  return b < 1 ? 1 : (b > 4 ? 4 : b);
+}
+// one resident wave; every warp gets at least two chunks when there is that much work
+static int ln_fast_grid(int64_t rows, int C, size_t smem) {
+  const int64_t nchunks = (rows + ln_chunk_rows(C) - 1) / ln_chunk_rows(C);
+  int64_t blocks = (nchunks + 2 * kLnWarps - 1) / (2 * kLnWarps);
+  const int64_t cap = (int64_t)sm_count() * ln_blocks_per_sm(smem);
+  if (blocks < 1) blocks = 1;
+  return (int)(blocks < cap ? blocks : cap);
+}
+static int ln_fast_bwd_grid(int64_t rows, int C) { return ln_fast_grid(rows, C, ln_bwd_smem(C, 3)); }
+
 static int ln_fwd_fast(const void* x, const void* residual, const float* gamma, const float* beta,
                        const float* row_scale, int64_t rps, void* y, float* mean, float* rstd, int64_t rows, int C,
                        float eps, cudaStream_t st) {
-  const size_t smem = (size_t)2 * C * sizeof(float);
-#define X(NV, LPR, U)                                                                                                \
+  const size_t smem = ln_fwd_smem(C);
+  const int grid = ln_fast_grid(rows, C, smem);
+#define X(NV, LPR, PASSES)                                                                                           \
   do {                                                                                                               \
-    const int64_t npass = (rows + (32 / LPR) - 1) / (32 / LPR);                                                      \
-    int64_t blocks = (npass + (int64_t)U * kLnWarps - 1) / ((int64_t)U * kLnWarps);                                  \
-    const int64_t cap = (int64_t)sm_count() * (NV <= 3 ? 3 : 2);     /* exactly the resident blocks: no second wave */ \
-    const int grid = (int)(blocks < cap ? blocks : cap);                                                             \
-    ln_fwd_bf16_kernel<NV, LPR, U><<<grid, kLnThreads, smem, st>>>(                                                  \
+    BSW_CUDA(cudaFuncSetAttribute(ln_fwd_bf16_kernel<NV, LPR, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                  (int)smem));                                                                       \
+    ln_fwd_bf16_kernel<NV, LPR, PASSES><<<grid, kLnThreads, smem, st>>>(                                             \
         (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, beta, row_scale, rps, (__nv_bfloat16*)y, mean, \
         rstd, rows, C, eps);                                                                                         \
   } while (0)
@@ -538,17 +683,22 @@ static int ln_fwd_fast(const void* x, const void* residual, const float* gamma, 
 static int ln_bwd_fast(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                        const float* row_scale, int64_t rps, void* dx, float* part, int grid, bool colsum, int64_t rows,
                        int C, cudaStream_t st) {
-  const size_t smem = (size_t)(1 + (colsum ? 3 : 2)) * C * sizeof(float);
-#define X(NV, LPR, U)                                                                                                \
+  const size_t smem = ln_bwd_smem(C, colsum ? 3 : 2);
+#define X(NV, LPR, PASSES)                                                                                           \
   do {                                                                                                               \
-    if (colsum)                                                                                                      \
-      ln_bwd_bf16_kernel<NV, LPR, U, true><<<grid, kLnThreads, smem, st>>>(                                          \
+    if (colsum) {                                                                                                    \
+      BSW_CUDA(cudaFuncSetAttribute(ln_bwd_bf16_kernel<NV, LPR, PASSES, true>,                                       \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
+      ln_bwd_bf16_kernel<NV, LPR, PASSES, true><<<grid, kLnThreads, smem, st>>>(                                     \
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, gamma, mean, rstd, row_scale, rps, (__nv_bfloat16*)dx,  \
           part, rows, C);                                                                                            \
-    else                                                                                                             \
-      ln_bwd_bf16_kernel<NV, LPR, U, false><<<grid, kLnThreads, smem, st>>>(                                         \
+    } else {                                                                                                         \
+      BSW_CUDA(cudaFuncSetAttribute(ln_bwd_bf16_kernel<NV, LPR, PASSES, false>,                                      \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
+      ln_bwd_bf16_kernel<NV, LPR, PASSES, false><<<grid, kLnThreads, smem, st>>>(                                    \
           (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, gamma, mean, rstd, row_scale, rps, (__nv_bfloat16*)dx,  \
           part, rows, C);                                                                                            \
+    }                                                                                                                \
   } while (0)
   LN_FAST_DISPATCH(C, X);
 #undef X
