@@ -201,12 +201,14 @@ def _run_b200(args, stream):
     model.train()
     crit = SiLogLoss()
     params = [p for p in model.parameters() if p.requires_grad]
-    # one flat fp32 gradient buffer: autograd accumulates into views of it, and the data-parallel exchange is ONE
-    # NCCL all-reduce (average) over NVLink -- the only collective of the path
+    # one flat fp32 gradient buffer for the data-parallel exchange: ONE NCCL all-reduce (average) over NVLink -- the only
+    # collective of the path.  Autograd ASSIGNS fresh gradients (p.grad = None before the
+    # backward); with N > 1 they are packed into the flat buffer by one multi-tensor copy.  (Pre-set .grad views made
+    # autograd launch one accumulation kernel per parameter: ~330 launch-bound adds per step.)
     flat_grad = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-    off = 0
+    flat_views, off = [], 0
     for p in params:
-        p.grad = flat_grad[off:off + p.numel()].view_as(p)
+        flat_views.append(flat_grad[off:off + p.numel()].view_as(p))
         off += p.numel()
     opt = torch.optim.AdamW(params, lr=5e-4, weight_decay=0.05, fused=True, capturable=True)
     P = args.pairs
@@ -217,16 +219,23 @@ def _run_b200(args, stream):
 
     def fwd_bwd(batch):
         img1, img2, d1, d2 = batch
-        flat_grad.zero_()
+        for p in params:
+            p.grad = None
         with torch.autocast("cuda", torch.bfloat16, enabled=use_amp):
             p1, p2 = model(img1, img2)
         loss = (crit(p1, d1) + crit(p2, d2)) / 2                 # train.py:215-217
         loss.backward()
+        if world > 1:
+            pairs = [(v, p.grad) for v, p in zip(flat_views, params) if p.grad is not None]
+            torch._foreach_copy_([v for v, _ in pairs], [g for _, g in pairs])
         return loss
 
     def finish():
         if world > 1:
             dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
+            for p, v in zip(params, flat_views):                 # the optimizer reads the averaged gradients
+                if p.grad is not None:
+                    p.grad = v
         opt.step()
 
     def step_eager(batch):
