@@ -162,13 +162,14 @@ def peaks():
 
 def gemm_traffic():
     """DRAM bytes of one representative launch of the dominant kernel, from the committed ncu --set full capture."""
-    f = os.path.join(ROOT, "profiles", "r01_ncu_gemm_tc_r01.json")
+    f = os.path.join(ROOT, "profiles", "r01_ncu_gemm_plain_st2.json")
     try:
         d = json.load(open(f))
         rd, wr = float(d["dram_read"].split()[0]), float(d["dram_write"].split()[0])      # Mbyte
-        M, N, K = 43200, 512, 2048
-        return {"launch": "gemm_tc_kernel M=43200 N=512 K=2048 (stage-2 fc2 forward)", "dram_bytes": (rd + wr) * 1e6,
-                "algorithmic_bytes": 2.0 * (M * K + N * K + M * N), "source": "profiles/r01_ncu_gemm_tc_r01.json"}
+        M, N, K = 43200, 2048, 512
+        return {"launch": "gemm_tc_kernel M=43200 N=2048 K=512 (stage-2 fc1 forward, plain epilogue)",
+                "dram_bytes": (rd + wr) * 1e6, "algorithmic_bytes": 2.0 * (M * K + N * K + M * N),
+                "source": "profiles/r01_ncu_gemm_plain_st2.json"}
     except Exception:
         return None
 

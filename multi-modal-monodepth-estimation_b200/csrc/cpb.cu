@@ -6,8 +6,8 @@
 // A few hundred kFLOP per block -- in PyTorch that is ~5 launches forward and ~10 backward per block, all of them
 // latency-bound; here it is one launch each way.  fp32 throughout (the reference runs this branch in fp32, :50-56).
 //   fwd: one CTA per table row t: the hidden vector goes to shared memory, then one warp per group of heads.
-//   bwd: one CTA per hidden unit k: threads stride over t, recompute hid[t,k], and accumulate
-//        dW2[:,k], dW0[k,:], db0[k] in registers; fixed-order block reduction (deterministic, no atomics).
+//   bwd: one warp per hidden unit k (8 per CTA sharing the staged dz tiles): lanes stride over t, recompute hid[t,k] and
+//        accumulate dW2[:,k], dW0[k,:], db0[k] in registers; fixed-order warp reduction (deterministic, no atomics).
 #include "common.cuh"
 #include "../../include/b200swin.h"
 
@@ -35,33 +35,36 @@ cpb_fwd_kernel(const float* __restrict__ coords, const float* __restrict__ w0, c
 }
 
 // dz[t,h] = dtable[t,h] * y (1 - y/16),  y = table[t,h]   (16 sigmoid' = y (1 - y/16)).
-// Every CTA needs all of dz: tiles of 128 table rows are read coalesced and staged TRANSPOSED in shared memory
-// ([h][t], row stride 129: conflict-free both ways) -- a thread that walks the heads of its own row straight from
-// global memory touches 32 different sectors per request.
-__global__ void __launch_bounds__(kCpbThreads)
+// One WARP per hidden unit k, kCpbUnits warps per CTA: the CTA stages tiles of 128 table rows of dz TRANSPOSED in shared
+// memory ([h][t], row stride 129: coalesced global reads, conflict-free both ways) and every warp reuses them, lanes
+// striding over the rows of the tile.  (One CTA per hidden unit re-read all of dz 512 times: 40 us per launch.)
+constexpr int kCpbUnits = 8;
+constexpr int kCpbTile = 128;
+__global__ void __launch_bounds__(kCpbUnits * 32)
 cpb_bwd_kernel(const float* __restrict__ coords, const float* __restrict__ w0, const float* __restrict__ b0,
                const float* __restrict__ w2, const float* __restrict__ table, const float* __restrict__ dtable,
                float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw2, int T, int HID, int nH) {
-  __shared__ float red[kCpbThreads / 32][kCpbMaxHeads + 3];
-  extern __shared__ float sdz[];     // [nH][129]
-  const int k = blockIdx.x;
-  const float wa = w0[2 * k], wb = w0[2 * k + 1], bb = b0[k];
+  extern __shared__ float sdz[];     // [nH][kCpbTile + 1]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kCpbUnits + warp;
+  const bool kvalid = k < HID;
+  const float wa = kvalid ? w0[2 * k] : 0.f, wb = kvalid ? w0[2 * k + 1] : 0.f, bb = kvalid ? b0[k] : 0.f;
   float acc[kCpbMaxHeads];           // dW2[h, k] partial sums (compile-time indexed below)
   float w2k[kCpbMaxHeads];
 #pragma unroll
-  for (int h = 0; h < kCpbMaxHeads; ++h) { acc[h] = 0.f; w2k[h] = h < nH ? w2[(int64_t)h * HID + k] : 0.f; }
+  for (int h = 0; h < kCpbMaxHeads; ++h) { acc[h] = 0.f; w2k[h] = (kvalid && h < nH) ? w2[(int64_t)h * HID + k] : 0.f; }
   float g0 = 0.f, g1 = 0.f, gb = 0.f;
-  for (int t0 = 0; t0 < T; t0 += kCpbThreads) {
+  for (int t0 = 0; t0 < T; t0 += kCpbTile) {
     __syncthreads();
-    const int nrow = min(kCpbThreads, T - t0);
-    for (int e = threadIdx.x; e < nrow * nH; e += kCpbThreads) {
+    const int nrow = min(kCpbTile, T - t0);
+    for (int e = threadIdx.x; e < nrow * nH; e += kCpbUnits * 32) {
       const int tl = e / nH, h = e - tl * nH;
       const float y = table[(int64_t)t0 * nH + e];
-      sdz[h * (kCpbThreads + 1) + tl] = dtable[(int64_t)t0 * nH + e] * y * (1.0f - y * 0.0625f);
+      sdz[h * (kCpbTile + 1) + tl] = dtable[(int64_t)t0 * nH + e] * y * (1.0f - y * 0.0625f);
     }
     __syncthreads();
-    const int t = t0 + threadIdx.x;
-    if (t < T) {
+    for (int tl = lane; tl < nrow; tl += 32) {
+      const int t = t0 + tl;
       const float c0 = coords[2 * t], c1 = coords[2 * t + 1];
       const float pre = fmaf(c0, wa, fmaf(c1, wb, bb));
       const float hv = fmaxf(pre, 0.f);
@@ -69,7 +72,7 @@ cpb_bwd_kernel(const float* __restrict__ coords, const float* __restrict__ w0, c
 #pragma unroll
       for (int h = 0; h < kCpbMaxHeads; ++h) {
         if (h < nH) {
-          const float dz = sdz[h * (kCpbThreads + 1) + threadIdx.x];
+          const float dz = sdz[h * (kCpbTile + 1) + tl];
           acc[h] = fmaf(dz, hv, acc[h]);
           dh = fmaf(dz, w2k[h], dh);
         }
@@ -81,28 +84,16 @@ cpb_bwd_kernel(const float* __restrict__ coords, const float* __restrict__ w0, c
       }
     }
   }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // fixed-order warp reductions (deterministic)
 #pragma unroll
   for (int h = 0; h < kCpbMaxHeads; ++h) {
     if (h < nH) {
       const float s = warp_sum(acc[h]);
-      if (lane == 0) red[warp][h] = s;
+      if (lane == 0 && kvalid) dw2[(int64_t)h * HID + k] = s;
     }
   }
   g0 = warp_sum(g0); g1 = warp_sum(g1); gb = warp_sum(gb);
-  if (lane == 0) { red[warp][kCpbMaxHeads] = g0; red[warp][kCpbMaxHeads + 1] = g1; red[warp][kCpbMaxHeads + 2] = gb; }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kCpbMaxHeads + 3; i += kCpbThreads) {
-    if (i < nH || i >= kCpbMaxHeads) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < kCpbThreads / 32; ++w) s += red[w][i];
-      if (i < nH) dw2[(int64_t)i * HID + k] = s;
-      else if (i == kCpbMaxHeads) dw0[2 * k] = s;
-      else if (i == kCpbMaxHeads + 1) dw0[2 * k + 1] = s;
-      else db0[k] = s;
-    }
-  }
+  if (lane == 0 && kvalid) { dw0[2 * k] = g0; dw0[2 * k + 1] = g1; db0[k] = gb; }
 }
 
 }  // namespace b200swin
@@ -126,7 +117,8 @@ extern "C" int b200swin_cpb_bwd(const float* coords, const float* w0, const floa
   BSW_REQUIRE(coords && w0 && b0 && w2 && table && dtable && dw0 && db0 && dw2, "cpb_bwd: null pointer");
   BSW_REQUIRE(T > 0 && HID > 0 && HID <= 8192 && nH > 0 && nH <= kCpbMaxHeads, "cpb_bwd: T=%d HID=%d nH=%d out of range",
               T, HID, nH);
-  cpb_bwd_kernel<<<HID, kCpbThreads, (size_t)nH * (kCpbThreads + 1) * sizeof(float), (cudaStream_t)stream>>>(coords, w0, b0, w2, table, dtable, dw0, db0, dw2, T, HID,
+  cpb_bwd_kernel<<<(HID + kCpbUnits - 1) / kCpbUnits, kCpbUnits * 32, (size_t)nH * (kCpbTile + 1) * sizeof(float),
+                   (cudaStream_t)stream>>>(coords, w0, b0, w2, table, dtable, dw0, db0, dw2, T, HID,
                                                                  nH);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
