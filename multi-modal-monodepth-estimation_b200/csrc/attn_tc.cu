@@ -314,6 +314,17 @@ static int launch_fwd(const TcArgs& a, cudaStream_t st) {
 bool attn_fwd_ws_supported(int ws);
 int attn_fwd_ws(const void* qkv, void* out, float* lse, const float* table16, const float* scale, const float* qpad,
                 const float* vpad, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st);
+// second-generation warp-specialised forward for 12x12 windows (attn_fwd_ws2.cu)
+bool attn_fwd_ws2_supported(int ws);
+int attn_fwd_ws2(const void* qkv, void* out, float* lse, const float* table16, const float* scale, const float* qpad,
+                 const float* vpad, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st);
+// Opt-in (B200SWIN_ATTN_FWD_GEN2=1): parity-green, but on B200 still 10 % slower than the first generation (201 us vs
+// 180 us for Swin-B stage 2) -- see the header of attn_fwd_ws2.cu and DESIGN.md section 8.
+static bool use_gen2_fwd() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200SWIN_ATTN_FWD_GEN2"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 // warp-specialised backward (attn_bwd_ws.cu)
 bool attn_bwd_ws_supported(int ws);
 size_t attn_bwd_ws_workspace_bytes(int B, int H, int W, int nH);
@@ -347,6 +358,8 @@ int attn_fwd_tc(const void* qkv, void* out, float* lse, const float* table16, co
   BSW_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && C % 8 == 0,
               "attn_fwd(tc): qkv/out must be 16-byte aligned");
   BSW_REQUIRE((int64_t)B * H * W < (1ll << 29), "attn_fwd(tc): too many tokens");
+  if (attn_fwd_ws2_supported(ws) && !use_legacy_fwd() && use_gen2_fwd())
+    return attn_fwd_ws2(qkv, out, lse, table16, scale, qpad, vpad, B, H, W, C, nH, ws, shift, st);
   if (attn_fwd_ws_supported(ws) && !use_legacy_fwd())
     return attn_fwd_ws(qkv, out, lse, table16, scale, qpad, vpad, B, H, W, C, nH, ws, shift, st);
   TcArgs a;
