@@ -38,6 +38,8 @@ CFG = dict(embed_dim=128, depths=[2, 2, 18, 2], num_heads=[4, 8, 16, 32], window
            pretrain_window_size=[12, 12, 12, 6], use_shift=[True, True, False, False], drop_path_rate=0.3)
 IMG = 480
 MAX_DEPTH = 10.0
+WORKLOAD = ("swin_v2_base_480x480_ws12_24pairs_per_gpu_train_step(encoder+pixelshuffle_readout+silog_x2+adamw; "
+            "decoder_v2 outside hot path, not included)")
 
 
 def parse():
@@ -385,8 +387,7 @@ def _run_b200(args, stream):
             "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if use_amp else "f32(split-bf16 x3)", "data": "synthetic",
-            "config": {"workload": "swin_v2_base_480x480_ws12_24pairs_per_gpu_train_step(encoder+pixelshuffle_readout"
-                                   "+silog_x2+adamw; decoder_v2 outside hot path, not included)",
+            "config": {"workload": WORKLOAD,
                        "pairs_per_gpu": P, "frames_per_gpu": 2 * P, "windows": CFG["window_size"],
                        "attn_impl": args.attn, "parallelism": f"dp{world}",
                        "execution": "cuda_graph_replay" if graph is not None else "eager",
@@ -428,7 +429,11 @@ def cpu_reference(pairs, steps, warmup):
     readout_b = torch.zeros(1024, requires_grad=True)
     img1, img2, d1, d2 = make_batch(pairs, 1234)
 
+    leaves = [v for v in sd.values() if v.requires_grad] + [readout_w, readout_b]
+    opt = torch.optim.AdamW(leaves, lr=5e-4, weight_decay=0.05)
+
     def one():
+        opt.zero_grad(set_to_none=True)
         feat = swin_ref.swin_v2(torch.cat([img1, img2]), sd, CFG["embed_dim"], CFG["depths"], CFG["num_heads"],
                                 CFG["window_size"], CFG["use_shift"], (3,))[0]
         B, C, h, w = feat.shape
@@ -437,6 +442,7 @@ def cpu_reference(pairs, steps, warmup):
         p1, p2 = d.chunk(2)
         loss = (silog_ref.silog_torch(p1, d1) + silog_ref.silog_torch(p2, d2)) / 2
         loss.backward()
+        opt.step()
         return loss.item()
 
     for _ in range(warmup):
@@ -446,7 +452,7 @@ def cpu_reference(pairs, steps, warmup):
         one()
     dt = time.perf_counter() - t0
     return {"value": 2 * pairs * steps / dt, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} step(s) of {pairs} pair(s) ({2 * pairs} frames) 480x480, Swin-V2-B ws12 fwd+bwd+SiLog, "
+            "sample": f"{steps} step(s) of {pairs} pair(s) ({2 * pairs} frames) 480x480, Swin-V2-B ws12 fwd+bwd+SiLog+AdamW, "
                       f"fp32 torch CPU, {dt:.1f} s"}
 
 
@@ -464,8 +470,11 @@ def run_reference(args):
         "value": base["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": (time.perf_counter() - t0) * 1e3 / (steps + warmup), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "swin_v2_base_480x480_ws12 train step, bounded CPU sample", "pairs_per_step": pairs,
-                   "note": "CPU oracle port of the reference PyTorch path on the host cores; requested steps/warmup "
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": args.pairs, "frames_per_gpu": 2 * args.pairs,
+                   "windows": CFG["window_size"], "parallelism": f"dp{args.gpus}", "execution": "cpu_reference_port",
+                   "sample": f"each step = {pairs} pair(s) of the workload (bounded sample of the 24-pair batch)",
+                   "note": "CPU oracle port of the reference PyTorch path on the host cores (the Python reference itself "
+                           "cannot travel to the GPU box); requested steps/warmup "
                            f"({args.steps}/{args.warmup}) clamped to ({steps}/{warmup}) to bound the run"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
