@@ -399,45 +399,48 @@ ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
       const int64_t row = row0 + rl;
       if (row0 + p * RPW >= rows) break;                             // warp-uniform
       const bool live = row < rows;
-      float f[NV][8];
-      float sm = 0.f;
+      // packed fp32x2 math (pairs of even / odd columns): the kernel is issue-bound once the loads are decoupled
+      float2 f[NV][4];
+      float2 sm2 = f2(0.f);
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int ch = k * LPR + lr;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (live && ch < chunks16) v = *reinterpret_cast<const uint4*>(xs + (size_t)rl * C * 2 + ch * 16);
-        unpack8(v, f[k]);
+        unpack8p(v, f[k]);
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) sm += f[k][e] + f[k][e + 1];
+        for (int e = 0; e < 4; ++e) sm2 = __fadd2_rn(sm2, f[k][e]);
       }
-      const float mean = row_sum<LPR>(sm) * inv_c;
-      float q = 0.f;
+      const float mean = row_sum<LPR>(sm2.x + sm2.y) * inv_c;
+      const float2 nmean = f2(-mean);
+      float2 q2 = f2(0.f);
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         if (k * LPR + lr < chunks16) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) { const float d = f[k][e] - mean; q = fmaf(d, d, q); }
+          for (int e = 0; e < 4; ++e) { const float2 d = __fadd2_rn(f[k][e], nmean); q2 = __ffma2_rn(d, d, q2); }
         }
       }
-      const float rstd = rsqrtf(row_sum<LPR>(q) * inv_c + eps);
+      const float rstd = rsqrtf(row_sum<LPR>(q2.x + q2.y) * inv_c + eps);
       const float sc = (row_scale && live) ? row_scale[row / rows_per_scale] : 1.0f;
       const float a = rstd * sc, b0 = -mean * a;    // ((x - mean) rstd g + b) sc + r = (x a + b0) g + (b sc + r)
+      const float2 a2 = f2(a), b02 = f2(b0), sc2 = f2(sc);
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int ch = k * LPR + lr;
         if (live && ch < chunks16) {
-          float r[8], g[8], b[8], o[8];
+          float2 r[4], g[4], b[4], o[4];
           if (residual) {
-            unpack8(*reinterpret_cast<const uint4*>(rs + (size_t)rl * C * 2 + ch * 16), r);
+            unpack8p(*reinterpret_cast<const uint4*>(rs + (size_t)rl * C * 2 + ch * 16), r);
           } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) r[e] = 0.f;
+            for (int e = 0; e < 4; ++e) r[e] = f2(0.f);
           }
-          lds_f8(gb + ch * 8, g);
-          lds_f8(gb + C + ch * 8, b);
+          lds_f8p(gb + ch * 8, g);
+          lds_f8p(gb + C + ch * 8, b);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = fmaf(fmaf(f[k][e], a, b0), g[e], fmaf(b[e], sc, r[e]));
-          *reinterpret_cast<uint4*>(y + row * C + ch * 8) = pack8(o);
+          for (int e = 0; e < 4; ++e) o[e] = __ffma2_rn(__ffma2_rn(f[k][e], a2, b02), g[e], __ffma2_rn(b[e], sc2, r[e]));
+          *reinterpret_cast<uint4*>(y + row * C + ch * 8) = pack8p(o);
         }
       }
       if (lr == 0 && live) { mean_out[row] = mean; rstd_out[row] = rstd; }
