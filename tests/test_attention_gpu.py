@@ -189,7 +189,12 @@ def test_swin_small_vs_reference_golden():
     (2, 24, 24, 128, 4, 12, 0, torch.bfloat16, "tc"), (2, 24, 24, 128, 4, 12, 6, torch.bfloat16, "tc"),
     (1, 30, 30, 64, 2, 12, 6, torch.bfloat16, "tc"), (2, 16, 20, 96, 3, 8, 4, torch.bfloat16, "tc"),
     (1, 15, 15, 64, 2, 6, 3, torch.bfloat16, "tc"), (1, 32, 32, 32, 1, 16, 8, torch.bfloat16, "tc"),
-    (3, 12, 12, 512, 16, 12, 0, torch.bfloat16, "tc"), (1, 9, 10, 64, 2, 4, 2, torch.bfloat16, "tc")])
+    (3, 12, 12, 512, 16, 12, 0, torch.bfloat16, "tc"), (1, 9, 10, 64, 2, 4, 2, torch.bfloat16, "tc"),
+    # BASELINE config 5 (window-attention microbench shapes: windows 8 / 12 / 16 / 24, heads 3 - 48, shifted and not) and
+    # the Swin-L / Swin-T head counts of configs 1 and 4, through whichever implementation "auto" picks
+    (1, 24, 24, 96, 3, 24, 12, torch.bfloat16, "auto"), (1, 32, 32, 192, 6, 16, 8, torch.bfloat16, "auto"),
+    (1, 24, 24, 768, 24, 12, 6, torch.bfloat16, "auto"), (1, 16, 16, 1536, 48, 8, 0, torch.bfloat16, "auto"),
+    (1, 22, 38, 384, 12, 24, 12, torch.float32, "auto")])
 def test_attention_core_vs_oracle(B, H, W, C, nH, ws, shift, dtype, impl):
     """The core kernel alone (natural-order qkv in, natural-order out), forward and every gradient, against the
     oracle's gather -> dense attention -> scatter in float64."""
