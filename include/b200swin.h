@@ -108,11 +108,15 @@ int b200swin_ln_bwd(const void* dy, const void* x, const float* gamma, const flo
  * WindowAttention.forward (models/swin_transformer_v2.py:304-313, rpe_output_type='sigmoid'):
  *   table[T,nH] = 16 * sigmoid( relu(coords[T,2] @ W0[HID,2]^T + b0[HID]) @ W2[nH,HID]^T ),  all float32.
  * bwd: given dtable (and the saved table) writes dW0, db0, dW2 (deterministic, no atomics).  nH <= 64.
+ * Optionally (logit_scale != NULL) the same launches also compute the per-head temperature of the cosine attention,
+ *   scale[h] = exp(min(logit_scale[h], ln 100))                                        (:294)
+ * and its gradient d logit_scale[h] = d scale[h] * scale[h] where the clamp is inactive.
  * ------------------------------------------------------------------------------------------ */
-int b200swin_cpb_fwd(const float* coords, const float* w0, const float* b0, const float* w2, float* table, int T,
-                     int HID, int nH, void* stream);
+int b200swin_cpb_fwd(const float* coords, const float* w0, const float* b0, const float* w2, float* table,
+                     const float* logit_scale, float* scale, int T, int HID, int nH, void* stream);
 int b200swin_cpb_bwd(const float* coords, const float* w0, const float* b0, const float* w2, const float* table,
-                     const float* dtable, float* dw0, float* db0, float* dw2, int T, int HID, int nH, void* stream);
+                     const float* dtable, float* dw0, float* db0, float* dw2, const float* logit_scale,
+                     const float* dscale, float* dlogit_scale, int T, int HID, int nH, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Attention core.  Replaces, for attn_type='cosine_mh', the body of WindowAttention.forward between

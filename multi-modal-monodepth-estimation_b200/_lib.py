@@ -35,8 +35,8 @@ SIGNATURES = {
     "b200swin_shift_mask": (I, [P, I, I, I, I, P]),
     "b200swin_patch_merge": (I, [P, P, I, I, I, I, I, I, P]),
     "b200swin_patchify": (I, [P, I, P, I, I, I, I, I, I, I, P]),
-    "b200swin_cpb_fwd": (I, [P, P, P, P, P, I, I, I, P]),
-    "b200swin_cpb_bwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, P]),
+    "b200swin_cpb_fwd": (I, [P, P, P, P, P, P, P, I, I, I, P]),
+    "b200swin_cpb_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "b200swin_ln_fwd": (I, [P, P, P, P, P, L, P, P, P, L, I, F, I, P]),
     "b200swin_ln_bwd_workspace_bytes": (Z, [L, I]),
     "b200swin_ln_bwd": (I, [P, P, P, P, P, P, L, P, P, P, P, L, I, I, P, Z, P]),

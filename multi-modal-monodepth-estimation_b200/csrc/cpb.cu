@@ -15,12 +15,16 @@ namespace b200swin {
 
 constexpr int kCpbThreads = 128;
 constexpr int kCpbMaxHeads = 64;
+constexpr float kLogitMax = 4.605170185988092f;   // ln(1 / 0.01)
 
 __global__ void __launch_bounds__(kCpbThreads)
 cpb_fwd_kernel(const float* __restrict__ coords, const float* __restrict__ w0, const float* __restrict__ b0,
-               const float* __restrict__ w2, float* __restrict__ table, int T, int HID, int nH) {
+               const float* __restrict__ w2, float* __restrict__ table, const float* __restrict__ logit_scale,
+               float* __restrict__ scale, int T, int HID, int nH) {
   extern __shared__ float hid[];   // [HID]
   const int t = blockIdx.x;
+  // per-head temperature of the cosine attention: exp(min(logit_scale, ln 100))   (swin_transformer_v2.py:294)
+  if (t == 0 && logit_scale && threadIdx.x < nH) scale[threadIdx.x] = __expf(fminf(logit_scale[threadIdx.x], kLogitMax));
   const float c0 = coords[2 * t], c1 = coords[2 * t + 1];
   for (int k = threadIdx.x; k < HID; k += kCpbThreads)
     hid[k] = fmaxf(fmaf(c0, w0[2 * k], fmaf(c1, w0[2 * k + 1], b0[k])), 0.f);
@@ -43,9 +47,16 @@ constexpr int kCpbTile = 128;
 __global__ void __launch_bounds__(kCpbUnits * 32)
 cpb_bwd_kernel(const float* __restrict__ coords, const float* __restrict__ w0, const float* __restrict__ b0,
                const float* __restrict__ w2, const float* __restrict__ table, const float* __restrict__ dtable,
-               float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw2, int T, int HID, int nH) {
+               float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw2,
+               const float* __restrict__ logit_scale, const float* __restrict__ dscale, float* __restrict__ dlogit, int T,
+               int HID, int nH) {
   extern __shared__ float sdz[];     // [nH][kCpbTile + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // d logit_scale = d scale * scale where the clamp is inactive (torch.clamp passes the gradient for x <= max)
+  if (blockIdx.x == 0 && logit_scale && threadIdx.x < nH) {
+    const float ls = logit_scale[threadIdx.x];
+    dlogit[threadIdx.x] = ls <= kLogitMax ? dscale[threadIdx.x] * __expf(ls) : 0.f;
+  }
   const int k = blockIdx.x * kCpbUnits + warp;
   const bool kvalid = k < HID;
   const float wa = kvalid ? w0[2 * k] : 0.f, wb = kvalid ? w0[2 * k + 1] : 0.f, bb = kvalid ? b0[k] : 0.f;
@@ -101,25 +112,29 @@ cpb_bwd_kernel(const float* __restrict__ coords, const float* __restrict__ w0, c
 using namespace b200swin;
 
 extern "C" int b200swin_cpb_fwd(const float* coords, const float* w0, const float* b0, const float* w2, float* table,
-                                int T, int HID, int nH, void* stream) {
+                                const float* logit_scale, float* scale, int T, int HID, int nH, void* stream) {
   BSW_REQUIRE(coords && w0 && b0 && w2 && table, "cpb_fwd: null pointer");
+  BSW_REQUIRE((logit_scale == nullptr) == (scale == nullptr), "cpb_fwd: logit_scale and scale go together");
   BSW_REQUIRE(T > 0 && HID > 0 && HID <= 8192 && nH > 0 && nH <= kCpbMaxHeads, "cpb_fwd: T=%d HID=%d nH=%d out of range",
               T, HID, nH);
-  cpb_fwd_kernel<<<T, kCpbThreads, (size_t)HID * sizeof(float), (cudaStream_t)stream>>>(coords, w0, b0, w2, table, T, HID,
-                                                                                     nH);
+  cpb_fwd_kernel<<<T, kCpbThreads, (size_t)HID * sizeof(float), (cudaStream_t)stream>>>(coords, w0, b0, w2, table, logit_scale,
+                                                                                     scale, T, HID, nH);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
 }
 
 extern "C" int b200swin_cpb_bwd(const float* coords, const float* w0, const float* b0, const float* w2,
-                                const float* table, const float* dtable, float* dw0, float* db0, float* dw2, int T,
-                                int HID, int nH, void* stream) {
+                                const float* table, const float* dtable, float* dw0, float* db0, float* dw2,
+                                const float* logit_scale, const float* dscale, float* dlogit, int T, int HID, int nH,
+                                void* stream) {
   BSW_REQUIRE(coords && w0 && b0 && w2 && table && dtable && dw0 && db0 && dw2, "cpb_bwd: null pointer");
+  BSW_REQUIRE((logit_scale == nullptr) == (dscale == nullptr) && (logit_scale == nullptr) == (dlogit == nullptr),
+              "cpb_bwd: logit_scale, dscale and dlogit go together");
   BSW_REQUIRE(T > 0 && HID > 0 && HID <= 8192 && nH > 0 && nH <= kCpbMaxHeads, "cpb_bwd: T=%d HID=%d nH=%d out of range",
               T, HID, nH);
   cpb_bwd_kernel<<<(HID + kCpbUnits - 1) / kCpbUnits, kCpbUnits * 32, (size_t)nH * (kCpbTile + 1) * sizeof(float),
-                   (cudaStream_t)stream>>>(coords, w0, b0, w2, table, dtable, dw0, db0, dw2, T, HID,
-                                                                 nH);
+                   (cudaStream_t)stream>>>(coords, w0, b0, w2, table, dtable, dw0, db0, dw2, logit_scale, dscale, dlogit, T,
+                                            HID, nH);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
 }

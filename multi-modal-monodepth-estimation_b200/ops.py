@@ -532,41 +532,51 @@ def qkv_project(x, weight, q_bias, v_bias, nH, passthrough=False):
 
 # ------------------------------------------------------------------------------ continuous position bias table
 class _CpbTable(torch.autograd.Function):
-    """table16[T,nH] = 16 sigmoid(relu(coords W0^T + b0) W2^T) in one kernel each way
-    (reference: rpe_mlp + sigmoid, swin_transformer_v2.py:304-313)."""
+    """table16[T,nH] = 16 sigmoid(relu(coords W0^T + b0) W2^T) and scale[nH] = exp(min(logit_scale, ln 100)) in one
+    kernel each way (reference: rpe_mlp + sigmoid, swin_transformer_v2.py:304-313; logit_scale clamp + exp, :294)."""
 
     @staticmethod
-    def forward(ctx, coords, w0, b0, w2):
-        L.require_cuda(coords, w0, b0, w2)
+    def forward(ctx, coords, w0, b0, w2, logit_scale):
+        L.require_cuda(coords, w0, b0, w2, logit_scale)
         lib = L.load()
         c = coords.reshape(-1, 2).contiguous().float()
         w0c, b0c, w2c = w0.contiguous().float(), b0.contiguous().float(), w2.contiguous().float()
+        lsc = logit_scale.reshape(-1).contiguous().float()
         T, HID, nH = c.shape[0], w0c.shape[0], w2c.shape[0]
         with torch.cuda.device_of(c):
             table = torch.empty((T, nH), dtype=torch.float32, device=c.device)
+            scale = torch.empty((nH,), dtype=torch.float32, device=c.device)
             L.check(lib.b200swin_cpb_fwd(c.data_ptr(), w0c.data_ptr(), b0c.data_ptr(), w2c.data_ptr(), table.data_ptr(),
-                                         T, HID, nH, L.stream_of(c)), "cpb_fwd")
-        ctx.save_for_backward(c, w0c, b0c, w2c, table)
-        ctx.dtypes = (w0.dtype, b0.dtype, w2.dtype)
-        return table
+                                         lsc.data_ptr(), scale.data_ptr(), T, HID, nH, L.stream_of(c)), "cpb_fwd")
+        ctx.save_for_backward(c, w0c, b0c, w2c, table, lsc)
+        ctx.dtypes = (w0.dtype, b0.dtype, w2.dtype, logit_scale.dtype)
+        ctx.ls_shape = logit_scale.shape
+        ctx.set_materialize_grads(False)
+        return table, scale
 
     @staticmethod
-    def backward(ctx, dtable):
-        c, w0c, b0c, w2c, table = ctx.saved_tensors
+    def backward(ctx, dtable, dscale):
+        c, w0c, b0c, w2c, table, lsc = ctx.saved_tensors
         lib = L.load()
         T, HID, nH = c.shape[0], w0c.shape[0], w2c.shape[0]
-        dt = dtable.contiguous().float()
         with torch.cuda.device_of(c):
-            dw0, db0, dw2 = torch.empty_like(w0c), torch.empty_like(b0c), torch.empty_like(w2c)
+            dt = torch.zeros_like(table) if dtable is None else dtable.contiguous().float()
+            ds = torch.zeros_like(lsc) if dscale is None else dscale.reshape(-1).contiguous().float()
+            dw0, db0, dw2, dls = torch.empty_like(w0c), torch.empty_like(b0c), torch.empty_like(w2c), torch.empty_like(lsc)
             L.check(lib.b200swin_cpb_bwd(c.data_ptr(), w0c.data_ptr(), b0c.data_ptr(), w2c.data_ptr(), table.data_ptr(),
-                                         dt.data_ptr(), dw0.data_ptr(), db0.data_ptr(), dw2.data_ptr(), T, HID, nH,
-                                         L.stream_of(c)), "cpb_bwd")
-        d0, d1, d2 = ctx.dtypes
-        return None, dw0.to(d0), db0.to(d1), dw2.to(d2)
+                                         dt.data_ptr(), dw0.data_ptr(), db0.data_ptr(), dw2.data_ptr(), lsc.data_ptr(),
+                                         ds.data_ptr(), dls.data_ptr(), T, HID, nH, L.stream_of(c)), "cpb_bwd")
+        d0, d1, d2, d3 = ctx.dtypes
+        return None, dw0.to(d0), db0.to(d1), dw2.to(d2), dls.view(ctx.ls_shape).to(d3)
+
+
+def cpb_table_and_scale(coords, w0, b0, w2, logit_scale):
+    return _CpbTable.apply(coords, w0, b0, w2, logit_scale)
 
 
 def cpb_table(coords, w0, b0, w2):
-    return _CpbTable.apply(coords, w0, b0, w2)
+    nH = w2.shape[0]
+    return _CpbTable.apply(coords, w0, b0, w2, torch.zeros(nH, device=w2.device))[0]
 
 
 # ------------------------------------------------------------------------------ attention core

@@ -197,11 +197,15 @@ class WindowAttention(nn.Module):
         self.softmax = nn.Softmax(dim=-1)
 
     # -- small host-side pieces (a few kFLOP; autograd carries their gradients) ---------------------
+    def _fused_small_ops(self):
+        l2 = self.rpe_mlp[2]
+        return (self.rpe_output_type == 'sigmoid' and self.relative_coords_table.is_cuda and l2.bias is None
+                and self.num_heads <= 64)
+
     def _bias_table(self):
         """[(2ws-1)^2, nH] fp32: rpe_mlp(coords) then 16*sigmoid (reference :304-313)."""
         l0, l2 = self.rpe_mlp[0], self.rpe_mlp[2]
-        if (self.rpe_output_type == 'sigmoid' and self.relative_coords_table.is_cuda and l2.bias is None
-                and self.num_heads <= 64):
+        if self._fused_small_ops():
             # one kernel forward, one backward (the PyTorch graph below is ~15 latency-bound launches per block)
             return ops.cpb_table(self.relative_coords_table, l0.weight, l0.bias, l2.weight)
         with torch.autocast('cuda', enabled=False):
@@ -213,6 +217,13 @@ class WindowAttention(nn.Module):
     def _scale(self):
         """exp(min(logit_scale, ln 100)) per head (reference :294, without its hard-coded cuda:0)."""
         return torch.clamp(self.logit_scale.float(), max=_LOGIT_MAX).exp().view(self.num_heads)
+
+    def _table_and_scale(self):
+        """Bias table and temperature; on the default configuration both come out of ONE kernel each way."""
+        if self._fused_small_ops():
+            l0, l2 = self.rpe_mlp[0], self.rpe_mlp[2]
+            return ops.cpb_table_and_scale(self.relative_coords_table, l0.weight, l0.bias, l2.weight, self.logit_scale)
+        return self._bias_table(), self._scale()
 
     def _pads(self, needed):
         if not needed or self.q_bias is None:
@@ -232,7 +243,8 @@ class WindowAttention(nn.Module):
         else:
             qkv, inv_norm = ops.qkv_project(x, self.qkv.weight, self.q_bias, self.v_bias, nH)
         qpad, vpad = self._pads(H % ws != 0 or W % ws != 0)
-        o = ops.attention_core(qkv.view(B, H, W, 3 * C), inv_norm, self._bias_table(), self._scale(), qpad, vpad, mask,
+        table16, scale = self._table_and_scale()
+        o = ops.attention_core(qkv.view(B, H, W, 3 * C), inv_norm, table16, scale, qpad, vpad, mask,
                                B, H, W, C, nH, ws, shift)
         pb = self.proj.bias.detach() if (proj_bias_grad_elsewhere and self.proj.bias is not None) else self.proj.bias
         y = ops.linear(o.view(B, H * W, C), self.proj.weight, pb)
