@@ -351,3 +351,30 @@ def test_tensor_core_attention_is_run_to_run_deterministic(B, H, C, ws, shift):
         assert torch.equal(outs[0], x), "forward differs between runs"
     for x in grads[1:]:
         assert torch.equal(grads[0], x), "dqkv differs between runs"
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_blocks_are_recompute_safe_under_checkpoint(autocast):
+    """use_checkpoint=True (models/swin_transformer_v2.py:895-896; the reference's configs turn it on) must give the same
+    outputs and gradients as the plain path: the custom autograd Functions (aliased residual inputs, detached producer
+    biases, gradients routed through the LayerNorm backward) are re-run under torch.utils.checkpoint."""
+    g = load_golden("layer_post_c128_ws12_pad")
+    res = []
+    for ckpt in (False, True):
+        layer, (H, W, down) = _build_layer(g)
+        layer.use_checkpoint = ckpt
+        layer.train()
+        x = torch.from_numpy(g["in.x"]).cuda().requires_grad_(True)
+        with torch.autocast("cuda", torch.bfloat16, enabled=autocast):
+            x_out, _, _, x_down, _, _ = layer(x, H, W)
+        total = (x_out.float() * torch.from_numpy(g["in.cot2"]).cuda()).sum()
+        if down:
+            total = total + (x_down.float() * torch.from_numpy(g["in.cot"]).cuda()).sum()
+        total.backward()
+        res.append((x_out.detach().float(), x.grad.float(), {n: p.grad.float() for n, p in layer.named_parameters()}))
+    (o0, gx0, gp0), (o1, gx1, gp1) = res
+    assert torch.equal(o0, o1)
+    assert _relerr(gx1, gx0.cpu().numpy()) < 1e-5
+    for n in gp0:
+        # bias-table / temperature gradients are accumulated with atomics: equal up to summation order
+        assert _relerr(gp1[n], gp0[n].cpu().numpy()) < 1e-4, n
