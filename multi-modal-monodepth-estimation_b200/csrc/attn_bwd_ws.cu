@@ -636,7 +636,10 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
     auto flush_head = [&](int h) {
       // register sums of the main rows -> smem table space
       {
-        const int r = row_local;
+        // `opaque` keeps the compiler from hoisting the 48 (loop-invariant) table indices of this once-per-head flush out
+        // of the unit loop, where they would occupy 48 registers for the whole kernel
+        int r = row_local;
+        asm volatile("" : "+r"(r));
         if (r < N) {
           const int base_i = ((r / WS) * TW + (r % WS)) + (WS - 1) * (TW + 1);
           const int c0 = kq == 0 ? CF::K0 : kq == 1 ? CF::K1 : CF::K2;
