@@ -234,6 +234,12 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
   __shared__ __align__(8) uint64_t kv_full[NSTAGE], kv_empty[NSTAGE];
   __shared__ __align__(8) uint64_t s_full[NSLOT], p_full[NSLOT], o_full[NSLOT], slot_free[NSLOT];
   __shared__ uint32_t tmem_slot;
+  // Item headers (head, batch, window row / column, window index), written by the gather warps, which derive them anyway.
+  // The softmax warps re-read them from shared memory wherever they need them: no divisions per item (three, one of
+  // them 64-bit, cost each warp ~1000 cycles per item) and nothing about the item lives in registers across the
+  // softmax (the allocator spilled it: seven L2 round trips per epilogue).  Twice as deep as the operand ring: the
+  // epilogue of an item may still read its header after the item's stage has been handed back.
+  __shared__ int s_hdr[2 * NSTAGE][8];
 
   const WinGeom& g = a.g;
   const uint32_t base_u32 = (ptx::smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -361,6 +367,10 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
           const int w = (int)(win - (int64_t)b * nW);
           const int wh = w / g.nWw, ww = w - wh * g.nWw;
           unsigned char* st = sm + (size_t)stage * CF::kStage;
+          if (lt == 0) {
+            int* hd = s_hdr[i % (2 * NSTAGE)];
+            hd[0] = h; hd[1] = b; hd[2] = wh; hd[3] = ww; hd[4] = (int)win;
+          }
           const uint32_t q_s = ptx::smem_u32(st), k_s = q_s + CF::kRow, v_s = k_s + CF::kRow;
           for (int idx = lt; idx < NPAD * 4; idx += kLoaders) {
             const int r = idx >> 2, c = idx & 3;
@@ -418,9 +428,16 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
     int cur_head = -1;
     float scale2 = 0.f;
 
+    auto hdr_ld = [&](int il, int f) {               // volatile: always from shared memory, never kept in a register
+      int v;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(ptx::smem_u32(&s_hdr[il % (2 * NSTAGE)][f])));
+      return v;
+    };
+    int c_h = (int)(g0 / a.nwin);                    // head of the current item, by a running counter
+    int c_left = (int)((int64_t)(c_h + 1) * a.nwin - g0);   // items left in this head
     for (int il = 0; il < n; ++il) {
-      const int64_t gi = g0 + il;
-      const int h = (int)(gi / a.nwin);
+      const int h = c_h;
+      if (--c_left == 0) { ++c_h; c_left = (int)a.nwin; }
       if (h != cur_head) {
         // every softmax warp has finished all earlier items: rebuild the expanded bias matrix of head h (log2 units)
         named_bar_sync(1, kSoftmax);
@@ -435,12 +452,6 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
         scale2 = a.scale[h] * kLog2e;
       }
       if ((il & 1) != ug) continue;
-      const int64_t win = gi - (int64_t)h * a.nwin;
-      const int b = (int)(win / nW);
-      const int w = (int)(win - (int64_t)b * nW);
-      const int wh = w / g.nWw, ww = w - wh * g.nWw;
-      const bool last_h = wh == g.nWh - 1, last_w = ww == g.nWw - 1;
-      const bool need_mask = g.shift > 0 && (last_h || last_w);          // CTA-uniform per item
 
 #pragma unroll 1
       for (int tile = 0; tile < MT; ++tile) {
@@ -459,6 +470,10 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
         ptx::mbar_wait(&s_full[slot], par);
         TR(31, u);
         ptx::tc_fence_after();
+        // S of the item exists, so its gather -- and its header -- have landed
+        const int wh = hdr_ld(il, 2), ww = hdr_ld(il, 3);
+        const bool last_h = wh == g.nWh - 1, last_w = ww == g.nWw - 1;
+        const bool need_mask = g.shift > 0 && (last_h || last_w);          // CTA-uniform per item
         float m = -INFINITY, l = 0.f;
         if (warp_active && (half == 0 || CF::KB > 0)) {
           uint32_t by = 0, bx = 0;
@@ -507,8 +522,9 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
           const float mm = fmaxf(mla.x, m);
           const float wa = ex2(mla.x - mm), wb = CF::KB > 0 ? ex2(m - mm) : 0.f;
           const float lt = mla.y * wa + l * wb;
-          a.lse[((int64_t)win * a.nH + h) * N + r] = (mm + log2f(lt)) * kLn2;
-          const int t = src_token(g, b, wh, ww, r / WS, r % WS);
+          const int hh = hdr_ld(il, 0);
+          a.lse[((int64_t)hdr_ld(il, 4) * a.nH + hh) * N + r] = (mm + log2f(lt)) * kLn2;
+          const int t = src_token(g, hdr_ld(il, 1), hdr_ld(il, 2), hdr_ld(il, 3), r / WS, r % WS);
           if (t >= 0) {
             const float ia = wa / lt, ib = wb / lt;
             float o[32];
@@ -517,7 +533,7 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
               o[c] = __uint_as_float(oa[c]) * ia;
               if (CF::KB > 0) o[c] = fmaf(__uint_as_float(ob[c]), ib, o[c]);
             }
-            uint4* dst = reinterpret_cast<uint4*>(a.out + (int64_t)t * a.C + h * HD);
+            uint4* dst = reinterpret_cast<uint4*>(a.out + (int64_t)t * a.C + hh * HD);
 #pragma unroll
             for (int c = 0; c < 4; ++c)
               dst[c] = make_uint4(pack_bf16(o[c * 8 + 0], o[c * 8 + 1]), pack_bf16(o[c * 8 + 2], o[c * 8 + 3]),
@@ -585,6 +601,7 @@ int attn_fwd_ws(const void* qkv, void* out, float* lse, const float* table16, co
   a.nwin = (int64_t)B * a.g.nWh * a.g.nWw;
   a.nitems = a.nwin * nH;
   a.trace = nullptr;
+  BSW_REQUIRE(a.nwin < (1ll << 31), "attn_fwd(ws): too many windows");
   switch (ws) {
     case 4: return launch_ws<4>(a, st);
     case 6: return launch_ws<6>(a, st);
