@@ -185,17 +185,17 @@ __device__ __forceinline__ int src_token(const WinGeom& g, int b, int wh, int ww
 // Warp-collective (tcgen05.ld): every lane calls it; `active` lanes own a row and store.
 __device__ __forceinline__ void normalize_bwd_store(uint32_t taddr, const unsigned char* tile, int r, float sc, float invn,
                                                     __nv_bfloat16* dst, bool active) {
-  // two passes over the accumulator in 16-column pieces: at most 16 registers of it are live at a time
+  // two passes over the accumulator (dot product, then the row), each with BOTH 16-column loads in flight and one wait
   float dot = 0.f;
-#pragma unroll
-  for (int hf = 0; hf < 2; ++hf) {
-    uint32_t o[16];
-    tmem_ld16(taddr + hf * 16, o);
+  {
+    uint32_t o[32];
+    tmem_ld16(taddr, o);
+    tmem_ld16(taddr + 16, o + 16);
     ptx::tmem_ld_wait();
     if (active) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint4 w = *reinterpret_cast<const uint4*>(tile + sw64_off(r, hf * 2 + c));
+      for (int c = 0; c < 4; ++c) {
+        const uint4 w = *reinterpret_cast<const uint4*>(tile + sw64_off(r, c));
         const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -207,15 +207,15 @@ __device__ __forceinline__ void normalize_bwd_store(uint32_t taddr, const unsign
     }
   }
   dot *= sc;
-#pragma unroll
-  for (int hf = 0; hf < 2; ++hf) {
-    uint32_t o[16];
-    tmem_ld16(taddr + hf * 16, o);
+  {
+    uint32_t o[32];
+    tmem_ld16(taddr, o);
+    tmem_ld16(taddr + 16, o + 16);
     ptx::tmem_ld_wait();
     if (active) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint4 w = *reinterpret_cast<const uint4*>(tile + sw64_off(r, hf * 2 + c));
+      for (int c = 0; c < 4; ++c) {
+        const uint4 w = *reinterpret_cast<const uint4*>(tile + sw64_off(r, c));
         const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
         uint32_t pk[4];
 #pragma unroll
@@ -224,7 +224,7 @@ __device__ __forceinline__ void normalize_bwd_store(uint32_t taddr, const unsign
           pk[e] = pack_bf16((__uint_as_float(o[c * 8 + 2 * e]) * sc - f.x * dot) * invn,
                             (__uint_as_float(o[c * 8 + 2 * e + 1]) * sc - f.y * dot) * invn);
         }
-        reinterpret_cast<uint4*>(dst)[hf * 2 + c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        reinterpret_cast<uint4*>(dst)[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
   }
