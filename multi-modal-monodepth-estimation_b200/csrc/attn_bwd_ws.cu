@@ -531,6 +531,14 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
       const int lt = threadIdx.x - kCompute;
       const int C3 = 3 * a.C;
       int pending = 0;
+      // item geometry by running counters (three runtime divisions per item and thread otherwise; these warps share
+      // their sub-partitions' issue slots with the compute warps)
+      const int nwin_i = (int)a.nwin;
+      int c_h = (int)(g0 / a.nwin);
+      int c_win = (int)(g0 - (int64_t)c_h * a.nwin);
+      int c_b = c_win / nW;
+      int c_wh = (c_win - c_b * nW) / g.nWw;
+      int c_ww = (c_win - c_b * nW) - c_wh * g.nWw;
       for (int i = 0; i < n; ++i) {
         const int stage = i % NSTAGE;
         const uint32_t par = ((i / NSTAGE) & 1) ^ 1;
@@ -545,12 +553,10 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
           ptx::mbar_wait(&kv_empty[stage], par);
         }
         TR(21, i);
-        const int64_t gi = g0 + i;
-        const int h = (int)(gi / a.nwin);
-        const int64_t win = gi - (int64_t)h * a.nwin;
-        const int b = (int)(win / nW);
-        const int w = (int)(win - (int64_t)b * nW);
-        const int wh = w / g.nWw, ww = w - wh * g.nWw;
+        const int h = c_h, b = c_b, wh = c_wh, ww = c_ww;
+        const int64_t win = c_win;
+        if (++c_win == nwin_i) { c_win = 0; ++c_h; c_b = c_wh = c_ww = 0; }
+        else if (++c_ww == g.nWw) { c_ww = 0; if (++c_wh == g.nWh) { c_wh = 0; ++c_b; } }
         unsigned char* st = ring + (size_t)stage * CF::kStage;
         const uint32_t q_s = ptx::smem_u32(st), g_s = q_s + CF::kRow, k_s = g_s + CF::kRow, v_s = k_s + CF::kRow;
         const uint32_t lse_s = v_s + CF::kRow, d_s = lse_s + NPAD * 4, iq_s = d_s + NPAD * 4, ik_s = iq_s + NPAD * 4;
@@ -969,6 +975,7 @@ int attn_bwd_ws(const void* qkv, const void* out, const void* dout, const float*
   a.C = C; a.nH = nH;
   a.nwin = (int64_t)B * a.g.nWh * a.g.nWw;
   a.nitems = a.nwin * nH;
+  BSW_REQUIRE(a.nwin < (1ll << 31), "attn_bwd(ws): too many windows");
   a.trace = nullptr;
   {
     const int64_t n = (int64_t)B * H * W * nH;

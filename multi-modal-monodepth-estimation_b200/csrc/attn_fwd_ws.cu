@@ -345,6 +345,13 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
       // (kv_full) as soon as it is LAG groups old -- and everything in flight is published before the warp goes to
       // sleep on a full ring, so the MMA warp can always run ahead on what has already landed.
       int pending = 0;
+      // item geometry by running counters (no runtime divisions per item)
+      const int nwin_i = (int)a.nwin;
+      int c_h = (int)(g0 / a.nwin);
+      int c_win = (int)(g0 - (int64_t)c_h * a.nwin);
+      int c_b = c_win / nW;
+      int c_wh = (c_win - c_b * nW) / g.nWw;
+      int c_ww = (c_win - c_b * nW) - c_wh * g.nWw;
       for (int i = 0; i < n; ++i) {
         {
           const int stage = i % NSTAGE;
@@ -360,12 +367,10 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
             ptx::mbar_wait(&kv_empty[stage], par);
           }
           TR(21, i);
-          const int64_t gi = g0 + i;
-          const int h = (int)(gi / a.nwin);
-          const int64_t win = gi - (int64_t)h * a.nwin;
-          const int b = (int)(win / nW);
-          const int w = (int)(win - (int64_t)b * nW);
-          const int wh = w / g.nWw, ww = w - wh * g.nWw;
+          const int h = c_h, b = c_b, wh = c_wh, ww = c_ww;
+          const int64_t win = c_win;
+          if (++c_win == nwin_i) { c_win = 0; ++c_h; c_b = c_wh = c_ww = 0; }
+          else if (++c_ww == g.nWw) { c_ww = 0; if (++c_wh == g.nWh) { c_wh = 0; ++c_b; } }
           unsigned char* st = sm + (size_t)stage * CF::kStage;
           if (lt == 0) {
             int* hd = s_hdr[i % (2 * NSTAGE)];
