@@ -311,11 +311,14 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
 
   // static persistent schedule: tile t -> (split z, m block, n block); n fastest so that CTAs running at the
   // same time share the streamed A tile in L2 (the weight-side B operand is small and stays resident)
+  // 32-bit arithmetic (the host checks num_tiles < 2^31): every role decodes every tile, the epilogue warps of the
+  // side-tensor epilogues three times per tile, and a 64-bit division is ~100 instructions
   auto decode = [&](int64_t t, int& mb, int& nb, int& z) {
-    nb = (int)(t % p.n_tiles);
-    int64_t r = t / p.n_tiles;
-    mb = (int)(r % p.m_tiles);
-    z = (int)(r / p.m_tiles);
+    const uint32_t tt = (uint32_t)t, nt = (uint32_t)p.n_tiles, mt = (uint32_t)p.m_tiles;
+    const uint32_t r = tt / nt;
+    nb = (int)(tt - r * nt);
+    z = (int)(r / mt);
+    mb = (int)(r - (uint32_t)z * mt);
   };
 
   if (warp == 0) {
@@ -644,6 +647,7 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   p.m_tiles = (int)((M + BM - 1) / BM);
   p.n_tiles = (int)((N + bn - 1) / bn);
   p.num_tiles = (int64_t)p.m_tiles * p.n_tiles * splits;
+  BSW_REQUIRE(p.num_tiles < (1ll << 31), "gemm: too many tiles");
   const unsigned grid = (unsigned)(p.num_tiles < sm_count() ? p.num_tiles : sm_count());
   const bool out_bf16 = out_dtype == B200SWIN_BF16 && splits == 1;     // split-K partials are fp32
 #define LAUNCH(AM, BMN, BNV, EPI, OB)                                                                              \
