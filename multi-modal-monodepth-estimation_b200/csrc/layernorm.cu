@@ -57,7 +57,7 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, const flo
         }
       }
       const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
-      const float sc = row_scale ? row_scale[row / rows_per_scale] : 1.0f;
+      const float sc = row_scale ? row_scale[(uint32_t)row / (uint32_t)rows_per_scale] : 1.0f;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int c = lane * 4 + k * 128;
@@ -117,7 +117,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
     for (int r = 0; r < R; ++r) {
       const int64_t row = row0 + r;
       if (row >= rows) break;                       // warp-uniform
-      const float sc = row_scale ? row_scale[row / rows_per_scale] : 1.0f;
+      const float sc = row_scale ? row_scale[(uint32_t)row / (uint32_t)rows_per_scale] : 1.0f;
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
@@ -422,7 +422,7 @@ ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         }
       }
       const float rstd = rsqrtf(row_sum<LPR>(q2.x + q2.y) * inv_c + eps);
-      const float sc = (row_scale && live) ? row_scale[row / rows_per_scale] : 1.0f;
+      const float sc = (row_scale && live) ? row_scale[(uint32_t)row / (uint32_t)rows_per_scale] : 1.0f;
       const float a = rstd * sc, b0 = -mean * a;    // ((x - mean) rstd g + b) sc + r = (x a + b0) g + (b sc + r)
       const float2 a2 = f2(a), b02 = f2(b0), sc2 = f2(sc);
 #pragma unroll
@@ -518,7 +518,7 @@ ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
       const int64_t row = row0 + rl;
       if (row0 + p * RPW >= rows) break;                             // warp-uniform
       const bool live = row < rows;
-      const float sc = (row_scale && live) ? row_scale[row / rows_per_scale] : 1.0f;
+      const float sc = (row_scale && live) ? row_scale[(uint32_t)row / (uint32_t)rows_per_scale] : 1.0f;
       const float a = rstd[p], b0 = -mean[p] * rstd[p];             // x_hat = x a + b0
       // packed fp32x2 math (the kernel is issue-bound once the loads are decoupled): pairs (even, odd column)
       const float2 a2 = f2(a), b2 = f2(b0), sc2 = f2(sc);
@@ -719,6 +719,7 @@ extern "C" int b200swin_ln_fwd(const void* x, const void* residual, const float*
   BSW_REQUIRE(x && gamma && beta && y && mean && rstd, "ln_fwd: null pointer");
   BSW_REQUIRE(rows >= 0 && C > 0 && C % 4 == 0 && C <= 3072, "ln_fwd: C=%d must be a multiple of 4, <= 3072", C);
   BSW_REQUIRE(!row_scale || rows_per_scale > 0, "ln_fwd: rows_per_scale must be > 0 with row_scale");
+  BSW_REQUIRE(!row_scale || (rows < (1ll << 32) && rows_per_scale < (1ll << 32)), "ln_fwd: row_scale needs rows < 2^32");
   BSW_REQUIRE(dtype == B200SWIN_F32 || dtype == B200SWIN_BF16, "ln_fwd: bad dtype %d", dtype);
   if (rows == 0) return B200SWIN_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -742,6 +743,7 @@ extern "C" int b200swin_ln_bwd(const void* dy, const void* x, const float* gamma
   BSW_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, "ln_bwd: null pointer");
   BSW_REQUIRE(rows > 0 && C > 0 && C % 4 == 0 && C <= 3072, "ln_bwd: bad rows/C");
   BSW_REQUIRE(!row_scale || rows_per_scale > 0, "ln_bwd: rows_per_scale must be > 0 with row_scale");
+  BSW_REQUIRE(!row_scale || (rows < (1ll << 32) && rows_per_scale < (1ll << 32)), "ln_bwd: row_scale needs rows < 2^32");
   BSW_REQUIRE(dtype == B200SWIN_F32 || dtype == B200SWIN_BF16, "ln_bwd: bad dtype %d", dtype);
   BSW_REQUIRE(workspace_bytes >= b200swin_ln_bwd_workspace_bytes(rows, C), "ln_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;

@@ -43,30 +43,32 @@ window_move_kernel(const V* __restrict__ src, V* __restrict__ dst, WinGeom g, in
 template <bool kGather>
 __global__ void __launch_bounds__(256)
 patch_merge_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int B, int H, int W, int H2, int W2,
-                   int row_vecs /* 16-byte vectors per C */, int64_t total) {
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+                   int row_vecs /* 16-byte vectors per C */, uint32_t total) {
+  // 32-bit index arithmetic (the host checks total < 2^31): a 64-bit division is ~100 instructions per vector
+  const uint32_t rv = (uint32_t)row_vecs;
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < total; v += gridDim.x * blockDim.x) {
     if (kGather) {
       // v over merged [B, H2, W2, 4, row_vecs]
-      int cv = (int)(v % row_vecs);
-      int64_t t = v / row_vecs;
+      uint32_t t = v / rv;
+      const uint32_t cv = v - t * rv;
       const int k = (int)(t & 3);
       t >>= 2;
-      const int j2 = (int)(t % W2);
-      t /= W2;
-      const int i2 = (int)(t % H2);
-      const int b = (int)(t / H2);
+      uint32_t t2 = t / (uint32_t)W2;
+      const int j2 = (int)(t - t2 * (uint32_t)W2);
+      const uint32_t b = t2 / (uint32_t)H2;
+      const int i2 = (int)(t2 - b * (uint32_t)H2);
       const int i = 2 * i2 + (k & 1), j = 2 * j2 + (k >> 1);
       uint4 val = make_uint4(0u, 0u, 0u, 0u);
       if (i < H && j < W) val = src[(((int64_t)b * H + i) * W + j) * row_vecs + cv];
       dst[v] = val;
     } else {
       // v over x [B, H, W, row_vecs]
-      int cv = (int)(v % row_vecs);
-      int64_t t = v / row_vecs;
-      const int j = (int)(t % W);
-      t /= W;
-      const int i = (int)(t % H);
-      const int b = (int)(t / H);
+      uint32_t t = v / rv;
+      const uint32_t cv = v - t * rv;
+      uint32_t t2 = t / (uint32_t)W;
+      const int j = (int)(t - t2 * (uint32_t)W);
+      const uint32_t b = t2 / (uint32_t)H;
+      const int i = (int)(t2 - b * (uint32_t)H);
       const int k = (i & 1) + 2 * (j & 1);
       dst[v] = src[((((int64_t)b * H2 + (i >> 1)) * W2 + (j >> 1)) * 4 + k) * row_vecs + cv];
     }
@@ -195,14 +197,15 @@ extern "C" int b200swin_patch_merge(const void* in, void* out, int B, int H, int
   const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
   const int row_vecs = (int)(row_bytes / 16);
   const int64_t total = backward ? (int64_t)B * H * W * row_vecs : (int64_t)B * H2 * W2 * 4 * row_vecs;
+  BSW_REQUIRE(total < (1ll << 31), "patch_merge: tensor too large for 32-bit vector indices");
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;
   const int grid = (int)(blocks < cap ? blocks : cap);
   cudaStream_t st = (cudaStream_t)stream;
   if (backward)
-    patch_merge_kernel<false><<<grid, 256, 0, st>>>((const uint4*)in, (uint4*)out, B, H, W, H2, W2, row_vecs, total);
+    patch_merge_kernel<false><<<grid, 256, 0, st>>>((const uint4*)in, (uint4*)out, B, H, W, H2, W2, row_vecs, (uint32_t)total);
   else
-    patch_merge_kernel<true><<<grid, 256, 0, st>>>((const uint4*)in, (uint4*)out, B, H, W, H2, W2, row_vecs, total);
+    patch_merge_kernel<true><<<grid, 256, 0, st>>>((const uint4*)in, (uint4*)out, B, H, W, H2, W2, row_vecs, (uint32_t)total);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
 }
