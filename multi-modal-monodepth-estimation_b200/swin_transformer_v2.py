@@ -50,10 +50,13 @@ class DropPath(nn.Module):
     def __init__(self, drop_prob: float = 0.0):
         super().__init__()
         self.drop_prob = float(drop_prob)
+        self._drawn = []          # masks pre-drawn for this forward by SwinTransformerV2._draw_drop_paths
 
     def sample_scale(self, x: torch.Tensor):
         if self.drop_prob == 0.0 or not self.training:
             return None
+        if self._drawn and self._drawn[0].shape[0] == x.shape[0]:
+            return self._drawn.pop(0)
         keep = 1.0 - self.drop_prob
         m = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device).bernoulli_(keep)
         return m.div_(keep) if keep > 0.0 else m
@@ -618,7 +621,34 @@ class SwinTransformerV2(nn.Module):
         elif pretrained is not None and pretrained != '':
             raise TypeError('pretrained must be a str or None')
 
+    def _draw_drop_paths(self, B, device):
+        """All stochastic-depth masks of one forward in two launches instead of two per DropPath call (each block draws
+        twice: ~94 launch-bound kernels per step on Swin-V2-B).  Same distribution as the per-call draw,
+        Bernoulli(keep) / keep per sample; skipped under activation checkpointing, whose recompute relies on replaying
+        the RNG of per-call draws."""
+        if not self.training or any(getattr(l, 'use_checkpoint', False) for l in self.layers):
+            return []
+        mods = [m for m in self.modules() if isinstance(m, DropPath) and m.training and 0.0 < m.drop_prob < 1.0]
+        if not mods:
+            return []
+        key = (str(device), tuple(m.drop_prob for m in mods))
+        if getattr(self, '_dp_keep_key', None) != key:
+            keep = torch.tensor([1.0 - m.drop_prob for m in mods for _ in range(2)], dtype=torch.float32)
+            self._dp_keep, self._dp_keep_key = keep.to(device).view(-1, 1), key
+        masks = torch.bernoulli(self._dp_keep.expand(-1, B)).div_(self._dp_keep)
+        for i, m in enumerate(mods):
+            m._drawn = [masks[2 * i], masks[2 * i + 1]]
+        return mods
+
     def forward(self, x):
+        drawn = self._draw_drop_paths(x.shape[0], x.device)
+        try:
+            return self._forward(x)
+        finally:
+            for m in drawn:
+                m._drawn = []
+
+    def _forward(self, x):
         x, Wh, Ww = self.patch_embed.forward_tokens(x)
         outs = []
         for i in range(self.num_layers):

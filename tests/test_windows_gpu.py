@@ -80,7 +80,8 @@ def test_patch_merge_bit_exact_forward_and_adjoint(B, H, W, C, dtype):
 
 
 @pytest.mark.parametrize("B,H,W,E,dtype", [(2, 480, 480, 128, torch.float32), (2, 64, 96, 96, torch.bfloat16),
-                                           (1, 30, 41, 128, torch.float32)])
+                                           (1, 30, 41, 128, torch.float32),
+                                           (1, 8, 1100, 32, torch.float32)])     # wide frame: the per-thread patchify
 def test_patch_embed_gemm_matches_conv(B, H, W, E, dtype):
     """PatchEmbed as patchify + GEMM against the conv it replaces (models/swin_transformer_v2.py:941-957), forward and
     the weight / bias gradients; fp32 within 1e-4, bf16 (autocast) within 2e-2 relative."""
