@@ -896,17 +896,18 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
   }
 }
 
-// D[t, h] = <dO[t, h, :], O[t, h, :]>  (one thread per (token, head); 2 x 64 B in, 4 B out)
+// D[t, h] = <dO[t, h, :], O[t, h, :]>: four threads per (token, head), 16 bytes of each tensor per thread (a warp
+// instruction reads 512 contiguous bytes), two shuffles, 4 B out.
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out, float* __restrict__ dvec,
                      int64_t n /* tokens * heads */) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint4* g4 = reinterpret_cast<const uint4*>(dout + i * HD);
-    const uint4* o4 = reinterpret_cast<const uint4*>(out + i * HD);
+  const int64_t n4 = 4 * n, stride = (int64_t)gridDim.x * blockDim.x;
+  // warp-uniform trip count: the shuffles below are executed by whole warps
+  for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < n4; w0 += stride) {
+    const int64_t i = w0 + (threadIdx.x & 31);
     float d = 0.f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint4 gv = g4[c], ov = o4[c];
+    if (i < n4) {
+      const uint4 gv = reinterpret_cast<const uint4*>(dout)[i], ov = reinterpret_cast<const uint4*>(out)[i];
       const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -916,7 +917,9 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
         d = fmaf(gf.y, of.y, d);
       }
     }
-    dvec[i] = d;
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    if ((i & 3) == 0 && i < n4) dvec[i >> 2] = d;
   }
 }
 
@@ -979,7 +982,7 @@ int attn_bwd_ws(const void* qkv, const void* out, const void* dout, const float*
   a.trace = nullptr;
   {
     const int64_t n = (int64_t)B * H * W * nH;
-    int64_t blocks = (n + 255) / 256, cap = (int64_t)sm_count() * 16;
+    int64_t blocks = (4 * n + 255) / 256, cap = (int64_t)sm_count() * 16;
     attn_bwd_prep_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(
         (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (float*)workspace, n);
     BSW_LAUNCH_CHECK();

@@ -32,7 +32,8 @@ cpb_fwd_kernel(const float* __restrict__ coords, const float* __restrict__ w0, c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int h = warp; h < nH; h += kCpbThreads / 32) {
     float s = 0.f;
-    for (int k = lane; k < HID; k += 32) s = fmaf(hid[k], w2[(int64_t)h * HID + k], s);
+#pragma unroll 8
+    for (int k = lane; k < HID; k += 32) s = fmaf(hid[k], w2[(int64_t)h * HID + k], s);   // 8 loads in flight: pure latency
     s = warp_sum(s);
     if (lane == 0) table[(int64_t)t * nH + h] = 16.0f / (1.0f + __expf(-s));
   }
