@@ -1,0 +1,65 @@
+"""Host-side logic of the drop-in modules that needs no GPU: stochastic-depth mask drawing (timm semantics,
+reference models/swin_transformer_v2.py DropPath usage in the blocks :419-488) and constructor validation."""
+import pytest
+import torch
+
+from b200swin.swin_transformer_v2 import DropPath, SwinTransformerV2
+
+CFG = dict(embed_dim=32, depths=[2, 2], num_heads=[1, 2], window_size=[4, 4], pretrain_window_size=[4, 4],
+           use_shift=[True, True], out_indices=(0, 1))
+
+
+def _drop_paths(net):
+    return [m for m in net.modules() if isinstance(m, DropPath)]
+
+
+def test_drop_path_rates_follow_the_linear_schedule():
+    net = SwinTransformerV2(drop_path_rate=0.3, **CFG)
+    rates = sorted(m.drop_prob for m in _drop_paths(net))
+    assert rates == pytest.approx([0.1, 0.2, 0.3], abs=1e-6)     # linspace(0, rate, sum(depths)); p = 0 is an Identity
+
+
+def test_masks_of_a_forward_are_drawn_in_one_batch_and_consumed_in_call_order():
+    torch.manual_seed(3)
+    net = SwinTransformerV2(drop_path_rate=0.5, **CFG).train()
+    B = 64
+    mods = net._draw_drop_paths(B, torch.device("cpu"))
+    assert [m.drop_prob for m in mods] == pytest.approx([1 / 6, 1 / 3, 0.5], abs=1e-6)   # the p = 0 block draws nothing
+    x = torch.zeros(B, 3)
+    for m in mods:
+        keep = 1.0 - m.drop_prob
+        a, b = m.sample_scale(x), m.sample_scale(x)                   # two draws per block: attention and MLP branch
+        for s in (a, b):
+            assert s.shape == (B,) and s.dtype == torch.float32
+            assert all(v == 0.0 or v == pytest.approx(1.0 / keep) for v in s.unique().tolist())   # Bernoulli(keep) / keep
+        assert not torch.equal(a, b)
+        assert m._drawn == []
+        c = m.sample_scale(x)                                         # a third call falls back to its own draw
+        assert c.shape == (B,)
+    big = net._draw_drop_paths(20000, torch.device("cpu"))
+    for m in big:                                                     # E[scale] = 1
+        assert m._drawn[0].mean().item() == pytest.approx(1.0, abs=0.05)
+
+
+def test_pre_drawn_masks_are_ignored_for_another_batch_size_and_in_eval():
+    net = SwinTransformerV2(drop_path_rate=0.5, **CFG).train()
+    mods = net._draw_drop_paths(8, torch.device("cpu"))
+    m = mods[-1]
+    s = m.sample_scale(torch.zeros(5, 2))                             # stale batch size: own draw, queue untouched
+    assert s.shape == (5,) and len(m._drawn) == 2
+    net.eval()
+    assert net._draw_drop_paths(8, torch.device("cpu")) == []
+    assert m.sample_scale(torch.zeros(8, 2)) is None
+
+
+def test_no_batched_draw_under_activation_checkpointing():
+    """The recompute of a checkpointed block replays the RNG of per-call draws; pre-drawn masks would be gone by then."""
+    net = SwinTransformerV2(drop_path_rate=0.5, use_checkpoint=True, **CFG).train()
+    assert net._draw_drop_paths(8, torch.device("cpu")) == []
+
+
+def test_forward_clears_the_queues_even_when_it_raises():
+    net = SwinTransformerV2(drop_path_rate=0.5, **CFG).train()
+    with pytest.raises(Exception):                                    # CPU tensors: the CUDA ops refuse loudly
+        net(torch.rand(2, 3, 32, 32))
+    assert all(m._drawn == [] for m in _drop_paths(net))
