@@ -231,6 +231,8 @@ class WindowAttention(nn.Module):
     def _pads(self, needed):
         if not needed or self.q_bias is None:
             return None, None
+        if getattr(self, '_qpad_pre', None) is not None:       # normalised for the whole stage by BasicLayer.forward
+            return self._qpad_pre, self.v_bias
         with torch.no_grad():
             qpad = F.normalize(self.q_bias.float().view(self.num_heads, -1), dim=-1).reshape(-1)
         return qpad, self.v_bias
@@ -434,16 +436,39 @@ class BasicLayer(nn.Module):
         # the reference rebuilds a [nW,N,N] mask tensor here on every call (:874-892); the kernels derive the
         # same {0,-100} values from token coordinates, so only a handle travels to the blocks.
         attn_mask = ShiftMask(H, W, self.window_size, self.shift_size, x.device)
-        for blk in self.blocks:
-            blk.H, blk.W = H, W
-            if self.use_checkpoint and torch.is_grad_enabled():
-                x = checkpoint.checkpoint(blk, x, attn_mask, use_reentrant=False)
-            else:
-                x = blk(x, attn_mask)
+        staged = self._stage_pad_queries(H, W)
+        try:
+            for blk in self.blocks:
+                blk.H, blk.W = H, W
+                if self.use_checkpoint and torch.is_grad_enabled():
+                    x = checkpoint.checkpoint(blk, x, attn_mask, use_reentrant=False)
+                else:
+                    x = blk(x, attn_mask)
+        finally:
+            for a in staged:
+                a._qpad_pre = None
         if self.downsample is not None:
             x_down = self.downsample(x, H, W)
             return x, H, W, x_down, (H + 1) // 2, (W + 1) // 2
         return x, H, W, x, H, W
+
+    def _stage_pad_queries(self, H, W):
+        """Padded grids: the query of a padding token is normalize(q_bias) per head (the reference pads x with zeros
+        before the qkv Linear, :446-452 / :283-291).  One batched normalisation for all blocks of the stage instead
+        of three small launches per block."""
+        attns = [blk.attn for blk in self.blocks if getattr(blk.attn, 'q_bias', None) is not None]
+        if len(attns) < 2 or (self.use_checkpoint and torch.is_grad_enabled()):
+            return []
+        ws = attns[0].window_size[0]
+        if (H % ws == 0 and W % ws == 0) or any(a.window_size[0] != ws or a.q_bias.shape != attns[0].q_bias.shape
+                                                 for a in attns):
+            return []
+        with torch.no_grad():
+            q = torch.stack([a.q_bias for a in attns]).float().view(len(attns), attns[0].num_heads, -1)
+            q = F.normalize(q, dim=-1).view(len(attns), -1)
+        for a, row in zip(attns, q):
+            a._qpad_pre = row
+        return attns
 
     def _init_block_norm_weights(self):
         for blk in self.blocks:

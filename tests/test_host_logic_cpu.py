@@ -63,3 +63,24 @@ def test_forward_clears_the_queues_even_when_it_raises():
     with pytest.raises(Exception):                                    # CPU tensors: the CUDA ops refuse loudly
         net(torch.rand(2, 3, 32, 32))
     assert all(m._drawn == [] for m in _drop_paths(net))
+
+
+def test_pad_queries_are_normalised_once_per_stage():
+    """Padded grids: every block's pad-token query (normalize(q_bias) per head) comes from one batched call and equals
+    the per-block computation; nothing is staged when the grid needs no padding."""
+    torch.manual_seed(5)
+    net = SwinTransformerV2(drop_path_rate=0.0, **CFG)
+    layer = net.layers[1]
+    with torch.no_grad():
+        for blk in layer.blocks:
+            blk.attn.q_bias.normal_()
+    assert layer._stage_pad_queries(8, 8) == []                       # 8 % 4 == 0: no padding
+    staged = layer._stage_pad_queries(7, 9)
+    assert len(staged) == len(layer.blocks)
+    for a in staged:
+        batched, _ = a._pads(True)
+        a._qpad_pre = None
+        own, _ = a._pads(True)
+        assert batched.shape == own.shape == (a.dim,)
+        assert torch.allclose(batched, own, rtol=0, atol=1e-7)
+        assert a._pads(False) == (None, None)
