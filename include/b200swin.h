@@ -143,7 +143,9 @@ int b200swin_cpb_bwd(const float* coords, const float* w0, const float* b0, cons
  * 1/max(|k|,1e-12)) and dv; plus float32 accumulators that the caller zero-initialises:
  * dtable16 [(2ws-1)^2, nH], dscale [nH] (= sum dS*cos), dvpad [C] (gradient reaching v_bias through
  * pad tokens).  impl: 0 = fp32 CUDA-core kernel (any dtype, reference precision),
- * 1 = tcgen05 tensor-core kernel (bf16 storage only).  head_dim must be 32 (every Swin-V2 variant).
+ * 1 = tcgen05 tensor-core kernels (bf16 storage only; any window up to 32x32: single-tile kernels for windows
+ * 4/6/7/8/12, KV-blocked kernels otherwise), 2 = the KV-blocked tcgen05 kernels whatever the window.
+ * head_dim must be 32 (every Swin-V2 variant).
  * ------------------------------------------------------------------------------------------ */
 int b200swin_attn_fwd(const void* qkv, void* out, float* lse, const float* table16, const float* scale,
                       const float* qpad, const float* vpad, const float* mask, int nWm, int B, int H, int W,

@@ -961,6 +961,15 @@ int launch_bw(const BwArgs& a, cudaStream_t st) {
 }
 }  // namespace
 
+// D[t, h] = <dO[t, h, :], O[t, h, :]> for n = tokens * heads rows of 32 bf16 (shared by the flash backward)
+int attn_bwd_prep(const void* dout, const void* out, float* dvec, int64_t n, cudaStream_t st) {
+  int64_t blocks = (4 * n + 255) / 256, cap = (int64_t)sm_count() * 16;
+  attn_bwd_prep_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(
+      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, dvec, n);
+  BSW_LAUNCH_CHECK();
+  return B200SWIN_OK;
+}
+
 bool attn_bwd_ws_supported(int ws) { return ws == 4 || ws == 6 || ws == 7 || ws == 8 || ws == 12; }
 
 size_t attn_bwd_ws_workspace_bytes(int B, int H, int W, int nH) { return (size_t)B * H * W * nH * sizeof(float); }
@@ -981,11 +990,8 @@ int attn_bwd_ws(const void* qkv, const void* out, const void* dout, const float*
   BSW_REQUIRE(a.nwin < (1ll << 31), "attn_bwd(ws): too many windows");
   a.trace = nullptr;
   {
-    const int64_t n = (int64_t)B * H * W * nH;
-    int64_t blocks = (4 * n + 255) / 256, cap = (int64_t)sm_count() * 16;
-    attn_bwd_prep_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(
-        (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (float*)workspace, n);
-    BSW_LAUNCH_CHECK();
+    int rc = attn_bwd_prep(dout, out, (float*)workspace, (int64_t)B * H * W * nH, st);
+    if (rc) return rc;
   }
   switch (ws) {
     case 4: return launch_bw<4>(a, st);

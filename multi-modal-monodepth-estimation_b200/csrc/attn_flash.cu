@@ -1,0 +1,658 @@
+// KV-blocked ("flash") attention core on tcgen05 for ANY window size up to 32x32 (bf16 storage): the tensor-core path of
+// every window the single-tile kernels of attn_fwd_ws.cu / attn_bwd_ws.cu do not cover -- 16x16, 24x24 and the
+// reference's default 30x30 (configs/config.yaml:55; N = 256 / 576 / 900 tokens per window), and the odd sizes.
+//
+// Same math as the other attention kernels (models/swin_transformer_v2.py:295-328 with the pad / roll / partition /
+// reverse / crop of :429-463 and the shift mask of :874-892 as address math; backward per SURVEY.md appendix A).
+//
+// One kernel template, three modes.  In every mode a CTA of 128 threads owns 128 "stationary" rows of one
+// (window, head) -- one row per thread = one TMEM lane -- and streams the other side of the window through a 3-stage
+// cp.async ring in blocks of 64 tokens:
+//   FWD  stationary = queries, streamed = keys:    S = Q K^T -> online softmax -> O += P V        (P: TMEM A operand)
+//   DQ   stationary = queries, streamed = keys:    S, dP = dO V^T -> dS -> dQ += dS K            (dS: TMEM A operand)
+//                                                  + the bias-table and temperature gradients
+//   DKV  stationary = keys,    streamed = queries: S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T ->
+//                                                  dV += P^T dO, dK += dS^T Q                    (both TMEM A operands)
+// The backward is two passes (DQ, DKV) that each recompute S and dP on the tensor cores: with the transposed
+// formulation of DKV every contraction has its left operand in TMEM exactly where the thread that produced it wrote
+// it -- no shared-memory panels, no transposes, no atomics on dQ -- and every pass has the shape of the forward.
+// Per-block products (O, dQ, dK, dV of one 64-token block) come back from TMEM and are accumulated in REGISTERS, which
+// makes the online-softmax rescale a register multiply.
+//
+// A CTA needs 128 TMEM columns and ~45-110 KB of shared memory, so up to FOUR CTAs share an SM: the latency of the
+// MMA -> softmax -> MMA chain of one CTA is hidden by the other three (the single-tile kernels hide it by warp
+// specialisation inside one CTA instead).  Work units are (head, window, row tile), head-major, a contiguous range per
+// CTA, so the bias table is rebuilt and the gradient sums are flushed only when the head changes.
+#include <stdlib.h>
+#include "common.cuh"
+#include "wingeom.cuh"
+#include "tc_ptx.cuh"
+#include "../../include/b200swin.h"
+
+namespace b200swin {
+
+namespace {
+constexpr int HD = 32;
+constexpr int KB = 64;                 // streamed tokens per block
+constexpr int kThreads = 128;
+constexpr int NSTAGE = 3;
+constexpr int MODE_FWD = 0, MODE_DQ = 1, MODE_DKV = 2;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kMaskLog2 = -100.0f * 1.4426950408889634f;
+constexpr uint32_t kSw64 = 4;          // UMMA layout type SWIZZLE_64B
+constexpr uint32_t kXTile = 128 * 64;  // stationary operand tile [128][64 B]
+constexpr uint32_t kYTile = KB * 64;   // streamed operand tile   [64][64 B]
+constexpr uint32_t kStage = 2 * kYTile;
+// TMEM columns of a CTA (128 allocated): S | dP, 64 fp32 columns each.  The bf16 A operand a thread derives from its
+// row of S (dP) overwrites the first 32 columns of that row; the block product lands in the last 32.
+constexpr uint32_t S_COL = 0, DP_COL = 64, RES_OFF = 32;
+
+struct FlArgs {
+  const __nv_bfloat16* qkv;
+  const __nv_bfloat16* dout;
+  __nv_bfloat16* out;
+  __nv_bfloat16* dqkv;
+  float* lse;
+  const float* dvec;        // [B*H*W, nH]  D = <dO, O>
+  const float* inv_norm;
+  const float* table16;
+  const float* scale;
+  const float* qpad;
+  const float* vpad;
+  float* dtable16;
+  float* dscale;
+  float* dvpad;
+  WinGeom g;
+  int C, nH, N, ntiles, rpt, nkb, ntab, nmeta;
+  int64_t nwin, nunits;
+};
+
+__device__ __forceinline__ uint32_t sw64_off(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// 16 bytes of one row of an operand tile: global (a real token), a pad value (fp32 -> bf16) or zeros
+__device__ __forceinline__ void put16(unsigned char* tile, uint32_t tile_s, uint32_t off, const __nv_bfloat16* src,
+                                      const float* padv) {
+  if (src) {
+    ptx::cp_async_16(tile_s + off, src);
+  } else {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (padv) v = make_uint4(pack_bf16(padv[0], padv[1]), pack_bf16(padv[2], padv[3]), pack_bf16(padv[4], padv[5]),
+                             pack_bf16(padv[6], padv[7]));
+    *reinterpret_cast<uint4*>(tile + off) = v;
+  }
+}
+
+// F.normalize backward of one gradient row held in registers: d = (g*sc - x_hat <g*sc, x_hat>) * inv_norm
+__device__ __forceinline__ void normalize_bwd_store(const float (&gacc)[HD], const unsigned char* tile, int r, float sc,
+                                                    float invn, __nv_bfloat16* dst) {
+  float xh[HD];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint4 w = *reinterpret_cast<const uint4*>(tile + sw64_off(r, c));
+    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+      xh[c * 8 + 2 * e] = f.x;
+      xh[c * 8 + 2 * e + 1] = f.y;
+    }
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int c = 0; c < HD; ++c) dot = fmaf(gacc[c], xh[c], dot);
+  dot *= sc;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      pk[e] = pack_bf16((gacc[c * 8 + 2 * e] * sc - xh[c * 8 + 2 * e] * dot) * invn,
+                        (gacc[c * 8 + 2 * e + 1] * sc - xh[c * 8 + 2 * e + 1] * dot) * invn);
+    reinterpret_cast<uint4*>(dst)[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 4)
+attn_flash_kernel(const __grid_constant__ FlArgs a) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float red_s[4];
+
+  const WinGeom& g = a.g;
+  const int ws = g.ws, N = a.N, TW = 2 * ws - 1;
+  const uint32_t base_u32 = (ptx::smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* sm = smem_dyn + (base_u32 - ptx::smem_u32(smem_dyn));
+  unsigned char* xt = sm;                                          // two stationary tiles
+  unsigned char* ring = xt + 2 * kXTile;                           // NSTAGE x (two streamed tiles)
+  float* blk_lse = reinterpret_cast<float*>(ring + NSTAGE * kStage);   // [NSTAGE][KB] (DKV: per streamed query)
+  float* blk_d = blk_lse + NSTAGE * KB;
+  int* tok = reinterpret_cast<int*>(blk_d + NSTAGE * KB);          // [nmeta] flat token index, -1 pad, -2 beyond the window
+  int* meta = tok + a.nmeta;                                       // [nmeta] koff | region << 16 | beyond << 24
+  float* tab = reinterpret_cast<float*>(meta + a.nmeta);           // [ntab] bias table of the head, log2 units
+  float* dtab = tab + a.ntab;                                      // DQ: [4 warps][ntab] private gradient sums
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t per = a.nunits / gridDim.x, rem = a.nunits % gridDim.x;
+  const int64_t u0 = (int64_t)blockIdx.x * per + min((int64_t)blockIdx.x, rem);
+  const int nu = (int)(per + ((int64_t)blockIdx.x < rem ? 1 : 0));
+  const int nW = g.nWh * g.nWw;
+  const int C3 = 3 * a.C;
+
+  if (tid == 0) {
+    ptx::mbar_init(&bar_mma, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(&tmem_slot, 128);
+    ptx::tmem_relinquish();
+  }
+  if (MODE == MODE_DQ)
+    for (int i = tid; i < 4 * a.ntab; i += kThreads) dtab[i] = 0.f;
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  uint32_t ph = 0;                                                 // phase of bar_mma (every thread waits every phase)
+
+  const uint32_t xt_s = ptx::smem_u32(xt), ring_s = ptx::smem_u32(ring);
+  constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KB, 0, 0);        // [128 x 32] . [64 x 32]^T
+  constexpr uint32_t idesc_r = ptx::make_idesc_bf16(128, HD, 0, 1);        // [128 x 64](TMEM) . [64 x 32] (MN-major B)
+  const uint64_t desc_k = ptx::make_smem_desc(0, 16, 512, kSw64);          // K-major tile of 64 B rows
+  const uint64_t desc_mn = ptx::make_smem_desc(0, 512, 512, kSw64);        // the same bytes read MN-major
+
+  int cur_h = -1;
+  int64_t cur_win = -1;
+  float sc = 0.f, scale2 = 0.f, dsc = 0.f;
+  float* dtabw = dtab + warp * a.ntab;
+  bool need_mask = false;
+
+  auto flush_head = [&](int h) {
+    // DQ: gradient sums of head h -> global (one atomic per table entry and CTA)
+    __syncthreads();
+    for (int r = tid; r < a.ntab; r += kThreads) {
+      const float v = (dtab[r] + dtab[a.ntab + r]) + (dtab[2 * a.ntab + r] + dtab[3 * a.ntab + r]);
+      dtab[r] = dtab[a.ntab + r] = dtab[2 * a.ntab + r] = dtab[3 * a.ntab + r] = 0.f;
+      if (v != 0.f) atomicAdd(a.dtable16 + (int64_t)r * a.nH + h, v);
+    }
+    const float s = warp_sum(dsc);
+    dsc = 0.f;
+    if (lane == 0) red_s[warp] = s;
+    __syncthreads();
+    if (tid == 0) atomicAdd(a.dscale + h, (red_s[0] + red_s[1]) + (red_s[2] + red_s[3]));
+  };
+
+#pragma unroll 1
+  for (int ui = 0; ui < nu; ++ui) {
+    const int64_t u = u0 + ui;
+    const int tile = (int)(u % a.ntiles);
+    const int64_t iw = u / a.ntiles;
+    const int64_t win = iw % a.nwin;
+    const int h = (int)(iw / a.nwin);
+    const int b = (int)(win / nW);
+    const int wrem = (int)(win - (int64_t)b * nW);
+    const int wh = wrem / g.nWw, ww = wrem - wh * g.nWw;
+
+    // ---- per-head / per-window tables (every thread has finished the previous unit: its last MMA wait is behind it)
+    if (h != cur_h || win != cur_win) {
+      if (MODE == MODE_DQ && cur_h >= 0 && h != cur_h) flush_head(cur_h);
+      __syncthreads();
+      if (h != cur_h) {
+        for (int t = tid; t < a.ntab; t += kThreads) tab[t] = a.table16[(int64_t)t * a.nH + h] * kLog2e;
+        sc = a.scale[h];
+        scale2 = sc * kLog2e;
+      }
+      if (win != cur_win) {
+        need_mask = g.shift > 0 && (wh == g.nWh - 1 || ww == g.nWw - 1);
+        for (int r = tid; r < a.nmeta; r += kThreads) {
+          int t = -2, m = 1 << 24;
+          if (r < N) {
+            const int y = r / ws, x = r - y * ws;
+            const int si = wh * ws + y, sj = ww * ws + x;
+            int i = si + g.shift; if (i >= g.Hp) i -= g.Hp;
+            int j = sj + g.shift; if (j >= g.Wp) j -= g.Wp;
+            t = (i < g.H && j < g.W) ? (b * g.H + i) * g.W + j : -1;
+            const int region = g.shift > 0 ? 3 * region_1d(si, g.Hp, ws, g.shift) + region_1d(sj, g.Wp, ws, g.shift) : 0;
+            m = (y * TW + x) | (region << 16);
+          }
+          tok[r] = t;
+          meta[r] = m;
+        }
+      }
+      cur_h = h;
+      cur_win = win;
+      __syncthreads();
+    }
+
+    // ---- this thread's stationary row
+    const int r_loc = tid;
+    const int r_st = tile * a.rpt + r_loc;
+    const bool row_valid = r_loc < a.rpt && r_st < N;
+    const int m_st = meta[row_valid ? r_st : 0];
+    const int t_st = row_valid ? tok[r_st] : -2;
+    const int koff_st = m_st & 0xffff, rid_st = (m_st >> 16) & 0xff;
+    const int base_st = koff_st + (ws - 1) * (TW + 1);             // bias index = base(query) - koff(key)
+    float lse2_st = INFINITY, d_st = 0.f;                           // DQ: per-query constants
+    if (MODE == MODE_DQ && row_valid) {
+      lse2_st = a.lse[(win * a.nH + h) * N + r_st] * kLog2e;
+      if (t_st >= 0) d_st = a.dvec[(int64_t)t_st * a.nH + h];
+    }
+
+    // ---- gather: the stationary tiles and the first two streamed blocks
+    auto gather_block = [&](int kb) {
+      const int stage = kb % NSTAGE;
+      unsigned char* y0 = ring + (size_t)stage * kStage;
+      const uint32_t y0_s = ring_s + (uint32_t)stage * kStage;
+      for (int idx = tid; idx < KB * 4; idx += kThreads) {
+        const int jj = idx >> 2, c = idx & 3;
+        const int j = kb * KB + jj;
+        const int t = tok[j];
+        const uint32_t off = sw64_off(jj, c);
+        const __nv_bfloat16* base = t >= 0 ? a.qkv + (int64_t)t * C3 + h * HD + c * 8 : nullptr;
+        if (MODE == MODE_DKV) {
+          // streamed queries: q_hat (pad: normalised q_bias) | dO (pad: 0)
+          put16(y0, y0_s, off, base, (t == -1 && a.qpad) ? a.qpad + h * HD + c * 8 : nullptr);
+          put16(y0 + kYTile, y0_s + kYTile, off, t >= 0 ? a.dout + (int64_t)t * a.C + h * HD + c * 8 : nullptr, nullptr);
+        } else {
+          // streamed keys: k_hat (pad: 0) | v (pad: v_bias)
+          put16(y0, y0_s, off, t >= 0 ? base + a.C : nullptr, nullptr);
+          put16(y0 + kYTile, y0_s + kYTile, off, t >= 0 ? base + 2 * a.C : nullptr,
+                (t == -1 && a.vpad) ? a.vpad + h * HD + c * 8 : nullptr);
+        }
+      }
+      if (MODE == MODE_DKV && tid < KB) {
+        const int j = kb * KB + tid;
+        const int t = tok[j];
+        blk_lse[stage * KB + tid] = j < N ? a.lse[(win * a.nH + h) * N + j] * kLog2e : INFINITY;
+        blk_d[stage * KB + tid] = t >= 0 ? a.dvec[(int64_t)t * a.nH + h] : 0.f;
+      }
+    };
+    for (int idx = tid; idx < 128 * 4; idx += kThreads) {
+      const int rr = idx >> 2, c = idx & 3;
+      const int r = tile * a.rpt + rr;
+      const int t = (rr < a.rpt && r < N) ? tok[r] : -2;
+      const uint32_t off = sw64_off(rr, c);
+      const __nv_bfloat16* base = t >= 0 ? a.qkv + (int64_t)t * C3 + h * HD + c * 8 : nullptr;
+      if (MODE == MODE_DKV) {
+        put16(xt, xt_s, off, t >= 0 ? base + a.C : nullptr, nullptr);                                   // k_hat
+        put16(xt + kXTile, xt_s + kXTile, off, t >= 0 ? base + 2 * a.C : nullptr,
+              (t == -1 && a.vpad) ? a.vpad + h * HD + c * 8 : nullptr);                                 // v
+      } else {
+        put16(xt, xt_s, off, base, (t == -1 && a.qpad) ? a.qpad + h * HD + c * 8 : nullptr);           // q_hat
+        if (MODE == MODE_DQ)
+          put16(xt + kXTile, xt_s + kXTile, off, t >= 0 ? a.dout + (int64_t)t * a.C + h * HD + c * 8 : nullptr, nullptr);
+      }
+    }
+    gather_block(0);
+    ptx::cp_async_commit();
+    if (a.nkb > 1) gather_block(1);
+    ptx::cp_async_commit();
+
+    float acc0[HD];                     // FWD: O, DQ: dQ, DKV: dV
+    float acc1[HD];                     // DKV: dK (dead in the other modes)
+#pragma unroll
+    for (int c = 0; c < HD; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
+    float m_run = -INFINITY, l_run = 0.f;
+    // DQ: row sums for the temperature gradient sum_j dS_ij cos_ij.  In exact arithmetic sum_j dS_ij = 0; with D = <dO, O>
+    // taken from the bf16 O it is -dD_i, which would leak into the sum as -dD_i * sum_j P_ij cos_ij.  Subtracting
+    // c_i * sum_j dS_ij (c_i = sum_j P_ij cos_ij) removes that first-order error of a heavily cancelling sum.
+    float row_a = 0.f, row_b = 0.f, row_c = 0.f;
+
+#pragma unroll 1
+    for (int kb = 0; kb < a.nkb; ++kb) {
+      const int stage = kb % NSTAGE;
+      ptx::cp_async_wait<1>();                       // block kb (and the stationary tiles) have landed
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      __syncthreads();                               // (A) also: everybody has read the products of block kb - 1
+      if (tid == 0) {
+        ptx::tc_fence_after();
+        const uint32_t y0_s = ring_s + (uint32_t)stage * kStage;
+        const uint64_t ax = desc_k + (xt_s >> 4), by = desc_k + (y0_s >> 4);
+        ptx::mma_bf16_ss(tmem_base + S_COL, ax, by, idesc_s, 0u);
+        ptx::mma_bf16_ss(tmem_base + S_COL, ax + 2, by + 2, idesc_s, 1u);
+        if (MODE != MODE_FWD) {
+          const uint64_t ax1 = desc_k + ((xt_s + kXTile) >> 4), by1 = desc_k + ((y0_s + kYTile) >> 4);
+          ptx::mma_bf16_ss(tmem_base + DP_COL, ax1, by1, idesc_s, 0u);
+          ptx::mma_bf16_ss(tmem_base + DP_COL, ax1 + 2, by1 + 2, idesc_s, 1u);
+        }
+        ptx::mma_commit(&bar_mma);
+      }
+      // the stage of block kb + 2 was last read by the MMAs of block kb - 1, which every thread has waited for
+      if (kb + 2 < a.nkb) gather_block(kb + 2);
+      ptx::cp_async_commit();
+
+      const bool tail_blk = (kb + 1) * KB > N;       // keys / queries beyond the window in this block
+      const int4* meta4 = reinterpret_cast<const int4*>(meta + kb * KB);
+      ptx::mbar_wait(&bar_mma, ph);
+      ph ^= 1;
+      ptx::tc_fence_after();
+
+      float alpha = 1.f;
+      if (MODE == MODE_FWD) {
+        // ---- pass 1: logits (log2 units) written back over S, block maximum
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int cq = 0; cq < KB / 16; ++cq) {
+          uint32_t sv[16];
+          tmem_ld16(t_row + S_COL + cq * 16, sv);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const int4 mm = meta4[cq * 4 + j4];
+            const int mj[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float s2 = fmaf(__uint_as_float(sv[j4 * 4 + k]), scale2, tab[base_st - (mj[k] & 0xffff)]);
+              if (need_mask && ((mj[k] >> 16) & 0xff) != rid_st) s2 += kMaskLog2;
+              if (tail_blk && (mj[k] >> 24)) s2 = -INFINITY;
+              mx = fmaxf(mx, s2);
+              sv[j4 * 4 + k] = __float_as_uint(s2);
+            }
+          }
+          tmem_st16(t_row + S_COL + cq * 16, sv);
+        }
+        ptx::tmem_st_wait();
+        const float m_new = fmaxf(m_run, mx);
+        alpha = ex2(m_run - m_new);
+        m_run = m_new;
+        // ---- pass 2: P = exp2(s - m) as packed bf16 over the first 32 columns, row sum
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+        for (int cq = 0; cq < KB / 16; ++cq) {
+          uint32_t sv[16], pk[8];
+          tmem_ld16(t_row + S_COL + cq * 16, sv);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float p0 = ex2(__uint_as_float(sv[2 * e]) - m_new), p1 = ex2(__uint_as_float(sv[2 * e + 1]) - m_new);
+            l0 += p0;
+            l1 += p1;
+            pk[e] = pack_bf16(p0, p1);
+          }
+          tmem_st8(t_row + S_COL + cq * 8, pk);      // columns [8 cq, 8 cq + 8) < [16 (cq + 1), ...): already consumed
+        }
+        ptx::tmem_st_wait();
+        l_run = fmaf(l_run, alpha, l0 + l1);
+      } else {
+        // ---- P = exp2(s - lse), dS = P (dP - D), eight streamed tokens per step
+        const float4* lse4 = reinterpret_cast<const float4*>(blk_lse + stage * KB);
+        const float4* d4 = reinterpret_cast<const float4*>(blk_d + stage * KB);
+#pragma unroll 1
+        for (int cc = 0; cc < KB / 8; ++cc) {
+          uint32_t sv[8], dv[8];
+          tmem_ld8(t_row + S_COL + cc * 8, sv);
+          tmem_ld8(t_row + DP_COL + cc * 8, dv);
+          int mj[8];
+          {
+            const int4 m0 = meta4[cc * 2], m1 = meta4[cc * 2 + 1];
+            mj[0] = m0.x; mj[1] = m0.y; mj[2] = m0.z; mj[3] = m0.w; mj[4] = m1.x; mj[5] = m1.y; mj[6] = m1.z; mj[7] = m1.w;
+          }
+          float lsev[8], dvv[8];
+          if (MODE == MODE_DKV) {
+            const float4 l0 = lse4[cc * 2], l1 = lse4[cc * 2 + 1], e0 = d4[cc * 2], e1 = d4[cc * 2 + 1];
+            lsev[0] = l0.x; lsev[1] = l0.y; lsev[2] = l0.z; lsev[3] = l0.w; lsev[4] = l1.x; lsev[5] = l1.y; lsev[6] = l1.z; lsev[7] = l1.w;
+            dvv[0] = e0.x; dvv[1] = e0.y; dvv[2] = e0.z; dvv[3] = e0.w; dvv[4] = e1.x; dvv[5] = e1.y; dvv[6] = e1.z; dvv[7] = e1.w;
+          }
+          ptx::tmem_ld_wait();
+          uint32_t pkd[4], pkp[4];
+#pragma unroll
+          for (int e2 = 0; e2 < 4; ++e2) {
+            float pl[2], dl[2];
+#pragma unroll
+            for (int e1 = 0; e1 < 2; ++e1) {
+              const int e = 2 * e2 + e1;
+              // DQ: this thread is the query, the streamed token the key; DKV: the other way round
+              const int idx = MODE == MODE_DQ ? base_st - (mj[e] & 0xffff) : (mj[e] & 0xffff) + (ws - 1) * (TW + 1) - koff_st;
+              const float cosv = __uint_as_float(sv[e]);
+              float s2 = fmaf(cosv, scale2, tab[idx]);
+              if (need_mask && ((mj[e] >> 16) & 0xff) != rid_st) s2 += kMaskLog2;
+              float p = ex2(s2 - (MODE == MODE_DQ ? lse2_st : lsev[e]));
+              if (MODE == MODE_DQ && tail_blk && (mj[e] >> 24)) p = 0.f;        // key beyond the window
+              const float dsv = p * (__uint_as_float(dv[e]) - (MODE == MODE_DQ ? d_st : dvv[e]));
+              pl[e1] = p;
+              dl[e1] = dsv;
+              if (MODE == MODE_DQ) {
+                row_a = fmaf(dsv, cosv, row_a);
+                row_b += dsv;
+                row_c = fmaf(p, cosv, row_c);
+                // gradient of the bias table: warp-private sums.  The 32 lanes of a step hit 32 distinct entries (one
+                // key, 32 different queries); consecutive steps of different lanes alias, hence the warp barrier.
+                dtabw[idx] += dsv;
+                __syncwarp();
+              }
+            }
+            pkd[e2] = pack_bf16(dl[0], dl[1]);
+            pkp[e2] = pack_bf16(pl[0], pl[1]);
+          }
+          tmem_st4(t_row + DP_COL + cc * 4, pkd);
+          if (MODE == MODE_DKV) tmem_st4(t_row + S_COL + cc * 4, pkp);
+        }
+        ptx::tmem_st_wait();
+      }
+      ptx::tc_fence_before();
+      __syncthreads();                               // (B) every row's A operand is in TMEM
+      if (tid == 0) {
+        ptx::tc_fence_after();
+        const uint32_t y0_s = ring_s + (uint32_t)stage * kStage;
+        if (MODE == MODE_FWD) {
+          const uint64_t bv = desc_mn + ((y0_s + kYTile) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < KB / 16; ++ks)
+            ptx::mma_bf16_ts(tmem_base + S_COL + RES_OFF, tmem_base + S_COL + ks * 8, bv + ks * 64, idesc_r, ks);
+        } else if (MODE == MODE_DQ) {
+          const uint64_t bk = desc_mn + (y0_s >> 4);
+#pragma unroll
+          for (int ks = 0; ks < KB / 16; ++ks)
+            ptx::mma_bf16_ts(tmem_base + DP_COL + RES_OFF, tmem_base + DP_COL + ks * 8, bk + ks * 64, idesc_r, ks);
+        } else {
+          const uint64_t bq = desc_mn + (y0_s >> 4), bg = desc_mn + ((y0_s + kYTile) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < KB / 16; ++ks)
+            ptx::mma_bf16_ts(tmem_base + S_COL + RES_OFF, tmem_base + S_COL + ks * 8, bg + ks * 64, idesc_r, ks);
+#pragma unroll
+          for (int ks = 0; ks < KB / 16; ++ks)
+            ptx::mma_bf16_ts(tmem_base + DP_COL + RES_OFF, tmem_base + DP_COL + ks * 8, bq + ks * 64, idesc_r, ks);
+        }
+        ptx::mma_commit(&bar_mma);
+      }
+      ptx::mbar_wait(&bar_mma, ph);
+      ph ^= 1;
+      ptx::tc_fence_after();
+      {
+        uint32_t o[HD];
+        tmem_ld16(t_row + (MODE == MODE_DQ ? DP_COL : S_COL) + RES_OFF, o);
+        tmem_ld16(t_row + (MODE == MODE_DQ ? DP_COL : S_COL) + RES_OFF + 16, o + 16);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < HD; ++c)
+          acc0[c] = MODE == MODE_FWD ? fmaf(acc0[c], alpha, __uint_as_float(o[c])) : acc0[c] + __uint_as_float(o[c]);
+        if (MODE == MODE_DKV) {
+          tmem_ld16(t_row + DP_COL + RES_OFF, o);
+          tmem_ld16(t_row + DP_COL + RES_OFF + 16, o + 16);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < HD; ++c) acc1[c] += __uint_as_float(o[c]);
+        }
+      }
+    }
+    ptx::cp_async_wait<0>();
+
+    // ---- epilogue of the unit (the stationary tiles stay valid until the next unit's gather, behind a barrier)
+    if (MODE == MODE_FWD) {
+      if (row_valid) {
+        a.lse[(win * a.nH + h) * N + r_st] = (m_run + log2f(l_run)) * kLn2;
+        if (t_st >= 0) {
+          const float inv = 1.0f / l_run;
+          uint4* dst = reinterpret_cast<uint4*>(a.out + (int64_t)t_st * a.C + h * HD);
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            dst[c] = make_uint4(pack_bf16(acc0[c * 8 + 0] * inv, acc0[c * 8 + 1] * inv),
+                                pack_bf16(acc0[c * 8 + 2] * inv, acc0[c * 8 + 3] * inv),
+                                pack_bf16(acc0[c * 8 + 4] * inv, acc0[c * 8 + 5] * inv),
+                                pack_bf16(acc0[c * 8 + 6] * inv, acc0[c * 8 + 7] * inv));
+        }
+      }
+    } else if (MODE == MODE_DQ) {
+      dsc += row_a - row_c * row_b;
+      if (t_st >= 0)
+        normalize_bwd_store(acc0, xt, r_loc, sc, a.inv_norm[((int64_t)t_st * 2 + 0) * a.nH + h],
+                            a.dqkv + (int64_t)t_st * C3 + h * HD);
+    } else {
+      if (t_st >= 0) {
+        uint4* dst = reinterpret_cast<uint4*>(a.dqkv + (int64_t)t_st * C3 + 2 * a.C + h * HD);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          dst[c] = make_uint4(pack_bf16(acc0[c * 8 + 0], acc0[c * 8 + 1]), pack_bf16(acc0[c * 8 + 2], acc0[c * 8 + 3]),
+                              pack_bf16(acc0[c * 8 + 4], acc0[c * 8 + 5]), pack_bf16(acc0[c * 8 + 6], acc0[c * 8 + 7]));
+        normalize_bwd_store(acc1, xt, r_loc, sc, a.inv_norm[((int64_t)t_st * 2 + 1) * a.nH + h],
+                            a.dqkv + (int64_t)t_st * C3 + a.C + h * HD);
+      }
+      // pad keys carry v = v_bias: their dV rows are gradient of v_bias (one atomic per column and warp)
+      if (a.dvpad && (g.Hp != g.H || g.Wp != g.W)) {
+        const bool is_pad = t_st == -1;
+        if (__any_sync(0xffffffffu, is_pad)) {
+#pragma unroll
+          for (int c = 0; c < HD; ++c) {
+            const float v = warp_sum(is_pad ? acc0[c] : 0.f);
+            if (lane == 0 && v != 0.f) atomicAdd(a.dvpad + h * HD + c, v);
+          }
+        }
+      }
+    }
+    __syncthreads();                                 // the stationary tiles / tables may be overwritten now
+  }
+  if (MODE == MODE_DQ && cur_h >= 0) flush_head(cur_h);
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 128);
+  }
+}
+
+size_t flash_smem(int mode, int ntab, int nmeta) {
+  size_t s = 1024 + 2 * (size_t)kXTile + (size_t)NSTAGE * kStage + 2 * (size_t)NSTAGE * KB * 4 + 2 * (size_t)nmeta * 4 +
+             (size_t)ntab * 4 + (mode == MODE_DQ ? 4 * (size_t)ntab * 4 : 0) + 16;
+  // at most four CTAs per SM (128 TMEM columns each): never let a fifth fit by shared memory
+  const size_t floor_bytes = 46 * 1024;
+  return s < floor_bytes ? floor_bytes : s;
+}
+
+template <int MODE>
+int launch_flash(FlArgs a, cudaStream_t st) {
+  const size_t smem = flash_smem(MODE, a.ntab, a.nmeta);
+  BSW_REQUIRE(smem <= 227 * 1024, "attn(flash): window %dx%d needs %zu bytes of shared memory", a.g.ws, a.g.ws, smem);
+  BSW_CUDA(cudaFuncSetAttribute(attn_flash_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  BSW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attn_flash_kernel<MODE>, kThreads, smem));
+  if (occ < 1) occ = 1;
+  if (occ > 4) occ = 4;
+  int64_t grid = (int64_t)sm_count() * occ;
+  if (grid > a.nunits) grid = a.nunits;
+  attn_flash_kernel<MODE><<<(unsigned)grid, kThreads, smem, st>>>(a);
+  BSW_LAUNCH_CHECK();
+  return B200SWIN_OK;
+}
+
+int fill_args(FlArgs* a, int B, int H, int W, int C, int nH, int ws, int shift) {
+  BSW_REQUIRE(B > 0 && H > 0 && W > 0 && nH > 0 && ws >= 1 && ws <= 32, "attn(flash): bad dimension");
+  BSW_REQUIRE(C == nH * HD, "attn(flash): head_dim must be 32 (C=%d, nH=%d)", C, nH);
+  BSW_REQUIRE(shift >= 0 && shift < ws, "attn(flash): bad shift");
+  BSW_REQUIRE(C % 8 == 0, "attn(flash): C must be a multiple of 8");
+  BSW_REQUIRE((int64_t)B * H * W < (1ll << 29), "attn(flash): too many tokens");
+  make_geom(&a->g, B, H, W, ws, shift);
+  a->C = C; a->nH = nH;
+  a->N = ws * ws;
+  a->ntiles = (a->N + 127) / 128;
+  a->rpt = (a->N + a->ntiles - 1) / a->ntiles;
+  a->nkb = (a->N + KB - 1) / KB;
+  a->ntab = (2 * ws - 1) * (2 * ws - 1);
+  a->nmeta = a->nkb * KB;
+  a->nwin = (int64_t)B * a->g.nWh * a->g.nWw;
+  a->nunits = a->nwin * nH * a->ntiles;
+  BSW_REQUIRE(a->nwin < (1ll << 31), "attn(flash): too many windows");
+  return B200SWIN_OK;
+}
+}  // namespace
+
+// D = <dO, O> per (token, head) (attn_bwd_ws.cu)
+int attn_bwd_prep(const void* dout, const void* out, float* dvec, int64_t n, cudaStream_t st);
+
+int attn_fwd_flash(const void* qkv, void* out, float* lse, const float* table16, const float* scale, const float* qpad,
+                   const float* vpad, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st) {
+  FlArgs a = {};
+  int rc = fill_args(&a, B, H, W, C, nH, ws, shift);
+  if (rc) return rc;
+  a.qkv = (const __nv_bfloat16*)qkv; a.out = (__nv_bfloat16*)out; a.lse = lse;
+  a.table16 = table16; a.scale = scale; a.qpad = qpad; a.vpad = vpad;
+  return launch_flash<MODE_FWD>(a, st);
+}
+
+size_t attn_bwd_flash_workspace_bytes(int B, int H, int W, int nH) { return (size_t)B * H * W * nH * sizeof(float); }
+
+int attn_bwd_flash(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
+                   const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
+                   float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH,
+                   int ws, int shift, cudaStream_t st) {
+  BSW_REQUIRE(workspace, "attn_bwd(flash): workspace for D = <dO, O> missing");
+  FlArgs a = {};
+  int rc = fill_args(&a, B, H, W, C, nH, ws, shift);
+  if (rc) return rc;
+  a.qkv = (const __nv_bfloat16*)qkv; a.dout = (const __nv_bfloat16*)dout; a.lse = const_cast<float*>(lse);
+  a.dvec = (const float*)workspace; a.inv_norm = inv_norm; a.table16 = table16; a.scale = scale; a.qpad = qpad;
+  a.vpad = vpad; a.dqkv = (__nv_bfloat16*)dqkv; a.dtable16 = dtable16; a.dscale = dscale; a.dvpad = dvpad;
+  rc = attn_bwd_prep(dout, out, (float*)workspace, (int64_t)B * H * W * nH, st);
+  if (rc) return rc;
+  rc = launch_flash<MODE_DQ>(a, st);
+  if (rc) return rc;
+  return launch_flash<MODE_DKV>(a, st);
+}
+
+}  // namespace b200swin

@@ -580,15 +580,14 @@ def cpb_table(coords, w0, b0, w2):
 
 
 # ------------------------------------------------------------------------------ attention core
-# "auto": tcgen05 kernels whenever they apply (bf16 storage, windows <= 16x16, on-the-fly mask), else the fp32
-# CUDA-core kernels.  "simt" / "tc" force one implementation (tests, A/B timing).  Backward has its own switch.
+# "auto": tcgen05 kernels whenever they apply (bf16 storage, on-the-fly mask; any window up to 32x32: the single-tile
+# kernels for windows 4/6/7/8/12, the KV-blocked kernels otherwise), else the fp32 CUDA-core kernels (fp32 tensors = the
+# reference-precision mode, or an explicit mask tensor).  "simt" / "tc" force one implementation (tests, A/B timing).
 ATTN_IMPL = {"mode": "auto", "bwd_mode": "auto"}
 
 
 def _tc_applicable(dtype, ws, mask, backward=False):
-    npad = (ws * ws + 15) // 16 * 16
-    # TMEM budget: forward holds S + O (N <= 256); backward holds S + dP + dQ/dK/dV (N <= 176, i.e. ws <= 13)
-    return dtype == torch.bfloat16 and mask is None and npad <= (176 if backward else 256)
+    return dtype == torch.bfloat16 and mask is None and 1 <= ws <= 32
 
 
 def _pick_impl(dtype, ws, mask, backward=False):
@@ -597,6 +596,8 @@ def _pick_impl(dtype, ws, mask, backward=False):
         return 0
     if mode == "tc":
         return 1
+    if mode == "flash":
+        return 2
     return 1 if _tc_applicable(dtype, ws, mask, backward) else 0
 
 

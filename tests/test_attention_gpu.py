@@ -194,7 +194,15 @@ def test_swin_small_vs_reference_golden():
     # the Swin-L / Swin-T head counts of configs 1 and 4, through whichever implementation "auto" picks
     (1, 24, 24, 96, 3, 24, 12, torch.bfloat16, "auto"), (1, 32, 32, 192, 6, 16, 8, torch.bfloat16, "auto"),
     (1, 24, 24, 768, 24, 12, 6, torch.bfloat16, "auto"), (1, 16, 16, 1536, 48, 8, 0, torch.bfloat16, "auto"),
-    (1, 22, 38, 384, 12, 24, 12, torch.float32, "auto")])
+    (1, 22, 38, 384, 12, 24, 12, torch.float32, "auto"),
+    # KV-blocked tcgen05 kernels (attn_flash.cu): every window the single-tile kernels do not cover -- 1x1 and 9x9
+    # (ADVICE r1), 16 / 24 / 30 / 32 (configs 2-alt, 4 and the reference default), shifted, padded, ragged last blocks
+    (2, 3, 4, 64, 2, 1, 0, torch.bfloat16, "tc"), (1, 20, 13, 64, 2, 9, 4, torch.bfloat16, "tc"),
+    (1, 10, 10, 32, 1, 5, 2, torch.bfloat16, "tc"), (1, 26, 30, 64, 2, 13, 6, torch.bfloat16, "tc"),
+    (2, 32, 32, 64, 2, 16, 0, torch.bfloat16, "tc"), (1, 40, 24, 96, 3, 16, 8, torch.bfloat16, "tc"),
+    (1, 30, 50, 64, 2, 24, 12, torch.bfloat16, "tc"), (1, 48, 48, 128, 4, 24, 0, torch.bfloat16, "tc"),
+    (1, 40, 40, 64, 2, 30, 15, torch.bfloat16, "tc"), (2, 30, 30, 32, 1, 30, 0, torch.bfloat16, "tc"),
+    (1, 40, 70, 32, 1, 32, 16, torch.bfloat16, "tc")])
 def test_attention_core_vs_oracle(B, H, W, C, nH, ws, shift, dtype, impl):
     """The core kernel alone (natural-order qkv in, natural-order out), forward and every gradient, against the
     oracle's gather -> dense attention -> scatter in float64."""

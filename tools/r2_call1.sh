@@ -1,0 +1,18 @@
+# round 2, call 1: the KV-blocked attention kernels -- parity, then A/B timings against the single-tile and CUDA-core kernels
+cd $GRAFT_REPO_ROOT
+timeout 1200 python -m pytest tests/test_attention_gpu.py -q -m gpu -k "core_vs_oracle" -x 2>&1 | tail -40 > gpurun_out/r2c1_tests.log
+tail -5 gpurun_out/r2c1_tests.log
+{
+for impl in 1 2; do
+  timeout 120 python tools/prof_attn_raw.py --impl $impl --B 48 --H 30 --C 512 --ws 12
+  timeout 120 python tools/prof_attn_raw.py --impl $impl --B 48 --H 120 --C 128 --ws 12 --shift 6
+  timeout 120 python tools/prof_attn_raw.py --impl $impl --B 48 --H 15 --C 1024 --ws 6
+done
+for impl in 0 1; do
+  timeout 300 python tools/prof_attn_raw.py --impl $impl --B 48 --H 120 --C 128 --ws 24 --shift 12 --iters 3
+  timeout 300 python tools/prof_attn_raw.py --impl $impl --B 48 --H 30 --C 512 --ws 24 --iters 3
+  timeout 300 python tools/prof_attn_raw.py --impl $impl --B 48 --H 120 --C 128 --ws 30 --shift 15 --iters 3
+  timeout 300 python tools/prof_attn_raw.py --impl $impl --B 48 --H 60 --C 256 --ws 16 --shift 8 --iters 3
+done
+} > gpurun_out/r2c1_timing.log 2>&1
+cat gpurun_out/r2c1_timing.log
