@@ -146,13 +146,18 @@ int b200swin_cpb_bwd(const float* coords, const float* w0, const float* b0, cons
  * 1 = tcgen05 tensor-core kernels (bf16 storage only; any window up to 32x32: single-tile kernels for windows
  * 4/6/7/8/12, KV-blocked kernels otherwise), 2 = the KV-blocked tcgen05 kernels whatever the window.
  * head_dim must be 32 (every Swin-V2 variant).
+ * out_lo (nullable; tensor-core implementations only): bf16 tensor of out's shape that receives the rounding residual
+ * O - bf16(O).  Given back to the backward it makes D = <dO, O> accurate to ~2^-17; the bias-table and temperature
+ * gradients are sums of dS = P (dP - D) that cancel row by row, and the 2^-9 rounding of O alone would put an error
+ * of the size of the signal into them.
  * ------------------------------------------------------------------------------------------ */
-int b200swin_attn_fwd(const void* qkv, void* out, float* lse, const float* table16, const float* scale,
+int b200swin_attn_fwd(const void* qkv, void* out, void* out_lo, float* lse, const float* table16, const float* scale,
                       const float* qpad, const float* vpad, const float* mask, int nWm, int B, int H, int W,
                       int C, int nH, int ws, int shift, int dtype, int impl, void* stream);
 /* bytes of caller-owned scratch the backward needs for this shape / implementation (0: none) */
 size_t b200swin_attn_bwd_workspace_bytes(int B, int H, int W, int nH, int ws, int dtype, int impl);
-int b200swin_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
+int b200swin_attn_bwd(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse,
+                      const float* inv_norm,
                       const float* table16, const float* scale, const float* qpad, const float* vpad,
                       const float* mask, int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, int B,
                       int H, int W, int C, int nH, int ws, int shift, int dtype, int impl, void* workspace,
@@ -190,6 +195,23 @@ int b200swin_split_bf16(const float* src, void* hi, void* lo, int64_t n, void* s
 size_t b200swin_colsum_workspace_bytes(int64_t M, int ncols);
 int b200swin_colsum(const void* x, int dtype, int64_t M, int64_t ld, int64_t col0, int ncols, const float* extra,
                     float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-tensor AdamW with per-tensor learning-rate scale and weight decay.  Replaces the optimizer step the
+ * reference builds with SwinLayerDecayOptimizerConstructor (models/optimizer.py:36-104: ~60 parameter groups, layer
+ * decay x {decay, no_decay}) and runs with torch.optim.AdamW after rewriting every group's lr (train.py:195-203).
+ * params / grads / exp_avg / exp_avg_sq are flat float32 buffers of nchunks * b200swin_adamw_chunk() elements in which
+ * every tensor occupies a whole number of chunks; chunk_tensor[c] is the tensor index of chunk c (-1: padding, skipped);
+ * lr_scale[t] and weight_decay[t] are per tensor.  lr and step point to DEVICE scalars (float32; step = 1, 2, ... is the
+ * number of this update), so a captured launch follows a schedule.  grads are multiplied by grad_scale first (1/world
+ * size after a SUM all-reduce).  params_bf16 (nullable) receives the bf16 copy of the updated parameters that the GEMMs
+ * read.  Math = torch.optim.AdamW (decoupled decay, bias correction), float32.
+ * ------------------------------------------------------------------------------------------ */
+int b200swin_adamw_chunk(void);
+int b200swin_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* params_bf16,
+                        const int* chunk_tensor, const float* lr_scale, const float* weight_decay, const float* lr,
+                        const float* step, double beta1, double beta2, float eps, float grad_scale, int64_t nchunks,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,15 +40,17 @@ SIGNATURES = {
     "b200swin_ln_fwd": (I, [P, P, P, P, P, L, P, P, P, L, I, F, I, P]),
     "b200swin_ln_bwd_workspace_bytes": (Z, [L, I]),
     "b200swin_ln_bwd": (I, [P, P, P, P, P, P, L, P, P, P, P, L, I, I, P, Z, P]),
-    "b200swin_attn_fwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P]),
+    "b200swin_attn_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P]),
     "b200swin_attn_bwd_workspace_bytes": (Z, [I, I, I, I, I, I, I]),
-    "b200swin_attn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, I, I, P, Z, P]),
+    "b200swin_attn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, I, I, P, Z, P]),
     "b200swin_gemm_splits": (I, [L, L, L]),
     "b200swin_gemm_workspace_bytes": (Z, [L, L, I]),
     "b200swin_gemm_bf16": (I, [P, P, I, P, P, I, L, L, L, I, P, P, P, P, P, I, P, I, I, P, Z, P]),
     "b200swin_split_bf16": (I, [P, P, P, L, P]),
     "b200swin_colsum_workspace_bytes": (Z, [L, I]),
     "b200swin_colsum": (I, [P, I, L, L, L, I, P, P, P, Z, P]),
+    "b200swin_adamw_chunk": (I, []),
+    "b200swin_adamw_step": (I, [P, P, P, P, P, P, P, P, P, P, ctypes.c_double, ctypes.c_double, F, F, L, P]),
 }
 
 
@@ -83,12 +85,13 @@ KERNELS_PER_CALL = {
     "b200swin_silog_fwd": 2, "b200swin_silog_bwd": 1, "b200swin_window_gather": 1, "b200swin_window_scatter": 1,
     "b200swin_shift_mask": 1, "b200swin_patch_merge": 1, "b200swin_patchify": 1, "b200swin_cpb_fwd": 1, "b200swin_cpb_bwd": 1, "b200swin_ln_fwd": 1, "b200swin_ln_bwd": 2, "b200swin_attn_fwd": 1,
     "b200swin_attn_bwd": 2, "b200swin_gemm_bf16": 1, "b200swin_split_bf16": 1, "b200swin_colsum": 2,
+    "b200swin_adamw_step": 1,
 }
 
 COUNTERS = {"launches": 0, "calls": {}}
-# optional live timing of one entry point with CUDA events on the launching stream (bench.py roofline):
-# TIMING = {"name": <symbol>, "events": [(start, end, work)], "work": callable(args) -> float}
-TIMING = {"name": None, "events": [], "work": None}
+# optional live timing of the entry points with CUDA events on the launching stream (bench.py rooflines):
+# TIMING = {"name": <symbol> | "*" | None, "events": [(start_event, end_event, symbol, args)]}
+TIMING = {"name": None, "events": []}
 
 
 def _wrap(name, fn):
@@ -98,6 +101,8 @@ def _wrap(name, fn):
         n = per_call
         if name == "b200swin_gemm_bf16" and args[18] > 1:
             n += 1
+        if name == "b200swin_attn_bwd" and args[24] in (1, 2) and (args[24] == 2 or args[21] not in (4, 6, 7, 8, 12)):
+            n += 1                                     # KV-blocked backward: prep + dQ pass + dK/dV pass
         COUNTERS["launches"] += n
         COUNTERS["calls"][name] = COUNTERS["calls"].get(name, 0) + 1
         if TIMING["name"] == name or TIMING["name"] == "*":
@@ -107,13 +112,7 @@ def _wrap(name, fn):
             e0.record(st)
             rc = fn(*args)
             e1.record(st)
-            tag = name
-            if name == "b200swin_gemm_bf16" and TIMING.get("detail"):
-                # (a_mn, b_mn, M, N, K, epilogue, splits)
-                tag = "gemm a_mn=%d b_mn=%d M=%d N=%d K=%d epi=%d splits=%d" % (args[2], args[5], args[6], args[7], args[8],
-                                                                              args[9], args[18])
-            TIMING["events"].append((e0, e1, TIMING["work"](args) if (TIMING["work"] and name == "b200swin_gemm_bf16")
-                                     else 0.0, tag))
+            TIMING["events"].append((e0, e1, name, tuple(a for a in args)))
             return rc
         return fn(*args)
 

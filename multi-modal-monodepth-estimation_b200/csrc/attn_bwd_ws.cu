@@ -897,10 +897,12 @@ attn_bwd_ws_kernel(const __grid_constant__ BwArgs a) {
 }
 
 // D[t, h] = <dO[t, h, :], O[t, h, :]>: four threads per (token, head), 16 bytes of each tensor per thread (a warp
-// instruction reads 512 contiguous bytes), two shuffles, 4 B out.
+// instruction reads 512 contiguous bytes), two shuffles, 4 B out.  out_lo (optional) is the bf16 residual of O that the
+// forward saved: with it D matches sum_j P_ij dP_ij to ~2^-17 instead of 2^-9, which is what keeps the heavily
+// cancelling sums of the backward (bias-table and temperature gradients: sum_j dS_ij = 0 per row) at the bf16 bar.
 __global__ void __launch_bounds__(256)
-attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out, float* __restrict__ dvec,
-                     int64_t n /* tokens * heads */) {
+attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                     const __nv_bfloat16* __restrict__ out_lo, float* __restrict__ dvec, int64_t n /* tokens * heads */) {
   const int64_t n4 = 4 * n, stride = (int64_t)gridDim.x * blockDim.x;
   // warp-uniform trip count: the shuffles below are executed by whole warps
   for (int64_t w0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); w0 < n4; w0 += stride) {
@@ -908,14 +910,20 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16
     float d = 0.f;
     if (i < n4) {
       const uint4 gv = reinterpret_cast<const uint4*>(dout)[i], ov = reinterpret_cast<const uint4*>(out)[i];
-      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
+      const uint4 lv = out_lo ? reinterpret_cast<const uint4*>(out_lo)[i] : make_uint4(0, 0, 0, 0);
+      const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w}, lw[4] = {lv.x, lv.y, lv.z, lv.w};
+      float dl = 0.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
         const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[e]));
+        const float2 lf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&lw[e]));
         d = fmaf(gf.x, of.x, d);
         d = fmaf(gf.y, of.y, d);
+        dl = fmaf(gf.x, lf.x, dl);
+        dl = fmaf(gf.y, lf.y, dl);
       }
+      d += dl;
     }
     d += __shfl_xor_sync(0xffffffffu, d, 1);
     d += __shfl_xor_sync(0xffffffffu, d, 2);
@@ -962,10 +970,10 @@ int launch_bw(const BwArgs& a, cudaStream_t st) {
 }  // namespace
 
 // D[t, h] = <dO[t, h, :], O[t, h, :]> for n = tokens * heads rows of 32 bf16 (shared by the flash backward)
-int attn_bwd_prep(const void* dout, const void* out, float* dvec, int64_t n, cudaStream_t st) {
+int attn_bwd_prep(const void* dout, const void* out, const void* out_lo, float* dvec, int64_t n, cudaStream_t st) {
   int64_t blocks = (4 * n + 255) / 256, cap = (int64_t)sm_count() * 16;
   attn_bwd_prep_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(
-      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, dvec, n);
+      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)out, (const __nv_bfloat16*)out_lo, dvec, n);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
 }
@@ -974,7 +982,7 @@ bool attn_bwd_ws_supported(int ws) { return ws == 4 || ws == 6 || ws == 7 || ws 
 
 size_t attn_bwd_ws_workspace_bytes(int B, int H, int W, int nH) { return (size_t)B * H * W * nH * sizeof(float); }
 
-int attn_bwd_ws(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
+int attn_bwd_ws(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
                 const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
                 float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH, int ws,
                 int shift, cudaStream_t st) {
@@ -990,7 +998,7 @@ int attn_bwd_ws(const void* qkv, const void* out, const void* dout, const float*
   BSW_REQUIRE(a.nwin < (1ll << 31), "attn_bwd(ws): too many windows");
   a.trace = nullptr;
   {
-    int rc = attn_bwd_prep(dout, out, (float*)workspace, (int64_t)B * H * W * nH, st);
+    int rc = attn_bwd_prep(dout, out, out_lo, (float*)workspace, (int64_t)B * H * W * nH, st);
     if (rc) return rc;
   }
   switch (ws) {

@@ -24,6 +24,7 @@
 // specialisation inside one CTA instead).  Work units are (head, window, row tile), head-major, a contiguous range per
 // CTA, so the bias table is rebuilt and the gradient sums are flushed only when the head changes.
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 #include "wingeom.cuh"
 #include "tc_ptx.cuh"
@@ -52,6 +53,7 @@ struct FlArgs {
   const __nv_bfloat16* qkv;
   const __nv_bfloat16* dout;
   __nv_bfloat16* out;
+  __nv_bfloat16* out_lo;    // optional bf16 residual O - bf16(O) (see attn_fwd_ws.cu)
   __nv_bfloat16* dqkv;
   float* lse;
   const float* dvec;        // [B*H*W, nH]  D = <dO, O>
@@ -172,8 +174,9 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
   float* blk_lse = reinterpret_cast<float*>(ring + NSTAGE * kStage);   // [NSTAGE][KB] (DKV: per streamed query)
   float* blk_d = blk_lse + NSTAGE * KB;
   int* tok = reinterpret_cast<int*>(blk_d + NSTAGE * KB);          // [nmeta] flat token index, -1 pad, -2 beyond the window
-  int* meta = tok + a.nmeta;                                       // [nmeta] koff | region << 16 | beyond << 24
-  float* tab = reinterpret_cast<float*>(meta + a.nmeta);           // [ntab] bias table of the head, log2 units
+  int* kof = tok + a.nmeta;                                        // [nmeta] byte offset 4 (y TW + x) into the bias table
+  int* rid = kof + a.nmeta;                                        // [nmeta] shift-mask region id | beyond the window << 8
+  float* tab = reinterpret_cast<float*>(rid + a.nmeta);            // [ntab] bias table of the head, log2 units
   float* dtab = tab + a.ntab;                                      // DQ: [4 warps][ntab] private gradient sums
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -250,7 +253,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
       if (win != cur_win) {
         need_mask = g.shift > 0 && (wh == g.nWh - 1 || ww == g.nWw - 1);
         for (int r = tid; r < a.nmeta; r += kThreads) {
-          int t = -2, m = 1 << 24;
+          int t = -2, ko = 0, rg = 1 << 8;
           if (r < N) {
             const int y = r / ws, x = r - y * ws;
             const int si = wh * ws + y, sj = ww * ws + x;
@@ -258,10 +261,12 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
             int j = sj + g.shift; if (j >= g.Wp) j -= g.Wp;
             t = (i < g.H && j < g.W) ? (b * g.H + i) * g.W + j : -1;
             const int region = g.shift > 0 ? 3 * region_1d(si, g.Hp, ws, g.shift) + region_1d(sj, g.Wp, ws, g.shift) : 0;
-            m = (y * TW + x) | (region << 16);
+            ko = 4 * (y * TW + x);
+            rg = region;
           }
           tok[r] = t;
-          meta[r] = m;
+          kof[r] = ko;
+          rid[r] = rg;
         }
       }
       cur_h = h;
@@ -273,10 +278,13 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
     const int r_loc = tid;
     const int r_st = tile * a.rpt + r_loc;
     const bool row_valid = r_loc < a.rpt && r_st < N;
-    const int m_st = meta[row_valid ? r_st : 0];
     const int t_st = row_valid ? tok[r_st] : -2;
-    const int koff_st = m_st & 0xffff, rid_st = (m_st >> 16) & 0xff;
-    const int base_st = koff_st + (ws - 1) * (TW + 1);             // bias index = base(query) - koff(key)
+    const int kof_st = kof[row_valid ? r_st : 0], rid_st = rid[row_valid ? r_st : 0] & 0xff;
+    // bias index = koff(query) + (ws-1)(TW+1) - koff(key).  FWD / DQ: this row is the query, `tabq - kof[key]` is the
+    // entry; DKV: this row is the key, `tabq + kof[query]`.
+    const int off_st = MODE == MODE_DKV ? 4 * (ws - 1) * (TW + 1) - kof_st : 4 * (ws - 1) * (TW + 1) + kof_st;
+    const char* tabq = reinterpret_cast<const char*>(tab) + off_st;
+    char* dtabq = reinterpret_cast<char*>(dtabw) + off_st;         // DQ: the same entry of this warp's gradient sums
     float lse2_st = INFINITY, d_st = 0.f;                           // DQ: per-query constants
     if (MODE == MODE_DQ && row_valid) {
       lse2_st = a.lse[(win * a.nH + h) * N + r_st] * kLog2e;
@@ -368,35 +376,48 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
       ptx::cp_async_commit();
 
       const bool tail_blk = (kb + 1) * KB > N;       // keys / queries beyond the window in this block
-      const int4* meta4 = reinterpret_cast<const int4*>(meta + kb * KB);
+      const bool general = need_mask || tail_blk;    // CTA-uniform: most blocks take the copy without mask / tail tests
+      const int4* kof4 = reinterpret_cast<const int4*>(kof + kb * KB);
+      const int4* rid4 = reinterpret_cast<const int4*>(rid + kb * KB);
       ptx::mbar_wait(&bar_mma, ph);
       ph ^= 1;
       ptx::tc_fence_after();
 
       float alpha = 1.f;
-      if (MODE == MODE_FWD) {
+      if constexpr (MODE == MODE_FWD) {
         // ---- pass 1: logits (log2 units) written back over S, block maximum
         float mx = -INFINITY;
+        auto pass1 = [&](auto gen_c) {
+          constexpr bool GEN = decltype(gen_c)::value;
 #pragma unroll 1
-        for (int cq = 0; cq < KB / 16; ++cq) {
-          uint32_t sv[16];
-          tmem_ld16(t_row + S_COL + cq * 16, sv);
-          ptx::tmem_ld_wait();
+          for (int cq = 0; cq < KB / 16; ++cq) {
+            uint32_t sv[16];
+            tmem_ld16(t_row + S_COL + cq * 16, sv);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const int4 mm = meta4[cq * 4 + j4];
-            const int mj[4] = {mm.x, mm.y, mm.z, mm.w};
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const int4 kk = kof4[cq * 4 + j4];
+              const int kj[4] = {kk.x, kk.y, kk.z, kk.w};
+              int rj[4] = {0, 0, 0, 0};
+              if (GEN) {
+                const int4 rr = rid4[cq * 4 + j4];
+                rj[0] = rr.x; rj[1] = rr.y; rj[2] = rr.z; rj[3] = rr.w;
+              }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float s2 = fmaf(__uint_as_float(sv[j4 * 4 + k]), scale2, tab[base_st - (mj[k] & 0xffff)]);
-              if (need_mask && ((mj[k] >> 16) & 0xff) != rid_st) s2 += kMaskLog2;
-              if (tail_blk && (mj[k] >> 24)) s2 = -INFINITY;
-              mx = fmaxf(mx, s2);
-              sv[j4 * 4 + k] = __float_as_uint(s2);
+              for (int k = 0; k < 4; ++k) {
+                float s2 = fmaf(__uint_as_float(sv[j4 * 4 + k]), scale2, *reinterpret_cast<const float*>(tabq - kj[k]));
+                if (GEN) {
+                  if (need_mask && (rj[k] & 0xff) != rid_st) s2 += kMaskLog2;
+                  if (rj[k] >> 8) s2 = -INFINITY;
+                }
+                mx = fmaxf(mx, s2);
+                sv[j4 * 4 + k] = __float_as_uint(s2);
+              }
             }
+            tmem_st16(t_row + S_COL + cq * 16, sv);
           }
-          tmem_st16(t_row + S_COL + cq * 16, sv);
-        }
+        };
+        if (general) pass1(std::true_type{}); else pass1(std::false_type{});
         ptx::tmem_st_wait();
         const float m_new = fmaxf(m_run, mx);
         alpha = ex2(m_run - m_new);
@@ -423,56 +444,65 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
         // ---- P = exp2(s - lse), dS = P (dP - D), eight streamed tokens per step
         const float4* lse4 = reinterpret_cast<const float4*>(blk_lse + stage * KB);
         const float4* d4 = reinterpret_cast<const float4*>(blk_d + stage * KB);
+        auto sweep = [&](auto gen_c) {
+          constexpr bool GEN = decltype(gen_c)::value;
 #pragma unroll 1
-        for (int cc = 0; cc < KB / 8; ++cc) {
-          uint32_t sv[8], dv[8];
-          tmem_ld8(t_row + S_COL + cc * 8, sv);
-          tmem_ld8(t_row + DP_COL + cc * 8, dv);
-          int mj[8];
-          {
-            const int4 m0 = meta4[cc * 2], m1 = meta4[cc * 2 + 1];
-            mj[0] = m0.x; mj[1] = m0.y; mj[2] = m0.z; mj[3] = m0.w; mj[4] = m1.x; mj[5] = m1.y; mj[6] = m1.z; mj[7] = m1.w;
-          }
-          float lsev[8], dvv[8];
-          if (MODE == MODE_DKV) {
-            const float4 l0 = lse4[cc * 2], l1 = lse4[cc * 2 + 1], e0 = d4[cc * 2], e1 = d4[cc * 2 + 1];
-            lsev[0] = l0.x; lsev[1] = l0.y; lsev[2] = l0.z; lsev[3] = l0.w; lsev[4] = l1.x; lsev[5] = l1.y; lsev[6] = l1.z; lsev[7] = l1.w;
-            dvv[0] = e0.x; dvv[1] = e0.y; dvv[2] = e0.z; dvv[3] = e0.w; dvv[4] = e1.x; dvv[5] = e1.y; dvv[6] = e1.z; dvv[7] = e1.w;
-          }
-          ptx::tmem_ld_wait();
-          uint32_t pkd[4], pkp[4];
-#pragma unroll
-          for (int e2 = 0; e2 < 4; ++e2) {
-            float pl[2], dl[2];
-#pragma unroll
-            for (int e1 = 0; e1 < 2; ++e1) {
-              const int e = 2 * e2 + e1;
-              // DQ: this thread is the query, the streamed token the key; DKV: the other way round
-              const int idx = MODE == MODE_DQ ? base_st - (mj[e] & 0xffff) : (mj[e] & 0xffff) + (ws - 1) * (TW + 1) - koff_st;
-              const float cosv = __uint_as_float(sv[e]);
-              float s2 = fmaf(cosv, scale2, tab[idx]);
-              if (need_mask && ((mj[e] >> 16) & 0xff) != rid_st) s2 += kMaskLog2;
-              float p = ex2(s2 - (MODE == MODE_DQ ? lse2_st : lsev[e]));
-              if (MODE == MODE_DQ && tail_blk && (mj[e] >> 24)) p = 0.f;        // key beyond the window
-              const float dsv = p * (__uint_as_float(dv[e]) - (MODE == MODE_DQ ? d_st : dvv[e]));
-              pl[e1] = p;
-              dl[e1] = dsv;
-              if (MODE == MODE_DQ) {
-                row_a = fmaf(dsv, cosv, row_a);
-                row_b += dsv;
-                row_c = fmaf(p, cosv, row_c);
-                // gradient of the bias table: warp-private sums.  The 32 lanes of a step hit 32 distinct entries (one
-                // key, 32 different queries); consecutive steps of different lanes alias, hence the warp barrier.
-                dtabw[idx] += dsv;
-                __syncwarp();
-              }
+          for (int cc = 0; cc < KB / 8; ++cc) {
+            uint32_t sv[8], dv[8];
+            tmem_ld8(t_row + S_COL + cc * 8, sv);
+            tmem_ld8(t_row + DP_COL + cc * 8, dv);
+            int kj[8], rj[8];
+            {
+              const int4 m0 = kof4[cc * 2], m1 = kof4[cc * 2 + 1];
+              kj[0] = m0.x; kj[1] = m0.y; kj[2] = m0.z; kj[3] = m0.w; kj[4] = m1.x; kj[5] = m1.y; kj[6] = m1.z; kj[7] = m1.w;
             }
-            pkd[e2] = pack_bf16(dl[0], dl[1]);
-            pkp[e2] = pack_bf16(pl[0], pl[1]);
+            if (GEN) {
+              const int4 m0 = rid4[cc * 2], m1 = rid4[cc * 2 + 1];
+              rj[0] = m0.x; rj[1] = m0.y; rj[2] = m0.z; rj[3] = m0.w; rj[4] = m1.x; rj[5] = m1.y; rj[6] = m1.z; rj[7] = m1.w;
+            }
+            float lsev[8], dvv[8];
+            if (MODE == MODE_DKV) {
+              const float4 l0 = lse4[cc * 2], l1 = lse4[cc * 2 + 1], e0 = d4[cc * 2], e1 = d4[cc * 2 + 1];
+              lsev[0] = l0.x; lsev[1] = l0.y; lsev[2] = l0.z; lsev[3] = l0.w; lsev[4] = l1.x; lsev[5] = l1.y; lsev[6] = l1.z; lsev[7] = l1.w;
+              dvv[0] = e0.x; dvv[1] = e0.y; dvv[2] = e0.z; dvv[3] = e0.w; dvv[4] = e1.x; dvv[5] = e1.y; dvv[6] = e1.z; dvv[7] = e1.w;
+            }
+            ptx::tmem_ld_wait();
+            uint32_t pkd[4], pkp[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              float pl[2], dl[2];
+#pragma unroll
+              for (int e1 = 0; e1 < 2; ++e1) {
+                const int e = 2 * e2 + e1;
+                // DQ: this thread is the query, the streamed token the key; DKV: the other way round
+                const int boff = MODE == MODE_DQ ? -kj[e] : kj[e];
+                const float cosv = __uint_as_float(sv[e]);
+                float s2 = fmaf(cosv, scale2, *reinterpret_cast<const float*>(tabq + boff));
+                if (GEN && need_mask && (rj[e] & 0xff) != rid_st) s2 += kMaskLog2;
+                float p = ex2(s2 - (MODE == MODE_DQ ? lse2_st : lsev[e]));
+                if (GEN && MODE == MODE_DQ && (rj[e] >> 8)) p = 0.f;              // key beyond the window
+                const float dsv = p * (__uint_as_float(dv[e]) - (MODE == MODE_DQ ? d_st : dvv[e]));
+                pl[e1] = p;
+                dl[e1] = dsv;
+                if (MODE == MODE_DQ) {
+                  row_a = fmaf(dsv, cosv, row_a);
+                  row_b += dsv;
+                  row_c = fmaf(p, cosv, row_c);
+                  // gradient of the bias table: warp-private sums.  The 32 lanes of a step hit 32 distinct entries (one
+                  // key, 32 different queries); consecutive steps of different lanes alias, hence the warp barrier.
+                  float* dst = reinterpret_cast<float*>(dtabq + boff);
+                  *dst += dsv;
+                  __syncwarp();
+                }
+              }
+              pkd[e2] = pack_bf16(dl[0], dl[1]);
+              pkp[e2] = pack_bf16(pl[0], pl[1]);
+            }
+            tmem_st4(t_row + DP_COL + cc * 4, pkd);
+            if (MODE == MODE_DKV) tmem_st4(t_row + S_COL + cc * 4, pkp);
           }
-          tmem_st4(t_row + DP_COL + cc * 4, pkd);
-          if (MODE == MODE_DKV) tmem_st4(t_row + S_COL + cc * 4, pkp);
-        }
+        };
+        if (general) sweep(std::true_type{}); else sweep(std::false_type{});
         ptx::tmem_st_wait();
       }
       ptx::tc_fence_before();
@@ -530,12 +560,22 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
         if (t_st >= 0) {
           const float inv = 1.0f / l_run;
           uint4* dst = reinterpret_cast<uint4*>(a.out + (int64_t)t_st * a.C + h * HD);
+          uint4* dlo = a.out_lo ? reinterpret_cast<uint4*>(a.out_lo + (int64_t)t_st * a.C + h * HD) : nullptr;
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            dst[c] = make_uint4(pack_bf16(acc0[c * 8 + 0] * inv, acc0[c * 8 + 1] * inv),
-                                pack_bf16(acc0[c * 8 + 2] * inv, acc0[c * 8 + 3] * inv),
-                                pack_bf16(acc0[c * 8 + 4] * inv, acc0[c * 8 + 5] * inv),
-                                pack_bf16(acc0[c * 8 + 6] * inv, acc0[c * 8 + 7] * inv));
+          for (int c = 0; c < 4; ++c) {
+            float o8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o8[e] = acc0[c * 8 + e] * inv;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              hi[e] = pack_bf16(o8[2 * e], o8[2 * e + 1]);
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi[e]));
+              lo[e] = pack_bf16(o8[2 * e] - f.x, o8[2 * e + 1] - f.y);
+            }
+            dst[c] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (dlo) dlo[c] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
         }
       }
     } else if (MODE == MODE_DQ) {
@@ -578,7 +618,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
 }
 
 size_t flash_smem(int mode, int ntab, int nmeta) {
-  size_t s = 1024 + 2 * (size_t)kXTile + (size_t)NSTAGE * kStage + 2 * (size_t)NSTAGE * KB * 4 + 2 * (size_t)nmeta * 4 +
+  size_t s = 1024 + 2 * (size_t)kXTile + (size_t)NSTAGE * kStage + 2 * (size_t)NSTAGE * KB * 4 + 3 * (size_t)nmeta * 4 +
              (size_t)ntab * 4 + (mode == MODE_DQ ? 4 * (size_t)ntab * 4 : 0) + 16;
   // at most four CTAs per SM (128 TMEM columns each): never let a fifth fit by shared memory
   const size_t floor_bytes = 46 * 1024;
@@ -590,8 +630,11 @@ int launch_flash(FlArgs a, cudaStream_t st) {
   const size_t smem = flash_smem(MODE, a.ntab, a.nmeta);
   BSW_REQUIRE(smem <= 227 * 1024, "attn(flash): window %dx%d needs %zu bytes of shared memory", a.g.ws, a.g.ws, smem);
   BSW_CUDA(cudaFuncSetAttribute(attn_flash_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  BSW_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attn_flash_kernel<MODE>, kThreads, smem));
+  // whole unified L1 as shared memory: several CTAs per SM.  (The occupancy query answers for the carve-out of the
+  // moment -- 1 CTA per SM before the first launch -- so the residency is computed here: 128 threads x 128 registers and
+  // 128 TMEM columns allow four CTAs, shared memory decides the rest.)
+  BSW_CUDA(cudaFuncSetAttribute(attn_flash_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  int occ = (int)((227 * 1024) / (smem + 1024));
   if (occ < 1) occ = 1;
   if (occ > 4) occ = 4;
   int64_t grid = (int64_t)sm_count() * occ;
@@ -623,21 +666,21 @@ int fill_args(FlArgs* a, int B, int H, int W, int C, int nH, int ws, int shift) 
 }  // namespace
 
 // D = <dO, O> per (token, head) (attn_bwd_ws.cu)
-int attn_bwd_prep(const void* dout, const void* out, float* dvec, int64_t n, cudaStream_t st);
+int attn_bwd_prep(const void* dout, const void* out, const void* out_lo, float* dvec, int64_t n, cudaStream_t st);
 
-int attn_fwd_flash(const void* qkv, void* out, float* lse, const float* table16, const float* scale, const float* qpad,
+int attn_fwd_flash(const void* qkv, void* out, void* out_lo, float* lse, const float* table16, const float* scale, const float* qpad,
                    const float* vpad, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st) {
   FlArgs a = {};
   int rc = fill_args(&a, B, H, W, C, nH, ws, shift);
   if (rc) return rc;
-  a.qkv = (const __nv_bfloat16*)qkv; a.out = (__nv_bfloat16*)out; a.lse = lse;
+  a.qkv = (const __nv_bfloat16*)qkv; a.out = (__nv_bfloat16*)out; a.out_lo = (__nv_bfloat16*)out_lo; a.lse = lse;
   a.table16 = table16; a.scale = scale; a.qpad = qpad; a.vpad = vpad;
   return launch_flash<MODE_FWD>(a, st);
 }
 
 size_t attn_bwd_flash_workspace_bytes(int B, int H, int W, int nH) { return (size_t)B * H * W * nH * sizeof(float); }
 
-int attn_bwd_flash(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
+int attn_bwd_flash(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
                    const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
                    float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH,
                    int ws, int shift, cudaStream_t st) {
@@ -648,7 +691,7 @@ int attn_bwd_flash(const void* qkv, const void* out, const void* dout, const flo
   a.qkv = (const __nv_bfloat16*)qkv; a.dout = (const __nv_bfloat16*)dout; a.lse = const_cast<float*>(lse);
   a.dvec = (const float*)workspace; a.inv_norm = inv_norm; a.table16 = table16; a.scale = scale; a.qpad = qpad;
   a.vpad = vpad; a.dqkv = (__nv_bfloat16*)dqkv; a.dtable16 = dtable16; a.dscale = dscale; a.dvpad = dvpad;
-  rc = attn_bwd_prep(dout, out, (float*)workspace, (int64_t)B * H * W * nH, st);
+  rc = attn_bwd_prep(dout, out, out_lo, (float*)workspace, (int64_t)B * H * W * nH, st);
   if (rc) return rc;
   rc = launch_flash<MODE_DQ>(a, st);
   if (rc) return rc;

@@ -57,6 +57,7 @@ constexpr uint32_t kSw64 = 4;       // UMMA layout type SWIZZLE_64B
 struct WsArgs {
   const __nv_bfloat16* qkv;
   __nv_bfloat16* out;
+  __nv_bfloat16* out_lo;      // optional: bf16 residual O - bf16(O), so that the backward's D = <dO, O> sees O to ~2^-17
   float* lse;
   const float* table16;
   const float* scale;
@@ -127,6 +128,17 @@ __device__ __forceinline__ uint32_t sw64_off(int r, int c) { return (uint32_t)(r
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+// bf16 of (fp32 values - the bf16 values already packed in `hi`): the low half of a hi/lo split
+__device__ __forceinline__ uint4 residual_bf16(const uint4& hi, const float* v) {
+  const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w};
+  uint32_t r[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h[e]));
+    r[e] = pack_bf16(v[2 * e] - f.x, v[2 * e + 1] - f.y);
+  }
+  return make_uint4(r[0], r[1], r[2], r[3]);
 }
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -539,10 +551,14 @@ attn_fwd_ws_kernel(const __grid_constant__ WsArgs a) {
               if (CF::KB > 0) o[c] = fmaf(__uint_as_float(ob[c]), ib, o[c]);
             }
             uint4* dst = reinterpret_cast<uint4*>(a.out + (int64_t)t * a.C + hh * HD);
+            uint4* dlo = a.out_lo ? reinterpret_cast<uint4*>(a.out_lo + (int64_t)t * a.C + hh * HD) : nullptr;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              dst[c] = make_uint4(pack_bf16(o[c * 8 + 0], o[c * 8 + 1]), pack_bf16(o[c * 8 + 2], o[c * 8 + 3]),
-                                  pack_bf16(o[c * 8 + 4], o[c * 8 + 5]), pack_bf16(o[c * 8 + 6], o[c * 8 + 7]));
+            for (int c = 0; c < 4; ++c) {
+              const uint4 hi = make_uint4(pack_bf16(o[c * 8 + 0], o[c * 8 + 1]), pack_bf16(o[c * 8 + 2], o[c * 8 + 3]),
+                                          pack_bf16(o[c * 8 + 4], o[c * 8 + 5]), pack_bf16(o[c * 8 + 6], o[c * 8 + 7]));
+              dst[c] = hi;
+              if (dlo) dlo[c] = residual_bf16(hi, &o[c * 8]);
+            }
           }
         }
       }
@@ -596,10 +612,10 @@ int launch_ws(const WsArgs& a, cudaStream_t st) {
 
 bool attn_fwd_ws_supported(int ws) { return ws == 4 || ws == 6 || ws == 7 || ws == 8 || ws == 12; }
 
-int attn_fwd_ws(const void* qkv, void* out, float* lse, const float* table16, const float* scale, const float* qpad,
+int attn_fwd_ws(const void* qkv, void* out, void* out_lo, float* lse, const float* table16, const float* scale, const float* qpad,
                 const float* vpad, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st) {
   WsArgs a;
-  a.qkv = (const __nv_bfloat16*)qkv; a.out = (__nv_bfloat16*)out; a.lse = lse;
+  a.qkv = (const __nv_bfloat16*)qkv; a.out = (__nv_bfloat16*)out; a.out_lo = (__nv_bfloat16*)out_lo; a.lse = lse;
   a.table16 = table16; a.scale = scale; a.qpad = qpad; a.vpad = vpad;
   make_geom(&a.g, B, H, W, ws, shift);
   a.C = C; a.nH = nH;

@@ -10,18 +10,18 @@
 namespace b200swin {
 
 bool attn_fwd_ws_supported(int ws);
-int attn_fwd_ws(const void* qkv, void* out, float* lse, const float* table16, const float* scale, const float* qpad,
+int attn_fwd_ws(const void* qkv, void* out, void* out_lo, float* lse, const float* table16, const float* scale, const float* qpad,
                 const float* vpad, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st);
 bool attn_bwd_ws_supported(int ws);
 size_t attn_bwd_ws_workspace_bytes(int B, int H, int W, int nH);
-int attn_bwd_ws(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
+int attn_bwd_ws(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
                 const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
                 float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH, int ws,
                 int shift, cudaStream_t st);
-int attn_fwd_flash(const void* qkv, void* out, float* lse, const float* table16, const float* scale, const float* qpad,
+int attn_fwd_flash(const void* qkv, void* out, void* out_lo, float* lse, const float* table16, const float* scale, const float* qpad,
                    const float* vpad, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st);
 size_t attn_bwd_flash_workspace_bytes(int B, int H, int W, int nH);
-int attn_bwd_flash(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
+int attn_bwd_flash(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
                    const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
                    float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH,
                    int ws, int shift, cudaStream_t st);
@@ -38,14 +38,14 @@ static int check_tc(const char* what, const void* qkv, const void* io, const voi
   return B200SWIN_OK;
 }
 
-int attn_fwd_tc(const void* qkv, void* out, float* lse, const float* table16, const float* scale, const float* qpad,
+int attn_fwd_tc(const void* qkv, void* out, void* out_lo, float* lse, const float* table16, const float* scale, const float* qpad,
                 const float* vpad, const float* mask, int nWm, int B, int H, int W, int C, int nH, int ws, int shift,
                 bool kv_blocked, cudaStream_t st) {
   (void)nWm;
   int rc = check_tc("attn_fwd", qkv, out, mask, B, H, W, C, nH, ws, shift);
   if (rc) return rc;
-  if (!kv_blocked && attn_fwd_ws_supported(ws)) return attn_fwd_ws(qkv, out, lse, table16, scale, qpad, vpad, B, H, W, C, nH, ws, shift, st);
-  return attn_fwd_flash(qkv, out, lse, table16, scale, qpad, vpad, B, H, W, C, nH, ws, shift, st);
+  if (!kv_blocked && attn_fwd_ws_supported(ws)) return attn_fwd_ws(qkv, out, out_lo, lse, table16, scale, qpad, vpad, B, H, W, C, nH, ws, shift, st);
+  return attn_fwd_flash(qkv, out, out_lo, lse, table16, scale, qpad, vpad, B, H, W, C, nH, ws, shift, st);
 }
 
 size_t attn_bwd_tc_workspace_bytes(int B, int H, int W, int nH, int ws) {
@@ -53,7 +53,7 @@ size_t attn_bwd_tc_workspace_bytes(int B, int H, int W, int nH, int ws) {
   return attn_bwd_ws_supported(ws) ? attn_bwd_ws_workspace_bytes(B, H, W, nH) : attn_bwd_flash_workspace_bytes(B, H, W, nH);
 }
 
-int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, const float* inv_norm,
+int attn_bwd_tc(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
                 const float* table16, const float* scale, const float* qpad, const float* vpad, const float* mask,
                 int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, void* workspace,
                 size_t workspace_bytes, int B, int H, int W, int C, int nH, int ws, int shift, bool kv_blocked,
@@ -64,9 +64,9 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float*
   BSW_REQUIRE(workspace && workspace_bytes >= attn_bwd_tc_workspace_bytes(B, H, W, nH, ws),
               "attn_bwd(tc): workspace too small (see b200swin_attn_bwd_workspace_bytes)");
   if (!kv_blocked && attn_bwd_ws_supported(ws))
-    return attn_bwd_ws(qkv, out, dout, lse, inv_norm, table16, scale, qpad, vpad, dqkv, dtable16, dscale, dvpad, workspace,
+    return attn_bwd_ws(qkv, out, out_lo, dout, lse, inv_norm, table16, scale, qpad, vpad, dqkv, dtable16, dscale, dvpad, workspace,
                        B, H, W, C, nH, ws, shift, st);
-  return attn_bwd_flash(qkv, out, dout, lse, inv_norm, table16, scale, qpad, vpad, dqkv, dtable16, dscale, dvpad,
+  return attn_bwd_flash(qkv, out, out_lo, dout, lse, inv_norm, table16, scale, qpad, vpad, dqkv, dtable16, dscale, dvpad,
                         workspace, B, H, W, C, nH, ws, shift, st);
 }
 

@@ -287,19 +287,50 @@ def stage_operand(t: torch.Tensor, exact: bool) -> Operand:
 
 
 _weight_cache: dict = {}
+_staged_registry: dict = {}      # id(param) -> [weakref(param), bf16 view kept current by FusedAdamW, version seen]
+
+
+def invalidate_weight_cache() -> None:
+    """Forget every staged bf16 copy of a weight.  Call after changing parameters through ``p.data`` (EMA, clipping:
+    such writes do not bump ``p._version``, which the cache keys on)."""
+    _weight_cache.clear()
+    for reg in _staged_registry.values():
+        reg[2] = -1
+
+
+def register_staged_weight(p: torch.Tensor, copy_bf16: torch.Tensor) -> None:
+    """``copy_bf16`` is a bf16 tensor of p's shape that the caller keeps equal to ``p`` (optim.FusedAdamW writes it in
+    the optimizer kernel); GEMMs read it instead of casting ``p`` every step."""
+    import weakref
+    key = id(p)
+    _staged_registry[key] = [weakref.ref(p, lambda _r, k=key: _staged_registry.pop(k, None)), copy_bf16, p._version]
 
 
 def stage_weight(w: torch.Tensor, exact: bool) -> Operand:
-    """Stage a parameter once per value (keyed on the tensor's version counter, which optimizers bump)."""
+    """Stage a parameter once per value.  Parameters owned by ``optim.FusedAdamW`` come with a bf16 copy that the
+    optimizer kernel refreshes; anything else is cast here and cached on (storage, version counter) -- except under
+    CUDA-graph capture, where the cast must be part of every capture and nothing is cached."""
+    if not exact:
+        reg = _staged_registry.get(id(w))
+        if reg is not None and reg[0]() is w:
+            if reg[2] != w._version:                       # changed outside the optimizer (init, load_state_dict)
+                wc = w.detach().contiguous()
+                with torch.cuda.device_of(wc):
+                    L.check(L.load().b200swin_split_bf16(wc.data_ptr(), reg[1].data_ptr(), 0, wc.numel(),
+                                                         L.stream_of(wc)), "split_bf16")
+                reg[2] = w._version
+            return Operand(reg[1])
+    if torch.cuda.is_current_stream_capturing():
+        return stage_operand(w.detach(), exact)
     key = (w.data_ptr(), exact)      # data_ptr is stable for a live parameter; version catches in-place updates
     hit = _weight_cache.get(key)
     if hit is not None and hit[0] == w._version and hit[1] == tuple(w.shape) and hit[3]() is w:
         return hit[2]
     import weakref
     op = stage_operand(w.detach(), exact)
-    if len(_weight_cache) > 4096:
+    if len(_weight_cache) > 1024:
         _weight_cache.clear()
-    _weight_cache[key] = (w._version, tuple(w.shape), op, weakref.ref(w))
+    _weight_cache[key] = (w._version, tuple(w.shape), op, weakref.ref(w, lambda _r, k=key: _weight_cache.pop(k, None)))
     return op
 
 
@@ -622,18 +653,21 @@ class _AttnCore(torch.autograd.Function):
         nWm = mask.shape[0] if mask is not None else 0
         with torch.cuda.device_of(qkv):
             out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
+            # bf16 residual of O for the backward's D = <dO, O> (tensor-core path, only when a backward will run)
+            need_lo = impl != 0 and any(ctx.needs_input_grad)
+            out_lo = torch.empty_like(out) if need_lo else None
             lse = torch.empty((nwin, nH, ws * ws), dtype=torch.float32, device=qkv.device)
-            L.check(lib.b200swin_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), t16.data_ptr(), sc.data_ptr(),
-                                          L.ptr(qp), L.ptr(vp), L.ptr(mk), nWm, B, H, W, C, nH, ws, shift,
+            L.check(lib.b200swin_attn_fwd(qkv.data_ptr(), out.data_ptr(), L.ptr(out_lo), lse.data_ptr(), t16.data_ptr(),
+                                          sc.data_ptr(), L.ptr(qp), L.ptr(vp), L.ptr(mk), nWm, B, H, W, C, nH, ws, shift,
                                           L.dtype_code(qkv), impl, L.stream_of(qkv)), "attn_fwd")
-        ctx.save_for_backward(qkv, out, lse, inv_norm, t16, sc, qp, vp, mk)
+        ctx.save_for_backward(qkv, out, out_lo, lse, inv_norm, t16, sc, qp, vp, mk)
         ctx.geom, ctx.impl, ctx.nWm = geom, impl, nWm
         ctx.dtypes = (table16.dtype, scale.dtype, vpad.dtype if vpad is not None else None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        qkv, out, lse, inv_norm, t16, sc, qp, vp, mk = ctx.saved_tensors
+        qkv, out, out_lo, lse, inv_norm, t16, sc, qp, vp, mk = ctx.saved_tensors
         B, H, W, C, nH, ws, shift = ctx.geom
         lib = L.load()
         dout = dout.contiguous()
@@ -647,7 +681,8 @@ class _AttnCore(torch.autograd.Function):
             dvp = acc[t16.numel() + nH:]
             ws_bytes = lib.b200swin_attn_bwd_workspace_bytes(B, H, W, nH, ws, L.dtype_code(qkv), ctx.impl_bwd)
             wsp = torch.empty(ws_bytes, dtype=torch.uint8, device=qkv.device) if ws_bytes else None
-            L.check(lib.b200swin_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+            L.check(lib.b200swin_attn_bwd(qkv.data_ptr(), out.data_ptr(), L.ptr(out_lo) if ctx.impl_bwd != 0 else 0,
+                                          dout.data_ptr(), lse.data_ptr(),
                                           inv_norm.data_ptr(), t16.data_ptr(), sc.data_ptr(), L.ptr(qp), L.ptr(vp),
                                           L.ptr(mk), ctx.nWm, dqkv.data_ptr(), dt16.data_ptr(), dsc.data_ptr(),
                                           dvp.data_ptr(), B, H, W, C, nH, ws, shift, L.dtype_code(qkv), ctx.impl_bwd,

@@ -34,6 +34,7 @@ sc = torch.full((nH,), 10.0, device=dev)
 qpad = torch.nn.functional.normalize(torch.randn(nH, 32, device=dev), dim=-1).reshape(C).contiguous()
 vpad = torch.randn(C, device=dev)
 out = torch.empty(B, H, W, C, device=dev, dtype=torch.bfloat16)
+out_lo = torch.empty_like(out)
 lse = torch.empty(nwin, nH, ws * ws, device=dev)
 dout = torch.randn(B, H, W, C, device=dev).bfloat16()
 dqkv = torch.empty_like(qkv)
@@ -44,12 +45,12 @@ wsp = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
 
 
 def fwd():
-    L.check(lib.b200swin_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), tab.data_ptr(), sc.data_ptr(),
+    L.check(lib.b200swin_attn_fwd(qkv.data_ptr(), out.data_ptr(), out_lo.data_ptr(), lse.data_ptr(), tab.data_ptr(), sc.data_ptr(),
                                   qpad.data_ptr(), vpad.data_ptr(), None, 0, B, H, W, C, nH, ws, a.shift, 1, a.impl, st), "fwd")
 
 
 def bwd():
-    L.check(lib.b200swin_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), inv.data_ptr(),
+    L.check(lib.b200swin_attn_bwd(qkv.data_ptr(), out.data_ptr(), out_lo.data_ptr(), dout.data_ptr(), lse.data_ptr(), inv.data_ptr(),
                                   tab.data_ptr(), sc.data_ptr(), qpad.data_ptr(), vpad.data_ptr(), None, 0,
                                   dqkv.data_ptr(), acc.data_ptr(), acc.data_ptr() + 4 * tab.numel(),
                                   acc.data_ptr() + 4 * (tab.numel() + nH), B, H, W, C, nH, ws, a.shift, 1, a.impl,

@@ -1,0 +1,16 @@
+cd $GRAFT_REPO_ROOT
+timeout 1200 python -m pytest tests/test_attention_gpu.py -q -m gpu -k "core_vs_oracle" 2>&1 | tail -30 > gpurun_out/r2c3_tests.log
+tail -5 gpurun_out/r2c3_tests.log
+{
+for impl in 2; do
+  timeout 120 python tools/prof_attn_raw.py --impl $impl --B 48 --H 30 --C 512 --ws 12
+  timeout 120 python tools/prof_attn_raw.py --impl $impl --B 48 --H 120 --C 128 --ws 12 --shift 6
+done
+for impl in 1; do
+  timeout 300 python tools/prof_attn_raw.py --impl $impl --B 48 --H 120 --C 128 --ws 24 --shift 12 --iters 3
+  timeout 300 python tools/prof_attn_raw.py --impl $impl --B 48 --H 30 --C 512 --ws 24 --iters 3
+  timeout 300 python tools/prof_attn_raw.py --impl $impl --B 48 --H 120 --C 128 --ws 30 --shift 15 --iters 3
+  timeout 300 python tools/prof_attn_raw.py --impl $impl --B 48 --H 60 --C 256 --ws 16 --shift 8 --iters 3
+done
+} > gpurun_out/r2c3_timing.log 2>&1
+cat gpurun_out/r2c3_timing.log
