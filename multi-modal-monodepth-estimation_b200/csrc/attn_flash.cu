@@ -6,8 +6,8 @@
 // reverse / crop of :429-463 and the shift mask of :874-892 as address math; backward per SURVEY.md appendix A).
 //
 // One kernel template, three modes.  In every mode a CTA of 128 threads owns 128 "stationary" rows of one
-// (window, head) -- one row per thread = one TMEM lane -- and streams the other side of the window through a 3-stage
-// cp.async ring in blocks of 64 tokens:
+// (window, head) -- one row per thread = one TMEM lane -- and streams the other side of the window through a
+// double-buffered cp.async ring in blocks of 64 tokens (the co-resident CTAs hide the rest of the latency):
 //   FWD  stationary = queries, streamed = keys:    S = Q K^T -> online softmax -> O += P V        (P: TMEM A operand)
 //   DQ   stationary = queries, streamed = keys:    S, dP = dO V^T -> dS -> dQ += dS K            (dS: TMEM A operand)
 //                                                  + the bias-table and temperature gradients
@@ -34,17 +34,14 @@ namespace b200swin {
 
 namespace {
 constexpr int HD = 32;
-constexpr int KB = 64;                 // streamed tokens per block
 constexpr int kThreads = 128;
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 2;
 constexpr int MODE_FWD = 0, MODE_DQ = 1, MODE_DKV = 2;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kMaskLog2 = -100.0f * 1.4426950408889634f;
 constexpr uint32_t kSw64 = 4;          // UMMA layout type SWIZZLE_64B
 constexpr uint32_t kXTile = 128 * 64;  // stationary operand tile [128][64 B]
-constexpr uint32_t kYTile = KB * 64;   // streamed operand tile   [64][64 B]
-constexpr uint32_t kStage = 2 * kYTile;
 // TMEM columns of a CTA (128 allocated): S | dP, 64 fp32 columns each.  The bf16 A operand a thread derives from its
 // row of S (dP) overwrites the first 32 columns of that row; the block product lands in the last 32.
 constexpr uint32_t S_COL = 0, DP_COL = 64, RES_OFF = 32;
@@ -66,7 +63,7 @@ struct FlArgs {
   float* dscale;
   float* dvpad;
   WinGeom g;
-  int C, nH, N, ntiles, rpt, nkb, ntab, nmeta;
+  int C, nH, N, ntiles, rpt, kb, nkb, ntab, nmeta;
   int64_t nwin, nunits;
 };
 
@@ -79,6 +76,15 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// shared-memory accesses by 32-bit shared-space address (generic 64-bit pointer arithmetic per element costs two adds)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -157,9 +163,12 @@ __device__ __forceinline__ void normalize_bwd_store(const float (&gacc)[HD], con
   }
 }
 
-template <int MODE>
+// KB = streamed tokens per block (64; 48 for 12x12 windows, whose 144 tokens are exactly three blocks)
+template <int MODE, int KB>
 __global__ void __launch_bounds__(kThreads, 4)
 attn_flash_kernel(const __grid_constant__ FlArgs a) {
+  constexpr uint32_t kYTile = KB * 64;             // streamed operand tile [KB][64 B]
+  constexpr uint32_t kStage = 2 * kYTile;
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t bar_mma;
   __shared__ uint32_t tmem_slot;
@@ -204,7 +213,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
   uint32_t ph = 0;                                                 // phase of bar_mma (every thread waits every phase)
 
   const uint32_t xt_s = ptx::smem_u32(xt), ring_s = ptx::smem_u32(ring);
-  constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KB, 0, 0);        // [128 x 32] . [64 x 32]^T
+  constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KB, 0, 0);        // [128 x 32] . [KB x 32]^T
   constexpr uint32_t idesc_r = ptx::make_idesc_bf16(128, HD, 0, 1);        // [128 x 64](TMEM) . [64 x 32] (MN-major B)
   const uint64_t desc_k = ptx::make_smem_desc(0, 16, 512, kSw64);          // K-major tile of 64 B rows
   const uint64_t desc_mn = ptx::make_smem_desc(0, 512, 512, kSw64);        // the same bytes read MN-major
@@ -278,13 +287,15 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
     const int r_loc = tid;
     const int r_st = tile * a.rpt + r_loc;
     const bool row_valid = r_loc < a.rpt && r_st < N;
+    // a warp without a single row (short last tile) only keeps the barriers company
+    const bool warp_live = warp * 32 < a.rpt && tile * a.rpt + warp * 32 < N;
     const int t_st = row_valid ? tok[r_st] : -2;
     const int kof_st = kof[row_valid ? r_st : 0], rid_st = rid[row_valid ? r_st : 0] & 0xff;
     // bias index = koff(query) + (ws-1)(TW+1) - koff(key).  FWD / DQ: this row is the query, `tabq - kof[key]` is the
     // entry; DKV: this row is the key, `tabq + kof[query]`.
     const int off_st = MODE == MODE_DKV ? 4 * (ws - 1) * (TW + 1) - kof_st : 4 * (ws - 1) * (TW + 1) + kof_st;
-    const char* tabq = reinterpret_cast<const char*>(tab) + off_st;
-    char* dtabq = reinterpret_cast<char*>(dtabw) + off_st;         // DQ: the same entry of this warp's gradient sums
+    const uint32_t tabq = ptx::smem_u32(tab) + (uint32_t)off_st;
+    const uint32_t dtabq = ptx::smem_u32(dtabw) + (uint32_t)off_st;   // DQ: the same entry of this warp's gradient sums
     float lse2_st = INFINITY, d_st = 0.f;                           // DQ: per-query constants
     if (MODE == MODE_DQ && row_valid) {
       lse2_st = a.lse[(win * a.nH + h) * N + r_st] * kLog2e;
@@ -338,23 +349,21 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
     }
     gather_block(0);
     ptx::cp_async_commit();
-    if (a.nkb > 1) gather_block(1);
-    ptx::cp_async_commit();
+    if (NSTAGE > 2) {
+      if (a.nkb > 1) gather_block(1);
+      ptx::cp_async_commit();
+    }
 
     float acc0[HD];                     // FWD: O, DQ: dQ, DKV: dV
     float acc1[HD];                     // DKV: dK (dead in the other modes)
 #pragma unroll
     for (int c = 0; c < HD; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
     float m_run = -INFINITY, l_run = 0.f;
-    // DQ: row sums for the temperature gradient sum_j dS_ij cos_ij.  In exact arithmetic sum_j dS_ij = 0; with D = <dO, O>
-    // taken from the bf16 O it is -dD_i, which would leak into the sum as -dD_i * sum_j P_ij cos_ij.  Subtracting
-    // c_i * sum_j dS_ij (c_i = sum_j P_ij cos_ij) removes that first-order error of a heavily cancelling sum.
-    float row_a = 0.f, row_b = 0.f, row_c = 0.f;
 
 #pragma unroll 1
     for (int kb = 0; kb < a.nkb; ++kb) {
       const int stage = kb % NSTAGE;
-      ptx::cp_async_wait<1>();                       // block kb (and the stationary tiles) have landed
+      ptx::cp_async_wait<NSTAGE - 2>();              // block kb (and the stationary tiles) have landed
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       __syncthreads();                               // (A) also: everybody has read the products of block kb - 1
@@ -371,8 +380,8 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
         }
         ptx::mma_commit(&bar_mma);
       }
-      // the stage of block kb + 2 was last read by the MMAs of block kb - 1, which every thread has waited for
-      if (kb + 2 < a.nkb) gather_block(kb + 2);
+      // the stage of block kb + NSTAGE - 1 was last read by the MMAs of block kb - 1, which every thread has waited for
+      if (kb + NSTAGE - 1 < a.nkb) gather_block(kb + NSTAGE - 1);
       ptx::cp_async_commit();
 
       const bool tail_blk = (kb + 1) * KB > N;       // keys / queries beyond the window in this block
@@ -384,7 +393,9 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
       ptx::tc_fence_after();
 
       float alpha = 1.f;
-      if constexpr (MODE == MODE_FWD) {
+      if (!warp_live) {
+        // nothing to compute; the block products of these lanes are never read
+      } else if constexpr (MODE == MODE_FWD) {
         // ---- pass 1: logits (log2 units) written back over S, block maximum
         float mx = -INFINITY;
         auto pass1 = [&](auto gen_c) {
@@ -405,7 +416,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
               }
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                float s2 = fmaf(__uint_as_float(sv[j4 * 4 + k]), scale2, *reinterpret_cast<const float*>(tabq - kj[k]));
+                float s2 = fmaf(__uint_as_float(sv[j4 * 4 + k]), scale2, lds_f32(tabq - (uint32_t)kj[k]));
                 if (GEN) {
                   if (need_mask && (rj[k] & 0xff) != rid_st) s2 += kMaskLog2;
                   if (rj[k] >> 8) s2 = -INFINITY;
@@ -477,7 +488,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
                 // DQ: this thread is the query, the streamed token the key; DKV: the other way round
                 const int boff = MODE == MODE_DQ ? -kj[e] : kj[e];
                 const float cosv = __uint_as_float(sv[e]);
-                float s2 = fmaf(cosv, scale2, *reinterpret_cast<const float*>(tabq + boff));
+                float s2 = fmaf(cosv, scale2, lds_f32(tabq + (uint32_t)boff));
                 if (GEN && need_mask && (rj[e] & 0xff) != rid_st) s2 += kMaskLog2;
                 float p = ex2(s2 - (MODE == MODE_DQ ? lse2_st : lsev[e]));
                 if (GEN && MODE == MODE_DQ && (rj[e] >> 8)) p = 0.f;              // key beyond the window
@@ -485,13 +496,10 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
                 pl[e1] = p;
                 dl[e1] = dsv;
                 if (MODE == MODE_DQ) {
-                  row_a = fmaf(dsv, cosv, row_a);
-                  row_b += dsv;
-                  row_c = fmaf(p, cosv, row_c);
+                  dsc = fmaf(dsv, cosv, dsc);
                   // gradient of the bias table: warp-private sums.  The 32 lanes of a step hit 32 distinct entries (one
                   // key, 32 different queries); consecutive steps of different lanes alias, hence the warp barrier.
-                  float* dst = reinterpret_cast<float*>(dtabq + boff);
-                  *dst += dsv;
+                  sts_f32(dtabq + (uint32_t)boff, lds_f32(dtabq + (uint32_t)boff) + dsv);
                   __syncwarp();
                 }
               }
@@ -534,7 +542,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
       ptx::mbar_wait(&bar_mma, ph);
       ph ^= 1;
       ptx::tc_fence_after();
-      {
+      if (warp_live) {
         uint32_t o[HD];
         tmem_ld16(t_row + (MODE == MODE_DQ ? DP_COL : S_COL) + RES_OFF, o);
         tmem_ld16(t_row + (MODE == MODE_DQ ? DP_COL : S_COL) + RES_OFF + 16, o + 16);
@@ -579,7 +587,6 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
         }
       }
     } else if (MODE == MODE_DQ) {
-      dsc += row_a - row_c * row_b;
       if (t_st >= 0)
         normalize_bwd_store(acc0, xt, r_loc, sc, a.inv_norm[((int64_t)t_st * 2 + 0) * a.nH + h],
                             a.dqkv + (int64_t)t_st * C3 + h * HD);
@@ -617,7 +624,8 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
   }
 }
 
-size_t flash_smem(int mode, int ntab, int nmeta) {
+size_t flash_smem(int mode, int KB, int ntab, int nmeta) {
+  const size_t kStage = 2 * (size_t)KB * 64;
   size_t s = 1024 + 2 * (size_t)kXTile + (size_t)NSTAGE * kStage + 2 * (size_t)NSTAGE * KB * 4 + 3 * (size_t)nmeta * 4 +
              (size_t)ntab * 4 + (mode == MODE_DQ ? 4 * (size_t)ntab * 4 : 0) + 16;
   // at most four CTAs per SM (128 TMEM columns each): never let a fifth fit by shared memory
@@ -625,23 +633,28 @@ size_t flash_smem(int mode, int ntab, int nmeta) {
   return s < floor_bytes ? floor_bytes : s;
 }
 
-template <int MODE>
-int launch_flash(FlArgs a, cudaStream_t st) {
-  const size_t smem = flash_smem(MODE, a.ntab, a.nmeta);
+template <int MODE, int KB>
+int launch_flash_kb(const FlArgs& a, cudaStream_t st) {
+  const size_t smem = flash_smem(MODE, KB, a.ntab, a.nmeta);
   BSW_REQUIRE(smem <= 227 * 1024, "attn(flash): window %dx%d needs %zu bytes of shared memory", a.g.ws, a.g.ws, smem);
-  BSW_CUDA(cudaFuncSetAttribute(attn_flash_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BSW_CUDA(cudaFuncSetAttribute(attn_flash_kernel<MODE, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // whole unified L1 as shared memory: several CTAs per SM.  (The occupancy query answers for the carve-out of the
   // moment -- 1 CTA per SM before the first launch -- so the residency is computed here: 128 threads x 128 registers and
   // 128 TMEM columns allow four CTAs, shared memory decides the rest.)
-  BSW_CUDA(cudaFuncSetAttribute(attn_flash_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  BSW_CUDA(cudaFuncSetAttribute(attn_flash_kernel<MODE, KB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   int occ = (int)((227 * 1024) / (smem + 1024));
   if (occ < 1) occ = 1;
   if (occ > 4) occ = 4;
   int64_t grid = (int64_t)sm_count() * occ;
   if (grid > a.nunits) grid = a.nunits;
-  attn_flash_kernel<MODE><<<(unsigned)grid, kThreads, smem, st>>>(a);
+  attn_flash_kernel<MODE, KB><<<(unsigned)grid, kThreads, smem, st>>>(a);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
+}
+
+template <int MODE>
+int launch_flash(const FlArgs& a, cudaStream_t st) {
+  return a.kb == 48 ? launch_flash_kb<MODE, 48>(a, st) : launch_flash_kb<MODE, 64>(a, st);
 }
 
 int fill_args(FlArgs* a, int B, int H, int W, int C, int nH, int ws, int shift) {
@@ -653,11 +666,14 @@ int fill_args(FlArgs* a, int B, int H, int W, int C, int nH, int ws, int shift) 
   make_geom(&a->g, B, H, W, ws, shift);
   a->C = C; a->nH = nH;
   a->N = ws * ws;
+  // row tiles of 128 (the last one short: its empty warps skip the element-wise work, so a 144-row window costs five
+  // warp passes, not eight) and streamed blocks of 64 tokens -- 48 where that divides the window exactly
   a->ntiles = (a->N + 127) / 128;
-  a->rpt = (a->N + a->ntiles - 1) / a->ntiles;
-  a->nkb = (a->N + KB - 1) / KB;
+  a->rpt = a->N < 128 ? a->N : 128;
+  a->kb = (a->N % 48 == 0 && a->N % 64 != 0 && a->N <= 192) ? 48 : 64;
+  a->nkb = (a->N + a->kb - 1) / a->kb;
   a->ntab = (2 * ws - 1) * (2 * ws - 1);
-  a->nmeta = a->nkb * KB;
+  a->nmeta = a->nkb * a->kb;
   a->nwin = (int64_t)B * a->g.nWh * a->g.nWw;
   a->nunits = a->nwin * nH * a->ntiles;
   BSW_REQUIRE(a->nwin < (1ll << 31), "attn(flash): too many windows");

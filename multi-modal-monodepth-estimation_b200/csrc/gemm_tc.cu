@@ -38,11 +38,14 @@ constexpr uint32_t kABytes = BM * BK * 2;
 // epilogue staging: one unit of 32 rows x 64 B (SWIZZLE_64B) per epilogue warp
 constexpr uint32_t kEpiUnitBytes = 32 * 64;
 constexpr uint32_t kEpiSmemBytes = kEpiWarps * kEpiUnitBytes;       // 32 KB
-template <int BN>
+// CG = CTAs per tile (cta_group): 1, or 2 = a CTA pair computing a 256 x BN tile with ONE tcgen05.mma.cta_group::2 per
+// k-step -- each CTA stages its own 128 A rows and HALF of the B rows (BN / 2), so a k-block costs 32 KB per CTA instead
+// of 48 KB: a third less L2 -> SM traffic per flop (the 128 x 256 mainloop was TMA-latency-bound) and six stages in flight.
+template <int BN, int CG>
 struct Tile {
-  static constexpr uint32_t kBBytes = BN * BK * 2;
+  static constexpr uint32_t kBBytes = (BN / CG) * BK * 2;            // this CTA's share of the B tile
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN == 256 ? 4 : 6;                  // 4 x 48 KB or 6 x 32 KB = 192 KB
+  static constexpr int kStages = kStageBytes > 32768 ? 4 : 6;        // 4 x 48 KB or 6 x 32 KB = 192 KB
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + kEpiSmemBytes + 1024;
   static constexpr uint32_t kTmemCols = 2 * BN;                      // double-buffered accumulator
 };
@@ -276,11 +279,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, Stager& st, 
 
 // EPI / OUT_BF16 are template parameters so that every launch carries only its own epilogue (registers, code size);
 // split-K launches (p.partial) are EPI_NONE with fp32 stores.
-template <bool A_MN, bool B_MN, int BN, int EPI, bool OUT_BF16>
+template <bool A_MN, bool B_MN, int BN, int EPI, bool OUT_BF16, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using TL = Tile<BN>;
+  using TL = Tile<BN, CG>;
   constexpr int STAGES = TL::kStages;
+  // CTA pair: rank 0 (the leader) issues the MMAs; both CTAs load, both drain their own 128 accumulator rows
+  const uint32_t rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+  const uint32_t unit = CG == 2 ? blockIdx.x >> 1 : blockIdx.x;       // persistent work unit: a CTA or a CTA pair
+  const uint32_t nunits = CG == 2 ? gridDim.x >> 1 : gridDim.x;
   extern __shared__ unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -293,19 +300,27 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kEpiWarps); }
+    // pair: the leader's full barrier counts one arrival per CTA (+ the bytes of both), its accumulator-free barrier
+    // the epilogue warps of both CTAs
+    for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full_bar[s], CG); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kEpiWarps * CG); }
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&p.tmA[0]);
     ptx::prefetch_tmap(&p.tmB[0]);
     ptx::prefetch_tmap(&p.tmOut);
   }
   if (warp == 1) {
-    ptx::tmem_alloc(&tmem_slot, TL::kTmemCols);
-    ptx::tmem_relinquish();
+    if constexpr (CG == 2) {
+      ptx::tmem_alloc_2sm(&tmem_slot, TL::kTmemCols);
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(&tmem_slot, TL::kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync_all();          // the peer's barriers exist before anything signals them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
@@ -313,22 +328,24 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   // same time share the streamed A tile in L2 (the weight-side B operand is small and stays resident)
   // 32-bit arithmetic (the host checks num_tiles < 2^31): every role decodes every tile, the epilogue warps of the
   // side-tensor epilogues three times per tile, and a 64-bit division is ~100 instructions
+  // (pair: p.m_tiles counts 256-row super-tiles; this CTA takes the 128-row block `rank` of it)
   auto decode = [&](int64_t t, int& mb, int& nb, int& z) {
     const uint32_t tt = (uint32_t)t, nt = (uint32_t)p.n_tiles, mt = (uint32_t)p.m_tiles;
     const uint32_t r = tt / nt;
     nb = (int)(tt - r * nt);
     z = (int)(r / mt);
-    mb = (int)(r - (uint32_t)z * mt);
+    mb = (int)((r - (uint32_t)z * mt) * CG + rank);
   };
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer
       uint32_t it = 0;
-      for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      constexpr int BNH = BN / CG;                                    // B rows staged by this CTA
+      for (int64_t t = unit; t < p.num_tiles; t += nunits) {
         int mb, nb, z;
         decode(t, mb, nb, z);
-        const int m0 = mb * BM, n0 = nb * BN;
+        const int m0 = mb * BM, n0 = nb * BN + (int)rank * BNH;
         const int kb0 = z * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         for (int seg = 0; seg < p.nseg; ++seg) {
           const CUtensorMap* ta = &p.tmA[seg == 2 ? 1 : 0];           // segments: hi.hi, hi.lo, lo.hi
@@ -339,40 +356,59 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
             ptx::mbar_wait(&empty_bar[s], ph ^ 1);
             unsigned char* sa = smem_al + (size_t)s * TL::kStageBytes;
             unsigned char* sb = sa + kABytes;
-            ptx::mbar_arrive_expect_tx(&full_bar[s], TL::kStageBytes);
             const int k0 = kb * BK;
-            if (A_MN) {
-              ptx::tma_load_2d(sa, ta, &full_bar[s], m0, k0);
-              ptx::tma_load_2d(sa + kABytes / 2, ta, &full_bar[s], m0 + 64, k0);
-            } else {
-              ptx::tma_load_2d(sa, ta, &full_bar[s], k0, m0);
-            }
-            if (B_MN) {
+            if constexpr (CG == 2) {
+              // every byte of the pair is counted on the LEADER's barrier (the only one the MMA thread waits on)
+              const uint32_t lead_bar = ptx::mapa_shared(ptx::smem_u32(&full_bar[s]), 0);
+              if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[s], TL::kStageBytes * 2);
+              else ptx::mbar_arrive_cluster(lead_bar);
+              if (A_MN) {
+                ptx::tma_load_2d_2sm(sa, ta, lead_bar, m0, k0);
+                ptx::tma_load_2d_2sm(sa + kABytes / 2, ta, lead_bar, m0 + 64, k0);
+              } else {
+                ptx::tma_load_2d_2sm(sa, ta, lead_bar, k0, m0);
+              }
+              if (B_MN) {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d(sb + j * 8192, tb, &full_bar[s], n0 + 64 * j, k0);
+                for (int j = 0; j < BNH / 64; ++j) ptx::tma_load_2d_2sm(sb + j * 8192, tb, lead_bar, n0 + 64 * j, k0);
+              } else {
+                ptx::tma_load_2d_2sm(sb, tb, lead_bar, k0, n0);
+              }
             } else {
-              ptx::tma_load_2d(sb, tb, &full_bar[s], k0, n0);
+              ptx::mbar_arrive_expect_tx(&full_bar[s], TL::kStageBytes);
+              if (A_MN) {
+                ptx::tma_load_2d(sa, ta, &full_bar[s], m0, k0);
+                ptx::tma_load_2d(sa + kABytes / 2, ta, &full_bar[s], m0 + 64, k0);
+              } else {
+                ptx::tma_load_2d(sa, ta, &full_bar[s], k0, m0);
+              }
+              if (B_MN) {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j) ptx::tma_load_2d(sb + j * 8192, tb, &full_bar[s], n0 + 64 * j, k0);
+              } else {
+                ptx::tma_load_2d(sb, tb, &full_bar[s], k0, n0);
+              }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (lane == 0 && rank == 0) {
+      // ------------------------------------------------------------------ MMA issuer (pair: the leader only)
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM * CG, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       // descriptors differ between k-steps only in the start-address field (low 14 bits, 16 B units)
       const uint64_t adesc0 = A_MN ? ptx::make_smem_desc(0, kABytes / 2, 1024) : ptx::make_smem_desc(0, 16, 1024);
       const uint64_t bdesc0 = B_MN ? ptx::make_smem_desc(0, 8192, 1024) : ptx::make_smem_desc(0, 16, 1024);
       constexpr uint32_t a_step = (A_MN ? 2048 : 32) >> 4, b_step = (B_MN ? 2048 : 32) >> 4;
       uint32_t it = 0, tcount = 0;
-      for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+      for (int64_t t = unit; t < p.num_tiles; t += nunits, ++tcount) {
         int mb, nb, z;
         decode(t, mb, nb, z);
         const int kb0 = z * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
         const int iters = (kb1 - kb0) * p.nseg;
         const uint32_t acc = tcount & 1;
-        ptx::mbar_wait(&acc_empty[acc], ((tcount >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+        ptx::mbar_wait(&acc_empty[acc], ((tcount >> 1) & 1) ^ 1);     // epilogue(s) have drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int i = 0; i < iters; ++i, ++it) {
@@ -383,11 +419,15 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           const uint32_t sa = smem_base + (uint32_t)s * TL::kStageBytes;
           const uint64_t ad = adesc0 + (sa >> 4), bd = bdesc0 + ((sa + kABytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            ptx::mma_bf16_ss(d_tmem, ad + k * a_step, bd + k * b_step, idesc, (i | k) != 0 ? 1u : 0u);
-          ptx::mma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs retire
+          for (int k = 0; k < BK / 16; ++k) {
+            if constexpr (CG == 2) ptx::mma_bf16_ss_2sm(d_tmem, ad + k * a_step, bd + k * b_step, idesc, (i | k) != 0 ? 1u : 0u);
+            else ptx::mma_bf16_ss(d_tmem, ad + k * a_step, bd + k * b_step, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if constexpr (CG == 2) ptx::mma_commit_2sm(&empty_bar[s], 3); else ptx::mma_commit(&empty_bar[s]);
         }
-        ptx::mma_commit(&acc_full[acc]);           // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (CG == 2) ptx::mma_commit_2sm(&acc_full[acc], 3); else ptx::mma_commit(&acc_full[acc]);
       }
     }
   } else {
@@ -416,9 +456,11 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
           if (cc0 + 8 * j < p.N) aux_next[j] = __ldg(ap + j);
       }
     };
-    if constexpr (aux_bf16) aux_fetch(blockIdx.x, sub);
+    if constexpr (aux_bf16) aux_fetch(unit, sub);
     uint32_t tcount = 0;
-    for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+    const uint32_t lead_empty0 = CG == 2 ? ptx::mapa_shared(ptx::smem_u32(&acc_empty[0]), 0) : 0u;
+    const uint32_t lead_empty1 = CG == 2 ? ptx::mapa_shared(ptx::smem_u32(&acc_empty[1]), 0) : 0u;
+    for (int64_t t = unit; t < p.num_tiles; t += nunits, ++tcount) {
       int mb, nb, z;
       decode(t, mb, nb, z);
       const int m0 = mb * BM + q * 32, n0 = nb * BN;
@@ -433,7 +475,7 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
         if constexpr (aux_bf16) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) aux[j] = aux_next[j];
-          if (c + kEpiSub < BN / 32) aux_fetch(t, c + kEpiSub); else aux_fetch(t + gridDim.x, sub);
+          if (c + kEpiSub < BN / 32) aux_fetch(t, c + kEpiSub); else aux_fetch(t + nunits, sub);
         }
         if (m0 < p.M && col0 < p.N) {              // warp-uniform: this 32 x 32 chunk exists
           const int nvalid = (int)min((int64_t)32, p.N - col0);
@@ -455,14 +497,21 @@ gemm_tc_kernel(const __grid_constant__ GemmParams p) {
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);    // one arrival per epilogue warp frees the accumulator
+      // one arrival per epilogue warp frees the accumulator -- on the leader's barrier: it owns the MMA thread
+      if (lane == 0) {
+        if constexpr (CG == 2) ptx::mbar_arrive_cluster(acc ? lead_empty1 : lead_empty0);
+        else ptx::mbar_arrive(&acc_empty[acc]);
+      }
     }
     if (lane == 0) ptx::bulk_wait<0>();            // all stores of this warp have landed before the CTA retires
   }
-  __syncthreads();
+  ptx::tc_fence_before();
+  if constexpr (CG == 2) ptx::cluster_sync_all();  // neither CTA leaves while its peer may still signal it / read its B half
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TL::kTmemCols);
+    if constexpr (CG == 2) ptx::tmem_dealloc_2sm(tmem_base, TL::kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, TL::kTmemCols);
   }
 }
 
@@ -562,9 +611,11 @@ extern "C" int b200swin_gemm_splits(int64_t M, int64_t N, int64_t K) {
   // Split-K factor for the persistent kernel: minimise  waves x (k-blocks per split + per-tile overhead)  where a
   // wave is one tile per SM -- i.e. prefer tile counts just BELOW a multiple of the SM count over ones just above
   // (160 tiles on 148 SMs cost two full waves).  Smaller factors win ties (fewer fp32 partials to reduce).
-  const int64_t tiles = ((M + BM - 1) / BM) * ((N + pick_bn(N) - 1) / pick_bn(N));
+  // work units: 128-row tiles on single CTAs, or 256-row tiles on CTA pairs (see b200swin_gemm_bf16)
+  const int64_t cg = (pick_bn(N) == 256 && M > BM) ? 2 : 1;
+  const int64_t tiles = ((M + BM * cg - 1) / (BM * cg)) * ((N + pick_bn(N) - 1) / pick_bn(N));
   const int64_t num_kb = (K + BK - 1) / BK;
-  const int64_t sms = sm_count();
+  const int64_t sms = sm_count() / cg;
   int64_t max_splits = num_kb / 4 > 0 ? num_kb / 4 : 1;      // keep >= 4 k-blocks per split
   if (max_splits > 512) max_splits = 512;
   int64_t best = 1, best_cost = -1;
@@ -615,13 +666,15 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   }
   // 128x256 tiles halve the A re-reads and the smem bandwidth per MMA; 128x128 when N does not fill them
   const int bn = pick_bn(N);
+  // CTA pairs (256 x 256 tiles, cta_group::2) whenever the tile is 256 wide and there are at least two row blocks
+  const int cg = (bn == 256 && M > BM) ? 2 : 1;
   int rc;
   if ((rc = operand_map(&p.tmA[0], a_hi, a_mn_major, M, K, BM))) return rc;
-  if ((rc = operand_map(&p.tmB[0], b_hi, b_mn_major, N, K, bn))) return rc;
+  if ((rc = operand_map(&p.tmB[0], b_hi, b_mn_major, N, K, bn / cg))) return rc;
   p.nseg = 1;
   if (a_lo) {
     if ((rc = operand_map(&p.tmA[1], a_lo, a_mn_major, M, K, BM))) return rc;
-    if ((rc = operand_map(&p.tmB[1], b_lo, b_mn_major, N, K, bn))) return rc;
+    if ((rc = operand_map(&p.tmB[1], b_lo, b_mn_major, N, K, bn / cg))) return rc;
     p.nseg = 3;
   }
   p.M = M; p.N = N; p.K = K;
@@ -644,20 +697,38 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   }
 
   cudaStream_t st = (cudaStream_t)stream;
-  p.m_tiles = (int)((M + BM - 1) / BM);
+  p.m_tiles = (int)((M + BM * cg - 1) / (BM * cg));                    // row blocks per work unit: 128, or 256 for a pair
   p.n_tiles = (int)((N + bn - 1) / bn);
   p.num_tiles = (int64_t)p.m_tiles * p.n_tiles * splits;
   BSW_REQUIRE(p.num_tiles < (1ll << 31), "gemm: too many tiles");
-  const unsigned grid = (unsigned)(p.num_tiles < sm_count() ? p.num_tiles : sm_count());
+  const int64_t max_units = sm_count() / cg;
+  const unsigned grid = (unsigned)((p.num_tiles < max_units ? p.num_tiles : max_units) * cg);
   const bool out_bf16 = out_dtype == B200SWIN_BF16 && splits == 1;     // split-K partials are fp32
-#define LAUNCH(AM, BMN, BNV, EPI, OB)                                                                              \
+#define LAUNCH(AM, BMN, BNV, EPI, OB, CGV)                                                                         \
   do {                                                                                                             \
-    BSW_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AM, BMN, BNV, EPI, OB>,                                           \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<BNV>::kSmemBytes));       \
-    gemm_tc_kernel<AM, BMN, BNV, EPI, OB><<<grid, kGemmThreads, Tile<BNV>::kSmemBytes, st>>>(p);                   \
+    BSW_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<AM, BMN, BNV, EPI, OB, CGV>,                                      \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tile<BNV, CGV>::kSmemBytes));  \
+    cudaLaunchConfig_t cfg = {};                                                                                   \
+    cfg.gridDim = dim3(grid);                                                                                      \
+    cfg.blockDim = dim3(kGemmThreads);                                                                             \
+    cfg.dynamicSmemBytes = Tile<BNV, CGV>::kSmemBytes;                                                             \
+    cfg.stream = st;                                                                                               \
+    cudaLaunchAttribute attr[1];                                                                                   \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                              \
+    attr[0].val.clusterDim.x = CGV;                                                                                \
+    attr[0].val.clusterDim.y = 1;                                                                                  \
+    attr[0].val.clusterDim.z = 1;                                                                                  \
+    cfg.attrs = attr;                                                                                              \
+    cfg.numAttrs = CGV == 2 ? 1 : 0;                                                                               \
+    BSW_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<AM, BMN, BNV, EPI, OB, CGV>, p));                             \
   } while (0)
-#define LAUNCH_OB(AM, BMN, BNV, EPI) do { if (out_bf16) LAUNCH(AM, BMN, BNV, EPI, true); else LAUNCH(AM, BMN, BNV, EPI, false); } while (0)
-#define LAUNCH_BN(AM, BMN, EPI) do { if (bn == 256) LAUNCH_OB(AM, BMN, 256, EPI); else LAUNCH_OB(AM, BMN, 128, EPI); } while (0)
+#define LAUNCH_OB(AM, BMN, BNV, EPI, CGV) do { if (out_bf16) LAUNCH(AM, BMN, BNV, EPI, true, CGV); else LAUNCH(AM, BMN, BNV, EPI, false, CGV); } while (0)
+#define LAUNCH_BN(AM, BMN, EPI)                                                  \
+  do {                                                                           \
+    if (bn == 256 && cg == 2) LAUNCH_OB(AM, BMN, 256, EPI, 2);                   \
+    else if (bn == 256) LAUNCH_OB(AM, BMN, 256, EPI, 1);                         \
+    else LAUNCH_OB(AM, BMN, 128, EPI, 1);                                        \
+  } while (0)
   // instantiated combinations: the plain epilogue for every operand layout; GELU and QKV for the forward layout
   // (both K-major); DGELU for the dgrad layout (B read MN-major)
   if (epilogue == B200SWIN_EPI_NONE) {
