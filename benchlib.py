@@ -258,7 +258,11 @@ def rooflines_from_events(events, steps, pk):
     for e0, e1, name, a in events:
         ms = e0.elapsed_time(e1)
         if name == "b200swin_gemm_bf16":
-            add("gemm", ms, 2.0 * a[6] * a[7] * a[8] * (3 if a[1] else 1))
+            fl = 2.0 * a[6] * a[7] * a[8] * (3 if a[1] else 1)
+            add("gemm", ms, fl)
+            kind = ("wgrad" if (a[2] and a[5]) else "dgrad" if a[5] else "fwd") + \
+                   {0: "", 1: "+gelu", 2: "+qkvnorm", 3: "*gelu'", 4: "+residual"}[a[9]]
+            add("gemm." + kind, ms, fl)
         elif name in ("b200swin_attn_fwd", "b200swin_attn_bwd"):
             off = 10 if name.endswith("fwd") else 16
             B, H, W, C, nH, ws = a[off:off + 6]

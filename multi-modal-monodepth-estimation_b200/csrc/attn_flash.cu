@@ -360,8 +360,145 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
     for (int c = 0; c < HD; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
     float m_run = -INFINITY, l_run = 0.f;
 
+    // ------------------------------------------------------------------------------------------------ FWD pipeline
+    // TMEM reads are the scarce resource of this kernel (a tcgen05.ld moves ~64 B per clock and SM: re-reading S for a
+    // second softmax pass, or fetching the block product every block, costs more than the exponentials).  So:
+    //  * S is read ONCE: the 48 logits of a row live in registers between the maximum and the exponentials;
+    //  * O accumulates in TMEM across the blocks of a row tile (tcgen05.mma accumulate) and is read once at the end.  The
+    //    reference maximum m_ref of a row only moves when a block exceeds it by more than 2^8 ("lazy rescale": P <= 256
+    //    is harmless in bf16 / fp32); then the row's O and l are rescaled in place -- rare after the first block;
+    //  * S is double-buffered: S = Q K^T of block kb + 1 is issued together with O += P V of block kb, one barrier and
+    //    one MMA round trip per block.
+    // TMEM columns: S buffer 0 | S buffer 1 | O = 48 + 48 + 32 (the forward always streams 48-token blocks).
+    if constexpr (MODE == MODE_FWD) {
+      static_assert(MODE != MODE_FWD || KB == 48, "the forward streams 48-token blocks");
+      constexpr uint32_t O_COL = 96;
+      constexpr float kLazy = 8.0f;
+      const uint64_t ax = desc_k + (xt_s >> 4);
+      ptx::cp_async_wait<0>();                         // the stationary tile and block 0 have landed
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        ptx::tc_fence_after();
+        const uint64_t by = desc_k + (ring_s >> 4);
+        ptx::mma_bf16_ss(tmem_base, ax, by, idesc_s, 0u);
+        ptx::mma_bf16_ss(tmem_base, ax + 2, by + 2, idesc_s, 1u);
+        ptx::mma_commit(&bar_mma);
+      }
 #pragma unroll 1
-    for (int kb = 0; kb < a.nkb; ++kb) {
+      for (int kb = 0; kb < a.nkb; ++kb) {
+        const uint32_t sb = (uint32_t)(kb & 1) * KB;
+        ptx::mbar_wait(&bar_mma, ph);                  // S of block kb exists, O holds the blocks before kb
+        ph ^= 1;
+        ptx::tc_fence_after();
+        // the other stage was last read by the MMAs of block kb - 1, which have just completed
+        if (kb + 1 < a.nkb) gather_block(kb + 1);
+        ptx::cp_async_commit();
+        if (warp_live) {
+          const bool tail_blk = (kb + 1) * KB > N;
+          const bool general = need_mask || tail_blk;
+          const int4* kof4 = reinterpret_cast<const int4*>(kof + kb * KB);
+          const int4* rid4 = reinterpret_cast<const int4*>(rid + kb * KB);
+          uint32_t sv[KB];
+#pragma unroll
+          for (int c = 0; c < KB / 16; ++c) tmem_ld16(t_row + sb + c * 16, &sv[c * 16]);
+          ptx::tmem_ld_wait();
+          float mx = -INFINITY;
+          auto logits = [&](auto gen_c) {
+            constexpr bool GEN = decltype(gen_c)::value;
+#pragma unroll
+            for (int j4 = 0; j4 < KB / 4; ++j4) {
+              // keep the loads of a group with their group: hoisting all twelve 16-byte key records to the top costs 48
+              // registers the 48 logits need
+              if ((j4 & 1) == 0) asm volatile("" ::: "memory");
+              const int4 kk = kof4[j4];
+              const int kj[4] = {kk.x, kk.y, kk.z, kk.w};
+              int rj[4] = {0, 0, 0, 0};
+              if (GEN) {
+                const int4 rr = rid4[j4];
+                rj[0] = rr.x; rj[1] = rr.y; rj[2] = rr.z; rj[3] = rr.w;
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float s2 = fmaf(__uint_as_float(sv[j4 * 4 + k]), scale2, lds_f32(tabq - (uint32_t)kj[k]));
+                if (GEN) {
+                  if (need_mask && (rj[k] & 0xff) != rid_st) s2 += kMaskLog2;
+                  if (rj[k] >> 8) s2 = -INFINITY;
+                }
+                mx = fmaxf(mx, s2);
+                sv[j4 * 4 + k] = __float_as_uint(s2);
+              }
+            }
+          };
+          if (general) logits(std::true_type{}); else logits(std::false_type{});
+          if (kb == 0) {
+            m_run = mx;                                // nothing accumulated yet: the first block sets the reference
+          } else {
+            const bool grow = mx > m_run + kLazy;
+            if (__any_sync(0xffffffffu, grow)) {       // rescale this warp's rows of O in place (factor 1 where not needed)
+              const float m_new = grow ? mx : m_run;
+              const float f = ex2(m_run - m_new);
+#pragma unroll
+              for (int hf = 0; hf < HD / 16; ++hf) {   // 16 columns at a time: the 48 logits stay live meanwhile
+                uint32_t o[16];
+                tmem_ld16(t_row + O_COL + hf * 16, o);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+                tmem_st16(t_row + O_COL + hf * 16, o);
+              }
+              l_run *= f;
+              m_run = m_new;
+            }
+          }
+          float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+          for (int e = 0; e < KB / 2; ++e) {           // packed in place: sv[e] <- (p[2e], p[2e+1])
+            const float p0 = ex2(__uint_as_float(sv[2 * e]) - m_run), p1 = ex2(__uint_as_float(sv[2 * e + 1]) - m_run);
+            l0 += p0;
+            l1 += p1;
+            sv[e] = pack_bf16(p0, p1);
+          }
+          l_run += l0 + l1;
+          tmem_st16(t_row + sb, sv);                   // P over the start of this block's own S buffer
+          tmem_st8(t_row + sb + 16, sv + 16);
+          ptx::tmem_st_wait();
+        }
+        ptx::cp_async_wait<0>();                       // block kb + 1 has landed
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncthreads();                               // every row's P (and any rescaled O) is in TMEM
+        if (tid == 0) {
+          ptx::tc_fence_after();
+          const uint32_t y0_s = ring_s + (uint32_t)(kb % NSTAGE) * kStage;
+          const uint64_t bv = desc_mn + ((y0_s + kYTile) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < KB / 16; ++ks)
+            ptx::mma_bf16_ts(tmem_base + O_COL, tmem_base + sb + ks * 8, bv + ks * 64, idesc_r, (kb | ks) != 0 ? 1u : 0u);
+          if (kb + 1 < a.nkb) {
+            const uint64_t by = desc_k + ((ring_s + (uint32_t)((kb + 1) % NSTAGE) * kStage) >> 4);
+            ptx::mma_bf16_ss(tmem_base + (KB - sb), ax, by, idesc_s, 0u);
+            ptx::mma_bf16_ss(tmem_base + (KB - sb), ax + 2, by + 2, idesc_s, 1u);
+          }
+          ptx::mma_commit(&bar_mma);
+        }
+      }
+      ptx::mbar_wait(&bar_mma, ph);
+      ph ^= 1;
+      ptx::tc_fence_after();
+      if (warp_live) {
+        uint32_t o[HD];
+        tmem_ld16(t_row + O_COL, o);
+        tmem_ld16(t_row + O_COL + 16, o + 16);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < HD; ++c) acc0[c] = __uint_as_float(o[c]);
+      }
+    }
+
+#pragma unroll 1
+    for (int kb = 0; MODE != MODE_FWD && kb < a.nkb; ++kb) {
       const int stage = kb % NSTAGE;
       ptx::cp_async_wait<NSTAGE - 2>();              // block kb (and the stationary tiles) have landed
       ptx::fence_proxy_async_smem();
@@ -392,65 +529,8 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
       ph ^= 1;
       ptx::tc_fence_after();
 
-      float alpha = 1.f;
       if (!warp_live) {
         // nothing to compute; the block products of these lanes are never read
-      } else if constexpr (MODE == MODE_FWD) {
-        // ---- pass 1: logits (log2 units) written back over S, block maximum
-        float mx = -INFINITY;
-        auto pass1 = [&](auto gen_c) {
-          constexpr bool GEN = decltype(gen_c)::value;
-#pragma unroll 1
-          for (int cq = 0; cq < KB / 16; ++cq) {
-            uint32_t sv[16];
-            tmem_ld16(t_row + S_COL + cq * 16, sv);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const int4 kk = kof4[cq * 4 + j4];
-              const int kj[4] = {kk.x, kk.y, kk.z, kk.w};
-              int rj[4] = {0, 0, 0, 0};
-              if (GEN) {
-                const int4 rr = rid4[cq * 4 + j4];
-                rj[0] = rr.x; rj[1] = rr.y; rj[2] = rr.z; rj[3] = rr.w;
-              }
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float s2 = fmaf(__uint_as_float(sv[j4 * 4 + k]), scale2, lds_f32(tabq - (uint32_t)kj[k]));
-                if (GEN) {
-                  if (need_mask && (rj[k] & 0xff) != rid_st) s2 += kMaskLog2;
-                  if (rj[k] >> 8) s2 = -INFINITY;
-                }
-                mx = fmaxf(mx, s2);
-                sv[j4 * 4 + k] = __float_as_uint(s2);
-              }
-            }
-            tmem_st16(t_row + S_COL + cq * 16, sv);
-          }
-        };
-        if (general) pass1(std::true_type{}); else pass1(std::false_type{});
-        ptx::tmem_st_wait();
-        const float m_new = fmaxf(m_run, mx);
-        alpha = ex2(m_run - m_new);
-        m_run = m_new;
-        // ---- pass 2: P = exp2(s - m) as packed bf16 over the first 32 columns, row sum
-        float l0 = 0.f, l1 = 0.f;
-#pragma unroll 1
-        for (int cq = 0; cq < KB / 16; ++cq) {
-          uint32_t sv[16], pk[8];
-          tmem_ld16(t_row + S_COL + cq * 16, sv);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float p0 = ex2(__uint_as_float(sv[2 * e]) - m_new), p1 = ex2(__uint_as_float(sv[2 * e + 1]) - m_new);
-            l0 += p0;
-            l1 += p1;
-            pk[e] = pack_bf16(p0, p1);
-          }
-          tmem_st8(t_row + S_COL + cq * 8, pk);      // columns [8 cq, 8 cq + 8) < [16 (cq + 1), ...): already consumed
-        }
-        ptx::tmem_st_wait();
-        l_run = fmaf(l_run, alpha, l0 + l1);
       } else {
         // ---- P = exp2(s - lse), dS = P (dP - D), eight streamed tokens per step
         const float4* lse4 = reinterpret_cast<const float4*>(blk_lse + stage * KB);
@@ -518,12 +598,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
       if (tid == 0) {
         ptx::tc_fence_after();
         const uint32_t y0_s = ring_s + (uint32_t)stage * kStage;
-        if (MODE == MODE_FWD) {
-          const uint64_t bv = desc_mn + ((y0_s + kYTile) >> 4);
-#pragma unroll
-          for (int ks = 0; ks < KB / 16; ++ks)
-            ptx::mma_bf16_ts(tmem_base + S_COL + RES_OFF, tmem_base + S_COL + ks * 8, bv + ks * 64, idesc_r, ks);
-        } else if (MODE == MODE_DQ) {
+        if (MODE == MODE_DQ) {
           const uint64_t bk = desc_mn + (y0_s >> 4);
 #pragma unroll
           for (int ks = 0; ks < KB / 16; ++ks)
@@ -549,7 +624,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < HD; ++c)
-          acc0[c] = MODE == MODE_FWD ? fmaf(acc0[c], alpha, __uint_as_float(o[c])) : acc0[c] + __uint_as_float(o[c]);
+          acc0[c] += __uint_as_float(o[c]);
         if (MODE == MODE_DKV) {
           tmem_ld16(t_row + DP_COL + RES_OFF, o);
           tmem_ld16(t_row + DP_COL + RES_OFF + 16, o + 16);
@@ -654,7 +729,14 @@ int launch_flash_kb(const FlArgs& a, cudaStream_t st) {
 
 template <int MODE>
 int launch_flash(const FlArgs& a, cudaStream_t st) {
-  return a.kb == 48 ? launch_flash_kb<MODE, 48>(a, st) : launch_flash_kb<MODE, 64>(a, st);
+  if constexpr (MODE == MODE_FWD) return launch_flash_kb<MODE, 48>(a, st);
+  else return a.kb == 48 ? launch_flash_kb<MODE, 48>(a, st) : launch_flash_kb<MODE, 64>(a, st);
+}
+
+void set_block(FlArgs* a, int kb) {
+  a->kb = kb;
+  a->nkb = (a->N + kb - 1) / kb;
+  a->nmeta = a->nkb * kb;
 }
 
 int fill_args(FlArgs* a, int B, int H, int W, int C, int nH, int ws, int shift) {
@@ -670,10 +752,8 @@ int fill_args(FlArgs* a, int B, int H, int W, int C, int nH, int ws, int shift) 
   // warp passes, not eight) and streamed blocks of 64 tokens -- 48 where that divides the window exactly
   a->ntiles = (a->N + 127) / 128;
   a->rpt = a->N < 128 ? a->N : 128;
-  a->kb = (a->N % 48 == 0 && a->N % 64 != 0 && a->N <= 192) ? 48 : 64;
-  a->nkb = (a->N + a->kb - 1) / a->kb;
   a->ntab = (2 * ws - 1) * (2 * ws - 1);
-  a->nmeta = a->nkb * a->kb;
+  set_block(a, 64);
   a->nwin = (int64_t)B * a->g.nWh * a->g.nWw;
   a->nunits = a->nwin * nH * a->ntiles;
   BSW_REQUIRE(a->nwin < (1ll << 31), "attn(flash): too many windows");
@@ -691,6 +771,7 @@ int attn_fwd_flash(const void* qkv, void* out, void* out_lo, float* lse, const f
   if (rc) return rc;
   a.qkv = (const __nv_bfloat16*)qkv; a.out = (__nv_bfloat16*)out; a.out_lo = (__nv_bfloat16*)out_lo; a.lse = lse;
   a.table16 = table16; a.scale = scale; a.qpad = qpad; a.vpad = vpad;
+  set_block(&a, 48);                                  // the forward always streams 48-token blocks (TMEM: 48 + 48 + 32)
   return launch_flash<MODE_FWD>(a, st);
 }
 
@@ -709,6 +790,8 @@ int attn_bwd_flash(const void* qkv, const void* out, const void* out_lo, const v
   a.vpad = vpad; a.dqkv = (__nv_bfloat16*)dqkv; a.dtable16 = dtable16; a.dscale = dscale; a.dvpad = dvpad;
   rc = attn_bwd_prep(dout, out, out_lo, (float*)workspace, (int64_t)B * H * W * nH, st);
   if (rc) return rc;
+  // backward passes: 64-token blocks, 48 where that divides a small window exactly (12x12)
+  set_block(&a, (a.N % 48 == 0 && a.N % 64 != 0 && a.N <= 192) ? 48 : 64);
   rc = launch_flash<MODE_DQ>(a, st);
   if (rc) return rc;
   return launch_flash<MODE_DKV>(a, st);
