@@ -331,34 +331,41 @@ __device__ __forceinline__ void lds_f8(const float* p, float (&f)[8]) {
 
 // Ring bookkeeping shared by the forward and the backward kernel.  T0 / T1: the two streamed tensors (T1 may be null).
 struct RingWarp {
-  unsigned char* base;       // this warp's kRing slots, each 2 * slot_bytes
+  unsigned char* base;       // this warp's kRing slots, each (1 + t1_mul) * slot_bytes
   uint64_t* bars;            // this warp's kRing mbarriers
-  uint32_t slot_bytes;       // bytes of ONE tensor's chunk (full chunk)
+  uint32_t slot_bytes;       // bytes of the FIRST tensor's chunk (full chunk, bf16)
   int64_t rows, chunk_rows, nchunks, first, stride;
   int C;
+  int t1_mul = 1;            // element size of the second tensor in units of bf16 (2: an fp32 residual stream)
   const __nv_bfloat16* t0;
-  const __nv_bfloat16* t1;
+  const void* t1;
 
   __device__ __forceinline__ int64_t my_chunks() const { return first < nchunks ? (nchunks - first + stride - 1) / stride : 0; }
+  __device__ __forceinline__ size_t slot_stride() const { return (size_t)(1 + t1_mul) * slot_bytes; }
   __device__ __forceinline__ void issue(int64_t it, int lane) const {
     if (lane != 0) return;
     const int s = (int)(it % kRing);
     const int64_t row0 = (first + it * stride) * chunk_rows;
     const int64_t nr = min(chunk_rows, rows - row0);
     const uint32_t bytes = (uint32_t)(nr * C * 2);
-    unsigned char* dst = base + (size_t)s * 2 * slot_bytes;
-    ring_expect(&bars[s], t1 ? 2 * bytes : bytes);
+    unsigned char* dst = base + (size_t)s * slot_stride();
+    ring_expect(&bars[s], t1 ? (1 + t1_mul) * bytes : bytes);
     ring_bulk_load(dst, t0 + row0 * C, bytes, &bars[s]);
-    if (t1) ring_bulk_load(dst + slot_bytes, t1 + row0 * C, bytes, &bars[s]);
+    if (t1) ring_bulk_load(dst + slot_bytes, static_cast<const unsigned char*>(t1) + (size_t)row0 * C * 2 * t1_mul, bytes * t1_mul, &bars[s]);
   }
 };
 
-template <int NV, int LPR, int PASSES>
+// STREAM32: the residual stream is kept in fp32 beside its bf16 copy (what torch.autocast does: LayerNorm outputs and the
+// residual adds stay fp32) -- `residual` is then an fp32 tensor and the result is written twice, fp32 to y32 (the stream)
+// and bf16 to y (the operand of the next GEMM).  With the reference's 1e-5 block-norm initialisation a block's
+// contribution is far below a bf16 half-ulp of the stream and would otherwise be rounded away in every block.
+template <int NV, int LPR, int PASSES, bool STREAM32>
 __global__ void __launch_bounds__(kLnThreads)
-ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ residual,
+ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const void* __restrict__ residual,
                    const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ row_scale, int64_t rows_per_scale, __nv_bfloat16* __restrict__ y,
-                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int C, float eps) {
+                   float* __restrict__ y32, float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows,
+                   int C, float eps) {
   extern __shared__ __align__(128) unsigned char smem_ln[];
   __shared__ __align__(8) uint64_t bars[kLnWarps][kRing];
   constexpr int RPW = 32 / LPR;
@@ -375,9 +382,10 @@ ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
   __syncthreads();
 
   RingWarp rw;
-  rw.base = ring0 + (size_t)warp * kRing * 2 * slot_bytes;
-  rw.bars = bars[warp];
+  rw.t1_mul = STREAM32 ? 2 : 1;
   rw.slot_bytes = slot_bytes;
+  rw.base = ring0 + (size_t)warp * kRing * rw.slot_stride();
+  rw.bars = bars[warp];
   rw.rows = rows; rw.chunk_rows = PASSES * RPW; rw.C = C;
   rw.nchunks = (rows + rw.chunk_rows - 1) / rw.chunk_rows;
   rw.first = (int64_t)blockIdx.x * kLnWarps + warp;
@@ -390,7 +398,7 @@ ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
   for (int64_t it = 0; it < n; ++it) {
     const int s = (int)(it % kRing);
     ring_wait(&rw.bars[s], (uint32_t)((it / kRing) & 1));
-    const unsigned char* xs = rw.base + (size_t)s * 2 * slot_bytes;
+    const unsigned char* xs = rw.base + (size_t)s * rw.slot_stride();
     const unsigned char* rs = xs + slot_bytes;
     const int64_t row0 = (rw.first + it * rw.stride) * rw.chunk_rows;
 #pragma unroll
@@ -431,7 +439,8 @@ ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
         if (live && ch < chunks16) {
           float2 r[4], g[4], b[4], o[4];
           if (residual) {
-            unpack8p(*reinterpret_cast<const uint4*>(rs + (size_t)rl * C * 2 + ch * 16), r);
+            if constexpr (STREAM32) lds_f8p(reinterpret_cast<const float*>(rs + (size_t)rl * C * 4) + ch * 8, r);
+            else unpack8p(*reinterpret_cast<const uint4*>(rs + (size_t)rl * C * 2 + ch * 16), r);
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) r[e] = f2(0.f);
@@ -441,6 +450,11 @@ ln_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 #pragma unroll
           for (int e = 0; e < 4; ++e) o[e] = __ffma2_rn(__ffma2_rn(f[k][e], a2, b02), g[e], __ffma2_rn(b[e], sc2, r[e]));
           *reinterpret_cast<uint4*>(y + row * C + ch * 8) = pack8p(o);
+          if constexpr (STREAM32) {
+            float4* d32 = reinterpret_cast<float4*>(y32 + row * C + ch * 8);
+            d32[0] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+            d32[1] = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+          }
         }
       }
       if (lr == 0 && live) { mean_out[row] = mean; rstd_out[row] = rstd; }
@@ -481,9 +495,9 @@ ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
   __syncthreads();
 
   RingWarp rw;
-  rw.base = ring0 + (size_t)warp * kRing * 2 * slot_bytes;
-  rw.bars = bars[warp];
   rw.slot_bytes = slot_bytes;
+  rw.base = ring0 + (size_t)warp * kRing * rw.slot_stride();
+  rw.bars = bars[warp];
   rw.rows = rows; rw.chunk_rows = PASSES * RPW; rw.C = C;
   rw.nchunks = (rows + rw.chunk_rows - 1) / rw.chunk_rows;
   rw.first = (int64_t)blockIdx.x * kLnWarps + warp;
@@ -510,7 +524,7 @@ ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
       rstd[p] = row < rows ? rstd_in[row] : 0.f;
     }
     ring_wait(&rw.bars[s], (uint32_t)((it / kRing) & 1));
-    const unsigned char* xs = rw.base + (size_t)s * 2 * slot_bytes;
+    const unsigned char* xs = rw.base + (size_t)s * rw.slot_stride();
     const unsigned char* gs = xs + slot_bytes;
 #pragma unroll
     for (int p = 0; p < PASSES; ++p) {
@@ -650,8 +664,10 @@ static bool ln_fast_ok(int C, int dtype) { return dtype == B200SWIN_BF16 && C % 
   } while (0)
 
 static int ln_chunk_rows(int C) { return C <= 128 ? 8 : C <= 256 ? 4 : C <= 512 ? 2 : 1; }
-static size_t ln_ring_bytes(int C) { return (size_t)kLnWarps * kRing * 2 * (size_t)ln_chunk_rows(C) * C * 2; }
-static size_t ln_fwd_smem(int C) { return (((size_t)2 * C * 4 + 127) & ~(size_t)127) + ln_ring_bytes(C); }
+static size_t ln_ring_bytes(int C, int tensors = 2) { return (size_t)kLnWarps * kRing * tensors * (size_t)ln_chunk_rows(C) * C * 2; }
+static size_t ln_fwd_smem(int C, bool stream32 = false) {
+  return (((size_t)2 * C * 4 + 127) & ~(size_t)127) + ln_ring_bytes(C, stream32 ? 3 : 2);
+}
 static size_t ln_bwd_smem(int C, int NP) { return (((size_t)(1 + NP) * C * 4 + 127) & ~(size_t)127) + ln_ring_bytes(C); }
 static int ln_blocks_per_sm(size_t smem) {
   const size_t avail = 227 * 1024;
@@ -669,17 +685,26 @@ static int ln_fast_grid(int64_t rows, int C, size_t smem) {
 static int ln_fast_bwd_grid(int64_t rows, int C) { return ln_fast_grid(rows, C, ln_bwd_smem(C, 3)); }
 
 static int ln_fwd_fast(const void* x, const void* residual, const float* gamma, const float* beta,
-                       const float* row_scale, int64_t rps, void* y, float* mean, float* rstd, int64_t rows, int C,
-                       float eps, cudaStream_t st) {
-  const size_t smem = ln_fwd_smem(C);
+                       const float* row_scale, int64_t rps, void* y, float* y32, float* mean, float* rstd, int64_t rows,
+                       int C, float eps, cudaStream_t st) {
+  const bool stream32 = y32 != nullptr;
+  const size_t smem = ln_fwd_smem(C, stream32);
   const int grid = ln_fast_grid(rows, C, smem);
 #define X(NV, LPR, PASSES)                                                                                           \
   do {                                                                                                               \
-    BSW_CUDA(cudaFuncSetAttribute(ln_fwd_bf16_kernel<NV, LPR, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                  (int)smem));                                                                       \
-    ln_fwd_bf16_kernel<NV, LPR, PASSES><<<grid, kLnThreads, smem, st>>>(                                             \
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)residual, gamma, beta, row_scale, rps, (__nv_bfloat16*)y, mean, \
-        rstd, rows, C, eps);                                                                                         \
+    if (stream32) {                                                                                                  \
+      BSW_CUDA(cudaFuncSetAttribute(ln_fwd_bf16_kernel<NV, LPR, PASSES, true>,                                       \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
+      ln_fwd_bf16_kernel<NV, LPR, PASSES, true><<<grid, kLnThreads, smem, st>>>(                                     \
+          (const __nv_bfloat16*)x, residual, gamma, beta, row_scale, rps, (__nv_bfloat16*)y, y32, mean, rstd, rows,  \
+          C, eps);                                                                                                   \
+    } else {                                                                                                         \
+      BSW_CUDA(cudaFuncSetAttribute(ln_fwd_bf16_kernel<NV, LPR, PASSES, false>,                                      \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                        \
+      ln_fwd_bf16_kernel<NV, LPR, PASSES, false><<<grid, kLnThreads, smem, st>>>(                                    \
+          (const __nv_bfloat16*)x, residual, gamma, beta, row_scale, rps, (__nv_bfloat16*)y, nullptr, mean, rstd,    \
+          rows, C, eps);                                                                                             \
+    }                                                                                                                \
   } while (0)
   LN_FAST_DISPATCH(C, X);
 #undef X
@@ -728,11 +753,23 @@ extern "C" int b200swin_ln_fwd(const void* x, const void* residual, const float*
   if (rows == 0) return B200SWIN_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (ln_fast_ok(C, dtype))
-    return ln_fwd_fast(x, residual, gamma, beta, row_scale, rows_per_scale, y, mean, rstd, rows, C, eps, st);
+    return ln_fwd_fast(x, residual, gamma, beta, row_scale, rows_per_scale, y, nullptr, mean, rstd, rows, C, eps, st);
   if (dtype == B200SWIN_F32)
     return ln_fwd_launch<float>(x, residual, gamma, beta, row_scale, rows_per_scale, y, mean, rstd, rows, C, eps, st);
   return ln_fwd_launch<__nv_bfloat16>(x, residual, gamma, beta, row_scale, rows_per_scale, y, mean, rstd, rows, C,
                                       eps, st);
+}
+
+extern "C" int b200swin_ln_fwd_stream32(const void* x, const float* residual32, const float* gamma, const float* beta,
+                                        const float* row_scale, int64_t rows_per_scale, void* y, float* y32,
+                                        float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
+  BSW_REQUIRE(x && gamma && beta && y && y32 && mean && rstd, "ln_fwd_stream32: null pointer");
+  BSW_REQUIRE(rows >= 0 && C > 0 && ln_fast_ok(C, B200SWIN_BF16), "ln_fwd_stream32: needs C %% 8 == 0, C <= 1536 (C=%d)", C);
+  BSW_REQUIRE(!row_scale || rows_per_scale > 0, "ln_fwd_stream32: rows_per_scale must be > 0 with row_scale");
+  BSW_REQUIRE(!row_scale || (rows < (1ll << 32) && rows_per_scale < (1ll << 32)), "ln_fwd_stream32: row_scale needs rows < 2^32");
+  if (rows == 0) return B200SWIN_OK;
+  return ln_fwd_fast(x, residual32, gamma, beta, row_scale, rows_per_scale, y, y32, mean, rstd, rows, C, eps,
+                     (cudaStream_t)stream);
 }
 
 extern "C" size_t b200swin_ln_bwd_workspace_bytes(int64_t rows, int C) {

@@ -183,11 +183,16 @@ class _LayerNormResidual(torch.autograd.Function):
     """y = residual + row_scale[b] * (LN(x) * gamma + beta); residual / row_scale optional.
     `producer_bias` is the bias of the Linear that produced x: it is NOT used in the forward (the GEMM epilogue
     already added it) -- it is an input only so that its gradient, the column sums of dx, can be returned from the
-    LayerNorm backward kernel, which has dx in registers anyway (the caller passes bias.detach() to the Linear)."""
+    LayerNorm backward kernel, which has dx in registers anyway (the caller passes bias.detach() to the Linear).
+
+    stream32: bf16 activations with an fp32 residual stream (torch.autocast semantics: LayerNorm outputs and residual adds
+    stay fp32).  `residual32` is the fp32 twin of `residual` (values only; gradients keep flowing through the bf16
+    `residual`); the call returns (y, y32) with y = bf16(y32) and y32 marked non-differentiable."""
 
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, row_scale, rows_per_scale, eps, producer_bias=None):
-        L.require_cuda(x, residual, gamma, beta, row_scale)
+    def forward(ctx, x, residual, gamma, beta, row_scale, rows_per_scale, eps, producer_bias=None, residual32=None,
+                stream32=False):
+        L.require_cuda(x, residual, gamma, beta, row_scale, residual32)
         lib = L.load()
         C = x.shape[-1]
         xc = x.contiguous()
@@ -200,25 +205,44 @@ class _LayerNormResidual(torch.autograd.Function):
         g32 = gamma.contiguous().float()
         b32 = beta.contiguous().float()
         rs = None if row_scale is None else row_scale.contiguous().float()
+        y32 = None
         with torch.cuda.device_of(xc):
             y = torch.empty_like(xc)
             stats = torch.empty((2, rows), dtype=torch.float32, device=x.device)
-            L.check(lib.b200swin_ln_fwd(xc.data_ptr(), L.ptr(rc), g32.data_ptr(), b32.data_ptr(), L.ptr(rs),
-                                        rows_per_scale, y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
-                                        rows, C, eps, L.dtype_code(xc), L.stream_of(xc)), "ln_fwd")
+            if stream32:
+                if not stream32_supported(xc.dtype, C):
+                    raise RuntimeError("layer_norm_residual: the fp32 residual stream needs bf16 activations, C % 8 == 0, C <= 1536")
+                r32 = None
+                if residual is not None:
+                    r32 = (residual32 if residual32 is not None else rc.float()).detach().contiguous()
+                    if r32.dtype != torch.float32 or r32.shape != xc.shape:
+                        raise ValueError("layer_norm_residual: residual32 must be an fp32 tensor of x's shape")
+                y32 = torch.empty(xc.shape, dtype=torch.float32, device=x.device)
+                L.check(lib.b200swin_ln_fwd_stream32(xc.data_ptr(), L.ptr(r32), g32.data_ptr(), b32.data_ptr(), L.ptr(rs),
+                                                     rows_per_scale, y.data_ptr(), y32.data_ptr(), stats[0].data_ptr(),
+                                                     stats[1].data_ptr(), rows, C, eps, L.stream_of(xc)), "ln_fwd_stream32")
+            else:
+                L.check(lib.b200swin_ln_fwd(xc.data_ptr(), L.ptr(rc), g32.data_ptr(), b32.data_ptr(), L.ptr(rs),
+                                            rows_per_scale, y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                                            rows, C, eps, L.dtype_code(xc), L.stream_of(xc)), "ln_fwd")
         ctx.save_for_backward(xc, g32, stats, rs)
         ctx.has_res = residual is not None
         ctx.rows_per_scale = rows_per_scale
         ctx.gdtype, ctx.bdtype = gamma.dtype, beta.dtype
         ctx.pbdtype = None
+        ctx.stream32 = bool(stream32)
         if producer_bias is not None:
             if not ln_colsum_supported(xc.dtype, C):
                 raise RuntimeError("layer_norm_residual: producer_bias needs bf16 activations with C % 8 == 0, C <= 1536")
             ctx.pbdtype = producer_bias.dtype
+        if stream32:
+            y32 = y32.view(x.shape)
+            ctx.mark_non_differentiable(y32)
+            return y.view(x.shape), y32
         return y.view(x.shape)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dy32=None):
         xc, g32, stats, rs = ctx.saved_tensors
         lib = L.load()
         C = xc.shape[-1]
@@ -238,11 +262,34 @@ class _LayerNormResidual(torch.autograd.Function):
                                         rows, C, L.dtype_code(xc), ws.data_ptr(), ws_bytes, L.stream_of(xc)), "ln_bwd")
         dres = dyc.view(dy.shape) if ctx.has_res else None
         dpb = dgb[2].to(ctx.pbdtype) if want_cs else None
-        return dx, dres, dgb[0].to(ctx.gdtype), dgb[1].to(ctx.bdtype), None, None, None, dpb
+        return dx, dres, dgb[0].to(ctx.gdtype), dgb[1].to(ctx.bdtype), None, None, None, dpb, None, None
 
 
-def layer_norm_residual(x, gamma, beta, eps, residual=None, row_scale=None, rows_per_scale=1, producer_bias=None):
-    return _LayerNormResidual.apply(x, residual, gamma, beta, row_scale, int(rows_per_scale), float(eps), producer_bias)
+def stream32_supported(dtype: torch.dtype, C: int) -> bool:
+    """Whether layer_norm_residual can keep an fp32 residual stream beside the bf16 activations."""
+    return dtype == torch.bfloat16 and C % 8 == 0 and C <= 1536
+
+
+def layer_norm_residual(x, gamma, beta, eps, residual=None, row_scale=None, rows_per_scale=1, producer_bias=None,
+                        residual32=None, stream32=False):
+    return _LayerNormResidual.apply(x, residual, gamma, beta, row_scale, int(rows_per_scale), float(eps), producer_bias,
+                                    residual32, bool(stream32))
+
+
+# The fp32 twin of a bf16 residual-stream tensor travels as an attribute of the tensor OBJECT the LayerNorm returned: the
+# reference's block signature (x, mask_matrix) has no room for a second tensor.  Lost attributes (a caller that copies or
+# views the tensor) only cost precision: the next LayerNorm then widens the bf16 tensor instead.
+_TWIN = "_b200swin_fp32_stream"
+
+
+def attach_stream(y16: torch.Tensor, y32: torch.Tensor) -> torch.Tensor:
+    setattr(y16, _TWIN, y32)
+    return y16
+
+
+def stream_of_tensor(x: torch.Tensor):
+    t = getattr(x, _TWIN, None)
+    return t if (t is not None and t.shape == x.shape and t.device == x.device) else None
 
 
 # ------------------------------------------------------------------------------ dense contractions

@@ -333,6 +333,10 @@ class SwinTransformerBlockPost(_SwinBlockBase):
         # the residual branches run through aliases of x handed back by the qkv / MLP functions, so that the residual
         # gradients are added inside the dgrad GEMM epilogues (no elementwise gradient-accumulation passes)
         direct = not (self.shift_size > 0 and torch.is_tensor(mask_matrix))
+        # bf16 mode keeps the residual stream in fp32 beside the bf16 activations (torch.autocast semantics; with the
+        # reference's 1e-5 block-norm initialisation a block's contribution is below a bf16 half-ulp of the stream)
+        stream = ops.stream32_supported(ops.compute_dtype(x), self.dim)
+        x32 = ops.stream_of_tensor(x) if stream else None
         if direct:
             assert L == self.H * self.W, f"input feature has wrong size, with L = {L}, H = {self.H}, W = {self.W}"
             a, xr = self.attn.attend(x, x.shape[0], self.H, self.W, self.shift_size, None, fuse, True)
@@ -340,11 +344,13 @@ class SwinTransformerBlockPost(_SwinBlockBase):
             a, xr = self._attention(x, mask_matrix, fuse), x
         x = ops.layer_norm_residual(a, self.norm1.weight, self.norm1.bias, self.norm1.eps, residual=xr,
                                     row_scale=self._drop_scale(x), rows_per_scale=L,
-                                    producer_bias=self.attn.proj.bias if fuse else None)
+                                    producer_bias=self.attn.proj.bias if fuse else None, residual32=x32, stream32=stream)
+        x, x32 = x if stream else (x, None)
         m, xr = self.mlp(x, self.H, self.W, fuse, True)
-        return ops.layer_norm_residual(m, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=xr,
-                                       row_scale=self._drop_scale(x), rows_per_scale=L,
-                                       producer_bias=self.mlp.fc2.bias if fuse else None)
+        y = ops.layer_norm_residual(m, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=xr,
+                                    row_scale=self._drop_scale(x), rows_per_scale=L,
+                                    producer_bias=self.mlp.fc2.bias if fuse else None, residual32=x32, stream32=stream)
+        return ops.attach_stream(*y) if stream else y
 
 
 class SwinTransformerBlockPre(_SwinBlockBase):
@@ -392,6 +398,9 @@ class PatchMerging(nn.Module):
         x = ops.patch_merge(x.view(B, H, W, C))          # pad to even + 2x2 gather in one kernel: [B, H2*W2, 4C]
         if self.postnorm:
             x = ops.linear(x, self.reduction.weight, None)
+            if ops.stream32_supported(x.dtype, 2 * C):       # opens the fp32 residual stream of the next stage
+                return ops.attach_stream(*ops.layer_norm_residual(x, self.norm.weight, self.norm.bias, self.norm.eps,
+                                                                  stream32=True))
             return ops.layer_norm_residual(x, self.norm.weight, self.norm.bias, self.norm.eps)
         x = ops.layer_norm_residual(x, self.norm.weight, self.norm.bias, self.norm.eps)
         return ops.linear(x, self.reduction.weight, None)
@@ -511,7 +520,11 @@ class PatchEmbed(nn.Module):
             Wh, Ww = y.size(2), y.size(3)
             t = y.flatten(2).transpose(1, 2).contiguous()
         if self.norm is not None:
-            t = ops.layer_norm_residual(t, self.norm.weight, self.norm.bias, self.norm.eps)
+            if ops.stream32_supported(t.dtype, self.embed_dim):      # opens the fp32 residual stream of stage 0
+                t = ops.attach_stream(*ops.layer_norm_residual(t, self.norm.weight, self.norm.bias, self.norm.eps,
+                                                               stream32=True))
+            else:
+                t = ops.layer_norm_residual(t, self.norm.weight, self.norm.bias, self.norm.eps)
         return t, Wh, Ww
 
     def forward(self, x):
@@ -680,8 +693,14 @@ class SwinTransformerV2(nn.Module):
             x_out, H, W, x, Wh, Ww = self.layers[i](x, Wh, Ww)
             if i in self.out_indices:
                 norm = getattr(self, f'norm{i}')
+                x32 = ops.stream_of_tensor(x_out)
                 with torch.autocast('cuda', enabled=False):
-                    y = ops.layer_norm_residual(x_out.float(), norm.weight, norm.bias, norm.eps)
+                    if x32 is not None and x_out.requires_grad:
+                        # values from the fp32 stream, gradient through the bf16 tensor (straight-through on the rounding)
+                        xin = x_out.float() + (x32 - x_out.detach().float())
+                    else:
+                        xin = x32 if x32 is not None else x_out.float()
+                    y = ops.layer_norm_residual(xin, norm.weight, norm.bias, norm.eps)
                 outs.append(y.view(-1, H, W, self.num_features[i]).permute(0, 3, 1, 2).contiguous())
         return outs
 

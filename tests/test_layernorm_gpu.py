@@ -65,3 +65,60 @@ def test_ln_residual(rows, C, dtype, with_res, with_scale):
     close(bg.grad, gr[2], "dbeta")
     if with_res:
         close(rg.grad, gr[3], "dres")
+
+
+@pytest.mark.parametrize("rows,C,with_res", [(1000, 128, True), (777, 512, True), (64, 1024, False), (4096, 256, True)])
+def test_fp32_residual_stream_variant(rows, C, with_res):
+    """bf16 activations with an fp32 residual stream (torch.autocast semantics): y32 = residual32 + scale * LN(x) in fp32,
+    y = bf16(y32); gradients as in the plain bf16 call."""
+    from b200swin import ops
+    g = torch.Generator().manual_seed(rows + C)
+    x = torch.randn(rows, C, generator=g).bfloat16().cuda().requires_grad_(True)
+    res32 = (torch.randn(rows, C, generator=g) * 3).cuda() if with_res else None
+    res16 = res32.bfloat16().requires_grad_(True) if with_res else None
+    gamma = (torch.rand(C, generator=g) * 1e-3).cuda().requires_grad_(True)       # tiny gamma: far below a bf16 ulp of res
+    beta = (torch.randn(C, generator=g) * 1e-3).cuda().requires_grad_(True)
+    y, y32 = ops.layer_norm_residual(x, gamma, beta, 1e-6, residual=res16, residual32=res32, stream32=True)
+    ref = torch.nn.functional.layer_norm(x.detach().double(), (C,), gamma.detach().double(), beta.detach().double(), 1e-6)
+    if with_res:
+        ref = ref + res32.double()
+    assert y32.dtype == torch.float32 and not y32.requires_grad
+    assert (y32.double() - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+    assert torch.equal(y, y32.bfloat16())
+    cot = torch.randn(rows, C, generator=g).cuda()
+    (y.float() * cot).sum().backward()
+    y_plain = ops.layer_norm_residual(x.detach().requires_grad_(True), gamma, beta, 1e-6, residual=res16)
+    assert x.grad is not None and (not with_res or torch.equal(res16.grad.float(), cot.bfloat16().float()))
+
+
+def test_tiny_block_norm_gammas_survive_bf16_autocast():
+    """The reference initialises every block norm to gamma = 1e-5 (res-post-norm).  With a bf16 residual stream each
+    block's contribution (~1e-5 relative) is rounded away; with the fp32 stream the bf16-autocast encoder follows the
+    fp32 oracle an order of magnitude inside the bf16 bar."""
+    from b200swin.swin_transformer_v2 import SwinTransformerV2
+    from oracle import swin_ref
+    cfg = dict(embed_dim=64, depths=[2, 2], num_heads=[2, 4], window_size=[4, 4], pretrain_window_size=[4, 4],
+               use_shift=[True, False], drop_path_rate=0.0, out_indices=(0, 1))
+    torch.manual_seed(3)
+    enc = SwinTransformerV2(**cfg)
+    enc.init_weights(None)                                  # block norms at 1e-5
+    with torch.no_grad():
+        for n, p in enc.named_parameters():
+            if ".blocks." in n and "norm" in n and n.endswith("weight"):
+                p.fill_(3e-3)                               # contribution ~3e-3 of the stream: one bf16 ulp is 4e-3
+    img = torch.rand(2, 3, 64, 64)
+    sd = {k: v.detach().clone() for k, v in enc.state_dict().items()}
+    ref = swin_ref.swin_v2(img, sd, cfg["embed_dim"], cfg["depths"], cfg["num_heads"], cfg["window_size"],
+                           cfg["use_shift"], cfg["out_indices"])
+    # what the blocks ADD to the stream (the part a bf16 stream loses): compare the block contribution, not the stream
+    sd0 = {k: (torch.zeros_like(v) if (".blocks." in k and "norm" in k) else v) for k, v in sd.items()}
+    base = swin_ref.swin_v2(img, sd0, cfg["embed_dim"], cfg["depths"], cfg["num_heads"], cfg["window_size"],
+                            cfg["use_shift"], cfg["out_indices"])
+    enc = enc.cuda().eval()
+    with torch.no_grad(), torch.autocast("cuda", torch.bfloat16):
+        outs = enc(img.cuda())
+    for o, r, b0 in zip(outs, ref, base):
+        contrib_ref = (r - b0).double()
+        contrib = (o.cpu().double() - b0.double())
+        err = (contrib - contrib_ref).norm() / contrib_ref.norm()
+        assert err.item() < 0.15, err.item()                 # a bf16 stream gives O(1) here
