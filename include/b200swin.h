@@ -100,7 +100,7 @@ int b200swin_ln_fwd(const void* x, const void* residual, const float* gamma, con
 /* bf16 activations with an fp32 RESIDUAL STREAM (what torch.autocast does: LayerNorm outputs and residual adds stay
  * fp32): x is the bf16 output of the producing GEMM, residual32 (nullable) the fp32 stream; the result is written twice,
  * y32 = residual32 + row_scale * LN(x) in fp32 (the stream handed to the next block) and y = bf16(y32) (the operand of the
- * next GEMM).  Backward is b200swin_ln_bwd on the bf16 tensors (the gradient stream stays bf16).  C % 8 == 0, C <= 1536. */
+ * next GEMM).  Backward is b200swin_ln_bwd on the bf16 tensors (the gradient stream stays bf16).  C % 8 == 0, C <= 1024. */
 int b200swin_ln_fwd_stream32(const void* x, const float* residual32, const float* gamma, const float* beta,
                              const float* row_scale, int64_t rows_per_scale, void* y, float* y32, float* mean,
                              float* rstd, int64_t rows, int C, float eps, void* stream);

@@ -764,7 +764,8 @@ extern "C" int b200swin_ln_fwd_stream32(const void* x, const float* residual32, 
                                         const float* row_scale, int64_t rows_per_scale, void* y, float* y32,
                                         float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
   BSW_REQUIRE(x && gamma && beta && y && y32 && mean && rstd, "ln_fwd_stream32: null pointer");
-  BSW_REQUIRE(rows >= 0 && C > 0 && ln_fast_ok(C, B200SWIN_BF16), "ln_fwd_stream32: needs C %% 8 == 0, C <= 1536 (C=%d)", C);
+  // three tensors per ring slot (bf16 x, fp32 residual): the per-warp rings of 1536-wide rows no longer fit in 227 KB
+  BSW_REQUIRE(rows >= 0 && C > 0 && C % 8 == 0 && C <= 1024, "ln_fwd_stream32: needs C %% 8 == 0, C <= 1024 (C=%d)", C);
   BSW_REQUIRE(!row_scale || rows_per_scale > 0, "ln_fwd_stream32: rows_per_scale must be > 0 with row_scale");
   BSW_REQUIRE(!row_scale || (rows < (1ll << 32) && rows_per_scale < (1ll << 32)), "ln_fwd_stream32: row_scale needs rows < 2^32");
   if (rows == 0) return B200SWIN_OK;

@@ -211,7 +211,7 @@ class _LayerNormResidual(torch.autograd.Function):
             stats = torch.empty((2, rows), dtype=torch.float32, device=x.device)
             if stream32:
                 if not stream32_supported(xc.dtype, C):
-                    raise RuntimeError("layer_norm_residual: the fp32 residual stream needs bf16 activations, C % 8 == 0, C <= 1536")
+                    raise RuntimeError("layer_norm_residual: the fp32 residual stream needs bf16 activations, C % 8 == 0, C <= 1024")
                 r32 = None
                 if residual is not None:
                     r32 = (residual32 if residual32 is not None else rc.float()).detach().contiguous()
@@ -267,7 +267,7 @@ class _LayerNormResidual(torch.autograd.Function):
 
 def stream32_supported(dtype: torch.dtype, C: int) -> bool:
     """Whether layer_norm_residual can keep an fp32 residual stream beside the bf16 activations."""
-    return dtype == torch.bfloat16 and C % 8 == 0 and C <= 1536
+    return dtype == torch.bfloat16 and C % 8 == 0 and C <= 1024
 
 
 def layer_norm_residual(x, gamma, beta, eps, residual=None, row_scale=None, rows_per_scale=1, producer_bias=None,
