@@ -272,13 +272,13 @@ def _run_train(args, w, name, stream):
     if rank == 0:
         gemm_f, attn_f, _ = BL.encoder_flops_per_frame(cfg, w["img"])
         g = fam.get("gemm", {})
-        tr = BL.committed_ncu("r01_ncu_gemm_plain_st2")
+        tr = BL.committed_ncu("r02_ncu_gemm_plain_st2")
         traffic = None
         if tr:
             M, N, K = 43200, 2048, 512
             traffic = {"launch": "gemm_tc_kernel M=43200 N=2048 K=512 (stage-2 fc1 forward)",
                        "dram_bytes": BL._mb(tr["dram_read"]) + BL._mb(tr["dram_write"]),
-                       "algorithmic_bytes": 2.0 * (M * K + N * K + M * N), "source": "profiles/r01_ncu_gemm_plain_st2.json"}
+                       "algorithmic_bytes": 2.0 * (M * K + N * K + M * N), "source": "profiles/r02_ncu_gemm_plain_st2.json"}
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -46,6 +46,7 @@ const char* b200swin_last_error(void);
  * pred: [n] (dtype pred_dtype), target: [n] float32.  stats[4] = {mean(d), n_valid, loss, mean(d^2)}
  * (float32, device) is written by fwd and read by bwd.  grad_out: device pointer to the 0-dim
  * upstream gradient.  grad_pred has pred's dtype.  No valid pixel -> NaN like the reference.
+ * workspace: 3 doubles per CTA of the forward grid for n elements on the CURRENT device (ask on the device you launch on).
  * ------------------------------------------------------------------------------------------ */
 size_t b200swin_silog_workspace_bytes(int64_t n);
 int b200swin_silog_fwd(const void* pred, int pred_dtype, const float* target, int64_t n, float lambd,

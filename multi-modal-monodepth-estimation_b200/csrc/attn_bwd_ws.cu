@@ -978,7 +978,9 @@ int attn_bwd_prep(const void* dout, const void* out, const void* out_lo, float* 
   return B200SWIN_OK;
 }
 
-bool attn_bwd_ws_supported(int ws) { return ws == 4 || ws == 6 || ws == 7 || ws == 8 || ws == 12; }
+// 8x8 windows are instantiated but not routed here: the KV-blocked two-pass backward is faster for them on B200
+// (713 us vs 925 us for 24576 items, tools/prof_attn_raw.py --ws 8), see attn_tc.cu
+bool attn_bwd_ws_supported(int ws) { return ws == 4 || ws == 6 || ws == 7 || ws == 12; }
 
 size_t attn_bwd_ws_workspace_bytes(int B, int H, int W, int nH) { return (size_t)B * H * W * nH * sizeof(float); }
 

@@ -600,30 +600,38 @@ ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
         }
       }
   }
-  // fixed-order cross-warp reduction in shared memory -> one partial row set per block
-  for (int w = 0; w < kLnWarps; ++w) {
-    if (warp == w && sub == 0) {
+  // fixed-order cross-warp reduction -> one partial row set per block.  Every warp parks its sums in its own row of a
+  // [warps][NP * C] matrix laid over the (now idle) ring, ONE barrier, then each thread adds the eight rows of its
+  // columns in warp order.  (Eight warps taking turns on one row cost eight barriers at the end of a 40 us kernel.)
+  __syncthreads();                                   // every warp has left its ring slots
+  float* stage = reinterpret_cast<float*>(ring0);    // ring >= kLnWarps * 3 slots * 4 KB >= kLnWarps * NP * C * 4
+  if (sub == 0) {
+    float* mine = stage + (size_t)warp * NP * C;
 #pragma unroll
-      for (int k = 0; k < NV; ++k) {
-        const int ch = k * LPR + lr;
-        if (ch < chunks16) {
+    for (int k = 0; k < NV; ++k) {
+      const int ch = k * LPR + lr;
+      if (ch < chunks16) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            red[ch * 8 + 2 * e] += dg[k][e].x;
-            red[ch * 8 + 2 * e + 1] += dg[k][e].y;
-            red[C + ch * 8 + 2 * e] += db[k][e].x;
-            red[C + ch * 8 + 2 * e + 1] += db[k][e].y;
-            if (COLSUM) {
-              red[2 * C + ch * 8 + 2 * e] += dc[k][e].x;
-              red[2 * C + ch * 8 + 2 * e + 1] += dc[k][e].y;
-            }
+        for (int e = 0; e < 4; ++e) {
+          mine[ch * 8 + 2 * e] = dg[k][e].x;
+          mine[ch * 8 + 2 * e + 1] = dg[k][e].y;
+          mine[C + ch * 8 + 2 * e] = db[k][e].x;
+          mine[C + ch * 8 + 2 * e + 1] = db[k][e].y;
+          if (COLSUM) {
+            mine[2 * C + ch * 8 + 2 * e] = dc[k][e].x;
+            mine[2 * C + ch * 8 + 2 * e + 1] = dc[k][e].y;
           }
         }
       }
     }
-    __syncthreads();
   }
-  for (int c = threadIdx.x; c < NP * C; c += kLnThreads) part[(int64_t)blockIdx.x * NP * C + c] = red[c];
+  __syncthreads();
+  for (int c = threadIdx.x; c < NP * C; c += kLnThreads) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLnWarps; ++w) t += stage[(size_t)w * NP * C + c];
+    part[(int64_t)blockIdx.x * NP * C + c] = t;
+  }
 }
 
 // dgamma / dbeta (/ dcolsum) = fixed-order sum of the per-block partial rows: 32 columns x 32 part lanes per block, so a

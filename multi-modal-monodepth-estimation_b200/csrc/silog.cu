@@ -127,8 +127,9 @@ static int silog_grid(int64_t n) {
 using namespace b200swin;
 
 extern "C" size_t b200swin_silog_workspace_bytes(int64_t n) {
-  (void)n;
-  return (size_t)148 * 8 * 4 * 3 * sizeof(double);     // upper bound on grid x 3 doubles
+  // exactly what b200swin_silog_fwd checks: one (sum d, sum d^2, count) triple of doubles per CTA of ITS grid on the
+  // current device (floor of one CTA so that n == 0 still hands out a valid pointer)
+  return (size_t)silog_grid(n < 0 ? 0 : n) * 3 * sizeof(double);
 }
 
 extern "C" int b200swin_silog_fwd(const void* pred, int pred_dtype, const float* target, int64_t n, float lambd,

@@ -238,12 +238,17 @@ class _LayerNormResidual(torch.autograd.Function):
         if stream32:
             y32 = y32.view(x.shape)
             ctx.mark_non_differentiable(y32)
+            # the twin never has a gradient: without this autograd hands the backward a zero-filled [T, C] fp32 tensor
+            # for it (an 88 MB fill per LayerNorm at Swin-B stage 2)
+            ctx.set_materialize_grads(False)
             return y.view(x.shape), y32
         return y.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy, _dy32=None):
         xc, g32, stats, rs = ctx.saved_tensors
+        if dy is None:                      # only reachable with set_materialize_grads(False): y itself was unused
+            dy = torch.zeros_like(xc)
         lib = L.load()
         C = xc.shape[-1]
         rows = xc.numel() // C

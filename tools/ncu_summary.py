@@ -16,6 +16,7 @@ want = {
  "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct_of_peak",
  "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
 }
+allk = []
 for r in rows[2:]:
     d = {"kernel": r[hdr.index("Kernel Name")][:90]}
     stalls = {}
@@ -28,4 +29,5 @@ for r in rows[2:]:
             except ValueError:
                 pass
     d["top_stalls_per_issue"] = dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:5])
-    print(json.dumps(d, indent=1))
+    allk.append(d)
+print(json.dumps(allk[0] if len(allk) == 1 else allk, indent=1))
