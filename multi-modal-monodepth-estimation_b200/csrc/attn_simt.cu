@@ -469,11 +469,11 @@ static int attn_bwd_simt(const void* qkv, const void* out, const void* dout, con
 // implemented in attn_tc.cu (tcgen05 path); returns B200SWIN_EINVAL with a message when the shape is unsupported
 int attn_fwd_tc(const void* qkv, void* out, void* out_lo, float* lse, const float* table16, const float* scale, const float* qpad,
                 const float* vpad, const float* mask, int nWm, int B, int H, int W, int C, int nH, int ws, int shift,
-                bool kv_blocked, cudaStream_t st);
+                int family, cudaStream_t st);
 int attn_bwd_tc(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
                 const float* table16, const float* scale, const float* qpad, const float* vpad, const float* mask,
                 int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, void* workspace,
-                size_t workspace_bytes, int B, int H, int W, int C, int nH, int ws, int shift, bool kv_blocked,
+                size_t workspace_bytes, int B, int H, int W, int C, int nH, int ws, int shift, int family,
                 cudaStream_t st);
 size_t attn_bwd_tc_workspace_bytes(int B, int H, int W, int nH, int ws);
 
@@ -487,9 +487,9 @@ extern "C" int b200swin_attn_fwd(const void* qkv, void* out, void* out_lo, float
   BSW_REQUIRE(qkv && out && lse && table16 && scale, "attn_fwd: null pointer");
   BSW_REQUIRE(dtype == B200SWIN_F32 || dtype == B200SWIN_BF16, "attn_fwd: bad dtype %d", dtype);
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 1 || impl == 2) {
+  if (impl >= 1 && impl <= 4) {
     BSW_REQUIRE(dtype == B200SWIN_BF16, "attn_fwd: the tensor-core path stores bf16");
-    return attn_fwd_tc(qkv, out, out_lo, lse, table16, scale, qpad, vpad, mask, nWm, B, H, W, C, nH, ws, shift, impl == 2, st);
+    return attn_fwd_tc(qkv, out, out_lo, lse, table16, scale, qpad, vpad, mask, nWm, B, H, W, C, nH, ws, shift, impl - 1, st);
   }
   BSW_REQUIRE(impl == 0, "attn_fwd: unknown impl %d", impl);
   (void)out_lo;                                     // the CUDA-core path is the reference-precision path: fp32 tensors, nothing to split
@@ -503,7 +503,7 @@ extern "C" int b200swin_attn_fwd(const void* qkv, void* out, void* out_lo, float
 
 extern "C" size_t b200swin_attn_bwd_workspace_bytes(int B, int H, int W, int nH, int ws, int dtype, int impl) {
   // scratch of the backward: D = <dO, O> per (token, head) for the warp-specialised tensor-core kernel
-  if ((impl != 1 && impl != 2) || dtype != B200SWIN_BF16 || B <= 0 || H <= 0 || W <= 0 || nH <= 0) return 0;
+  if (impl < 1 || impl > 4 || dtype != B200SWIN_BF16 || B <= 0 || H <= 0 || W <= 0 || nH <= 0) return 0;
   return attn_bwd_tc_workspace_bytes(B, H, W, nH, ws);
 }
 
@@ -516,10 +516,10 @@ extern "C" int b200swin_attn_bwd(const void* qkv, const void* out, const void* o
               "attn_bwd: null pointer");
   BSW_REQUIRE(dtype == B200SWIN_F32 || dtype == B200SWIN_BF16, "attn_bwd: bad dtype %d", dtype);
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == 1 || impl == 2) {
+  if (impl >= 1 && impl <= 4) {
     BSW_REQUIRE(dtype == B200SWIN_BF16, "attn_bwd: the tensor-core path stores bf16");
     return attn_bwd_tc(qkv, out, out_lo, dout, lse, inv_norm, table16, scale, qpad, vpad, mask, nWm, dqkv, dtable16, dscale,
-                       dvpad, workspace, workspace_bytes, B, H, W, C, nH, ws, shift, impl == 2, st);
+                       dvpad, workspace, workspace_bytes, B, H, W, C, nH, ws, shift, impl - 1, st);
   }
   BSW_REQUIRE(impl == 0, "attn_bwd: unknown impl %d", impl);
   (void)out_lo;

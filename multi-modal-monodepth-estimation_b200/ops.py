@@ -681,6 +681,10 @@ def _pick_impl(dtype, ws, mask, backward=False):
         return 1
     if mode == "flash":
         return 2
+    if mode == "ws":                      # single-tile tcgen05 kernels (A/B timing against the warp-MMA kernels)
+        return 3
+    if mode == "mma":
+        return 4
     return 1 if _tc_applicable(dtype, ws, mask, backward) else 0
 
 
