@@ -200,10 +200,16 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
         tokm[stage * NP + row] = t;
         ridm[stage * NP + row] = region;
       }
-      const __nv_bfloat16* src = t >= 0 ? a.qkv + (int64_t)t * C3 + pp.h * HD + pc * 8 : nullptr;
-      put16(q0, q0_s, off, src, t == -1 ? qp : nullptr);
-      put16(q0 + TILE, q0_s + TILE, off, t >= 0 ? src + a.C : nullptr, nullptr);
-      put16(q0 + 2 * TILE, q0_s + 2 * TILE, off, t >= 0 ? src + 2 * a.C : nullptr, t == -1 ? vp : nullptr);
+      if (t >= 0) {
+        const __nv_bfloat16* src = a.qkv + (int64_t)t * C3 + pp.h * HD + pc * 8;
+        ptx::cp_async_16(q0_s + off, src);
+        ptx::cp_async_16(q0_s + TILE + off, src + a.C);
+        ptx::cp_async_16(q0_s + 2 * TILE + off, src + 2 * a.C);
+      } else {
+        put16(q0, q0_s, off, nullptr, t == -1 ? qp : nullptr);
+        put16(q0 + TILE, q0_s + TILE, off, nullptr, nullptr);
+        put16(q0 + 2 * TILE, q0_s + 2 * TILE, off, nullptr, t == -1 ? vp : nullptr);
+      }
     }
     item_next(a, pp);
   };
@@ -390,6 +396,417 @@ int launch_mma_fwd(const MmaArgs& a, cudaStream_t st) {
   return B200SWIN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------ backward
+// One CTA (NT warps) per (window, head) item, ONE pass, two phases per item:
+//   phase 1  warp j owns 16 KEYS: S^T = K_j Q^T and dP^T = V_j dO^T (rows = keys, columns = queries) -> P^T, dS^T in
+//            registers, which ARE the A operands of dV_j += P^T dO and dK_j += dS^T Q (no transposes); dS^T also goes to a
+//            bf16 panel [key][query] in shared memory; the bias-table gradient is summed in registers across all windows
+//            of a head (a thread sees the same (key, query) positions in every item);
+//   phase 2  warp i owns 16 QUERIES: dQ_i = dS_i K with dS_i read from the panel (ldmatrix.trans).
+// Two CTA barriers per item; the q / k / v / dO tiles, lse and D = <dO, O> of the next item are in flight meanwhile.
+constexpr int kBwdStages = 2;
+
+template <int WS>
+struct BCfg {
+  using Cf = MCfg<WS>;
+  static constexpr uint32_t STAGE_TILES = 4 * Cf::TILE;                       // q | k | v | dO
+  static constexpr uint32_t PSTRIDE = Cf::NP * 2 + 16;                        // bytes per key row of the dS panel
+  static constexpr uint32_t OFF_QMETA = kBwdStages * STAGE_TILES;             // [stages][NP] {lse, D}
+  static constexpr uint32_t OFF_TOK = OFF_QMETA + kBwdStages * Cf::NP * 8;    // [stages][NP]
+  static constexpr uint32_t OFF_RID = OFF_TOK + kBwdStages * Cf::NP * 4;      // [stages][NP]
+  static constexpr uint32_t OFF_KOF = OFF_RID + kBwdStages * Cf::NP * 4;      // [NP]
+  static constexpr uint32_t OFF_TAB = OFF_KOF + Cf::NP * 4;                   // [NTAB]
+  static constexpr uint32_t OFF_PANEL = (OFF_TAB + Cf::NTAB * 4 + 127) / 128 * 128;
+  static constexpr uint32_t OFF_RED = OFF_PANEL + Cf::NP * PSTRIDE;           // [NT] floats (+ pad to 16 B)
+  // per-thread gradient sums that do not fit the register file (168 registers per thread with nine warps: three warps on
+  // one SM sub-partition): the bias-gradient sums of the last DBS column tiles and the v_bias gradient, [slot][thread]
+  static constexpr int DBS = Cf::NTILES8 >= 18 ? 10 : 0;                       // column tiles (of 8 queries) kept in smem
+  static constexpr uint32_t OFF_DBS = OFF_RED + (Cf::NT * 4 + 15) / 16 * 16;  // [DBS * 2][THREADS] float2
+  static constexpr uint32_t OFF_DVP = OFF_DBS + DBS * 2 * Cf::THREADS * 8;    // [8][THREADS] float
+  static constexpr uint32_t SMEM = OFF_DVP + 8 * Cf::THREADS * 4 + 128;
+  static_assert((Cf::NP / 2) * Cf::NP * 4 <= Cf::NP * PSTRIDE, "the flush staging lives in the panel");
+};
+
+template <int WS>
+__global__ void __launch_bounds__(MCfg<WS>::THREADS, 1)
+attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
+  using Cf = MCfg<WS>;
+  using Bc = BCfg<WS>;
+  constexpr int N = Cf::N, NP = Cf::NP, TW = Cf::TW, NT8 = Cf::NTILES8;
+  constexpr uint32_t TILE = Cf::TILE, PSTRIDE = Bc::PSTRIDE;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base_u32 = (ptx::smem_u32(smem_dyn) + 127u) & ~127u;
+  unsigned char* sm = smem_dyn + (base_u32 - ptx::smem_u32(smem_dyn));
+  float2* qmeta = reinterpret_cast<float2*>(sm + Bc::OFF_QMETA);
+  int* tokm = reinterpret_cast<int*>(sm + Bc::OFF_TOK);
+  int* ridm = reinterpret_cast<int*>(sm + Bc::OFF_RID);
+  int* kofk = reinterpret_cast<int*>(sm + Bc::OFF_KOF);
+  float* tab = reinterpret_cast<float*>(sm + Bc::OFF_TAB);
+  unsigned char* panel = sm + Bc::OFF_PANEL;
+  float* red = reinterpret_cast<float*>(sm + Bc::OFF_RED);
+  float2* dbs = reinterpret_cast<float2*>(sm + Bc::OFF_DBS) + threadIdx.x;   // + slot * THREADS
+  float* dvps = reinterpret_cast<float*>(sm + Bc::OFF_DVP) + threadIdx.x;    // + slot * THREADS
+  const uint32_t panel_s = base_u32 + Bc::OFF_PANEL;
+  constexpr int DBS = Bc::DBS, NREG = Cf::NTILES8 - DBS;                      // column tiles summed in registers
+
+  const WinGeom& g = a.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int64_t per = a.nitems / gridDim.x, rem = a.nitems % gridDim.x;
+  const int64_t it0 = (int64_t)blockIdx.x * per + min((int64_t)blockIdx.x, rem);
+  const int nit = (int)(per + ((int64_t)blockIdx.x < rem ? 1 : 0));
+  const int C3 = 3 * a.C;
+
+  for (int r = tid; r < NP; r += Cf::THREADS) kofk[r] = r < N ? 4 * ((r / WS) * TW + (r % WS)) : 0;
+
+  static_assert(NP * 4 == 2 * Cf::THREADS, "two slots per thread");
+  const int pc = tid & 3, prow0 = tid >> 2, prow1 = prow0 + Cf::THREADS / 4;
+  const int py0 = prow0 / WS, px0 = prow0 - py0 * WS, py1 = prow1 / WS, px1 = prow1 - py1 * WS;
+  const uint32_t poff0 = sw64(prow0, pc), poff1 = sw64(prow1, pc);
+  ItemPos pp = item_pos(a, it0);
+  auto prefetch = [&](int i) {
+    const int stage = i % kBwdStages;
+    unsigned char* q0 = sm + (size_t)stage * Bc::STAGE_TILES;
+    const uint32_t q0_s = base_u32 + (uint32_t)stage * Bc::STAGE_TILES;
+    const float* lse_it = a.lse + (pp.win * a.nH + pp.h) * N;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int row = k ? prow1 : prow0;
+      const uint32_t off = k ? poff1 : poff0;
+      int region = 0, t = -2;
+      if (!Cf::RAGGED || row < N) t = row_token<WS>(g, pp, k ? py1 : py0, k ? px1 : px0, &region);
+      if (pc == 0) {
+        tokm[stage * NP + row] = t;
+        ridm[stage * NP + row] = region;
+        float2* qm = qmeta + stage * NP + row;
+        const uint32_t qm_s = base_u32 + Bc::OFF_QMETA + (uint32_t)(stage * NP + row) * 8u;
+        if (t >= 0) {
+          ptx::cp_async_4(qm_s, lse_it + row);
+          ptx::cp_async_4(qm_s + 4, a.dvec + (int64_t)t * a.nH + pp.h);
+        } else if (t == -1) {
+          ptx::cp_async_4(qm_s, lse_it + row);
+          qm->y = 0.f;
+        } else {
+          *qm = make_float2(INFINITY, 0.f);          // beyond the window: P = 0
+        }
+      }
+      if (t >= 0) {
+        const __nv_bfloat16* src = a.qkv + (int64_t)t * C3 + pp.h * HD + pc * 8;
+        ptx::cp_async_16(q0_s + off, src);
+        ptx::cp_async_16(q0_s + TILE + off, src + a.C);
+        ptx::cp_async_16(q0_s + 2 * TILE + off, src + 2 * a.C);
+        ptx::cp_async_16(q0_s + 3 * TILE + off, a.dout + (int64_t)t * a.C + pp.h * HD + pc * 8);
+      } else {
+        const float* qp = (t == -1 && a.qpad) ? a.qpad + pp.h * HD + pc * 8 : nullptr;
+        const float* vp = (t == -1 && a.vpad) ? a.vpad + pp.h * HD + pc * 8 : nullptr;
+        put16(q0, q0_s, off, nullptr, qp);
+        put16(q0 + TILE, q0_s + TILE, off, nullptr, nullptr);
+        put16(q0 + 2 * TILE, q0_s + 2 * TILE, off, nullptr, vp);
+        put16(q0 + 3 * TILE, q0_s + 3 * TILE, off, nullptr, nullptr);
+      }
+    }
+    item_next(a, pp);
+  };
+
+  if (nit > 0) prefetch(0);
+  ptx::cp_async_commit();
+
+  int cur_h = -1;
+  float sc = 0.f, scale2 = 0.f, dsc = 0.f;
+  const int rA = warp * 16 + gq, rB = rA + 8;      // phase 1: keys; phase 2: queries
+  ItemPos p = item_pos(a, it0);
+  const uint32_t la_off = sw64(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, lane >> 4);      // A fragments of the warp's 16 rows
+  const uint32_t lk_off = sw64(lane & 7, lane >> 3);                                            // B fragments, K-major (8 rows x 4 chunks)
+  const uint32_t lv_off0 = sw64((lane & 7) + ((lane >> 3) & 1) * 8, lane >> 4);                 // B fragments, MN-major (16 rows x chunks 0, 1)
+  const uint32_t lv_off2 = sw64((lane & 7) + ((lane >> 3) & 1) * 8, 2 + (lane >> 4));
+  // panel: phase 1 writes (key row, query pair); phase 2 reads 8 keys x 8 queries blocks transposed
+  const uint32_t pw_offA = (uint32_t)rA * PSTRIDE + (uint32_t)tq * 4u, pw_offB = pw_offA + 8u * PSTRIDE;
+  const uint32_t pr_off = (uint32_t)((lane & 7) + (lane >> 4) * 8) * PSTRIDE + (uint32_t)(warp * 16 + ((lane >> 3) & 1) * 8) * 2u;
+
+  float db[NREG > 0 ? NREG : 1][4];                 // bias-table gradient of this thread's (key, query) positions
+#pragma unroll
+  for (int n = 0; n < NREG; ++n) db[n][0] = db[n][1] = db[n][2] = db[n][3] = 0.f;
+#pragma unroll
+  for (int n = 0; n < DBS * 2; ++n) dbs[n * Cf::THREADS] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) dvps[e * Cf::THREADS] = 0.f;   // dV rows of pad keys = gradient of v_bias
+
+  auto flush_head = [&](int h) {
+    // every warp is past phase 2 of its last item (the caller sits behind a CTA barrier): the panel is free
+    const float s = warp_sum(dsc);
+    dsc = 0.f;
+    if (lane == 0) red[warp] = s;
+    if (a.dvpad) {
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float v = dvps[(dn * 2 + e) * Cf::THREADS];
+          dvps[(dn * 2 + e) * Cf::THREADS] = 0.f;
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (gq == 0 && v != 0.f) atomicAdd(a.dvpad + h * HD + dn * 8 + 2 * tq + e, v);
+        }
+    }
+    float* stg = reinterpret_cast<float*>(panel);   // [NP / 2][NP]
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int lo = half * (NP / 2);
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = rr ? rB : rA;
+        if (r >= lo && r < lo + NP / 2) {
+#pragma unroll
+          for (int n = 0; n < NREG; ++n)
+            *reinterpret_cast<float2*>(stg + (r - lo) * NP + n * 8 + 2 * tq) = make_float2(db[n][2 * rr], db[n][2 * rr + 1]);
+#pragma unroll
+          for (int n = 0; n < DBS; ++n)
+            *reinterpret_cast<float2*>(stg + (r - lo) * NP + (NREG + n) * 8 + 2 * tq) = dbs[(n * 2 + rr) * Cf::THREADS];
+        }
+      }
+      __syncthreads();
+      if (half == 0 && tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < Cf::NT; ++w) t += red[w];
+        atomicAdd(a.dscale + h, t);
+      }
+      for (int r = tid; r < Cf::NTAB; r += Cf::THREADS) {
+        const int dy = r / TW - (WS - 1), dx = r % TW - (WS - 1);
+        float sum = 0.f;
+        for (int key = lo; key < lo + NP / 2 && key < N; ++key) {
+          const int yk = key / WS, xk = key - yk * WS;
+          const int yq = yk + dy, xq = xk + dx;
+          if (yq >= 0 && yq < WS && xq >= 0 && xq < WS) sum += stg[(key - lo) * NP + yq * WS + xq];
+        }
+        if (sum != 0.f) atomicAdd(a.dtable16 + (int64_t)r * a.nH + h, sum);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int n = 0; n < NREG; ++n) db[n][0] = db[n][1] = db[n][2] = db[n][3] = 0.f;
+#pragma unroll
+    for (int n = 0; n < DBS * 2; ++n) dbs[n * Cf::THREADS] = make_float2(0.f, 0.f);
+  };
+
+#pragma unroll 1
+  for (int i = 0;; ++i, item_next(a, p)) {        // one extra round after the last item: the final flush (single call site)
+    const int stage = i % kBwdStages;
+    const bool done = i >= nit;
+    ptx::cp_async_wait<0>();                      // this thread's copies of item i have landed
+    __syncthreads();                              // (B1) everybody's; every warp is done with item i - 1 (panel, other stage)
+    if (done || p.h != cur_h) {                   // CTA-uniform
+      if (cur_h >= 0) flush_head(cur_h);
+      if (done) break;
+      for (int t = tid; t < Cf::NTAB; t += Cf::THREADS) tab[t] = a.table16[(int64_t)t * a.nH + p.h] * kLog2e;
+      sc = a.scale[p.h];
+      scale2 = sc * kLog2e;
+      cur_h = p.h;
+      __syncthreads();
+    }
+    if (i + 1 < nit) prefetch(i + 1);
+    ptx::cp_async_commit();
+
+    const bool need_mask = g.shift > 0 && (p.wh == g.nWh - 1 || p.ww == g.nWw - 1);
+    const uint32_t q_s = base_u32 + (uint32_t)stage * Bc::STAGE_TILES, k_s = q_s + TILE, v_s = k_s + TILE, g_s = v_s + TILE;
+    const int* tokS = tokm + stage * NP;
+    const int* ridS = ridm + stage * NP;
+    const float4* qm4 = reinterpret_cast<const float4*>(qmeta + stage * NP);
+    const int tokA = tokS[rA], tokB = tokS[rB];
+
+    // ------------------------------------------------------------------ phase 1: this warp's 16 keys x all queries
+    {
+      // bias entry of (query, key) = tab[kof(query) - kof(key) + (WS-1)(TW+1)]
+      const uint32_t tab_s = ptx::smem_u32(tab) + 4u * (uint32_t)((WS - 1) * (TW + 1));
+      const uint32_t tabA = tab_s - (uint32_t)kofk[rA], tabB = tab_s - (uint32_t)kofk[rB];
+      const int ridA = ridS[rA], ridB = ridS[rB];
+      uint32_t ka[2][4], va[2][4];
+      ldsm4(ka[0], k_s + la_off);
+      ldsm4(ka[1], k_s + (la_off ^ 32u));
+      ldsm4(va[0], v_s + la_off);
+      ldsm4(va[1], v_s + (la_off ^ 32u));
+      float dk[4][4], dv[4][4];
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) {
+        dk[dn][0] = dk[dn][1] = dk[dn][2] = dk[dn][3] = 0.f;
+        dv[dn][0] = dv[dn][1] = dv[dn][2] = dv[dn][3] = 0.f;
+      }
+      auto sweep = [&](auto mask_c) {
+        constexpr bool MASK = decltype(mask_c)::value;
+#pragma unroll
+        for (int c = 0; c < NT8 / 2; ++c) {         // 16 queries per step
+          float st[2][4], dp[2][4];
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+            st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
+            dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+            uint32_t b[4];
+            ldsm4(b, q_s + (uint32_t)(c * 16 + n * 8) * 64u + lk_off);
+            mma16816(st[n], ka[0], b[0], b[1]);
+            mma16816(st[n], ka[1], b[2], b[3]);
+            ldsm4(b, g_s + (uint32_t)(c * 16 + n * 8) * 64u + lk_off);
+            mma16816(dp[n], va[0], b[0], b[1]);
+            mma16816(dp[n], va[1], b[2], b[3]);
+          }
+          uint32_t aP[4], aD[4];
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+            const int qcol = c * 16 + n * 8 + 2 * tq;
+            const float4 m = qm4[(c * 16 + n * 8) / 2 + tq];             // {lse, D} of queries qcol, qcol + 1
+            const int2 kq = *reinterpret_cast<const int2*>(kofk + qcol);
+            const uint32_t aA0 = tabA + (uint32_t)kq.x, aB0 = tabB + (uint32_t)kq.x;
+            const uint32_t aA1 = (WS % 2 == 0) ? aA0 + 4u : tabA + (uint32_t)kq.y;
+            const uint32_t aB1 = (WS % 2 == 0) ? aB0 + 4u : tabB + (uint32_t)kq.y;
+            float s2[4] = {fmaf(st[n][0], scale2, lds32(aA0)), fmaf(st[n][1], scale2, lds32(aA1)),
+                           fmaf(st[n][2], scale2, lds32(aB0)), fmaf(st[n][3], scale2, lds32(aB1))};
+            if (MASK) {
+              const int2 rr = *reinterpret_cast<const int2*>(ridS + qcol);
+              if (rr.x != ridA) s2[0] += kMaskLog2;
+              if (rr.y != ridA) s2[1] += kMaskLog2;
+              if (rr.x != ridB) s2[2] += kMaskLog2;
+              if (rr.y != ridB) s2[3] += kMaskLog2;
+            }
+            float pv[4], ds[4];
+            pv[0] = ex2f(fmaf(m.x, -kLog2e, s2[0]));
+            pv[1] = ex2f(fmaf(m.z, -kLog2e, s2[1]));
+            pv[2] = ex2f(fmaf(m.x, -kLog2e, s2[2]));
+            pv[3] = ex2f(fmaf(m.z, -kLog2e, s2[3]));
+            if (Cf::RAGGED) {                       // key rows beyond the window
+              if (rA >= N) pv[0] = pv[1] = 0.f;
+              if (rB >= N) pv[2] = pv[3] = 0.f;
+            }
+            ds[0] = pv[0] * (dp[n][0] - m.y);
+            ds[1] = pv[1] * (dp[n][1] - m.w);
+            ds[2] = pv[2] * (dp[n][2] - m.y);
+            ds[3] = pv[3] * (dp[n][3] - m.w);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dsc = fmaf(ds[e], st[n][e], dsc);
+            if (c * 2 + n < NREG) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) db[c * 2 + n < NREG ? c * 2 + n : 0][e] += ds[e];
+            } else {
+              float2* slot = dbs + ((c * 2 + n - NREG) * 2) * Cf::THREADS;
+              float2 u = slot[0], w = slot[Cf::THREADS];
+              u.x += ds[0]; u.y += ds[1]; w.x += ds[2]; w.y += ds[3];
+              slot[0] = u; slot[Cf::THREADS] = w;
+            }
+            aP[2 * n] = pack2(pv[0], pv[1]);
+            aP[2 * n + 1] = pack2(pv[2], pv[3]);
+            aD[2 * n] = pack2(ds[0], ds[1]);
+            aD[2 * n + 1] = pack2(ds[2], ds[3]);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(panel_s + pw_offA + (uint32_t)(c * 16 + n * 8) * 2u), "r"(aD[2 * n]) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(panel_s + pw_offB + (uint32_t)(c * 16 + n * 8) * 2u), "r"(aD[2 * n + 1]) : "memory");
+          }
+          // dV += P^T dO, dK += dS^T Q over these 16 queries
+          const uint32_t row16 = (uint32_t)(c * 16) * 64u;
+          uint32_t b[4];
+          ldsm4t(b, g_s + row16 + lv_off0);
+          mma16816(dv[0], aP, b[0], b[1]);
+          mma16816(dv[1], aP, b[2], b[3]);
+          ldsm4t(b, g_s + row16 + lv_off2);
+          mma16816(dv[2], aP, b[0], b[1]);
+          mma16816(dv[3], aP, b[2], b[3]);
+          ldsm4t(b, q_s + row16 + lv_off0);
+          mma16816(dk[0], aD, b[0], b[1]);
+          mma16816(dk[1], aD, b[2], b[3]);
+          ldsm4t(b, q_s + row16 + lv_off2);
+          mma16816(dk[2], aD, b[0], b[1]);
+          mma16816(dk[3], aD, b[2], b[3]);
+        }
+      };
+      if (need_mask) sweep(std::true_type{}); else sweep(std::false_type{});
+
+      // ---- dV, dK of the warp's 16 keys.  k_hat of row g / g + 8 sits in the A fragments at the accumulator's columns.
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int t = half ? tokB : tokA;
+        // (the quad sum runs on every lane: a pad row's lanes must not skip a full-mask shuffle)
+        float kh[4][2], dot = 0.f;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) {
+          const uint32_t w = ka[dn >> 1][(dn & 1) * 2 + half];
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+          kh[dn][0] = f.x; kh[dn][1] = f.y;
+          dot = fmaf(dk[dn][2 * half], f.x, dot);
+          dot = fmaf(dk[dn][2 * half + 1], f.y, dot);
+        }
+        dot = quad_sum(dot) * sc;
+        if (t >= 0) {
+          const float invn = a.inv_norm[((int64_t)t * 2 + 1) * a.nH + p.h];   // 1 / ||k||
+          uint32_t* dkd = reinterpret_cast<uint32_t*>(a.dqkv + (int64_t)t * C3 + a.C + p.h * HD) + tq;
+          uint32_t* dvd = reinterpret_cast<uint32_t*>(a.dqkv + (int64_t)t * C3 + 2 * a.C + p.h * HD) + tq;
+#pragma unroll
+          for (int dn = 0; dn < 4; ++dn) {
+            dkd[dn * 4] = pack2((dk[dn][2 * half] * sc - kh[dn][0] * dot) * invn, (dk[dn][2 * half + 1] * sc - kh[dn][1] * dot) * invn);
+            dvd[dn * 4] = pack2(dv[dn][2 * half], dv[dn][2 * half + 1]);
+          }
+        } else if (t == -1) {
+#pragma unroll
+          for (int dn = 0; dn < 4; ++dn) {
+            dvps[(dn * 2) * Cf::THREADS] += dv[dn][2 * half];
+            dvps[(dn * 2 + 1) * Cf::THREADS] += dv[dn][2 * half + 1];
+          }
+        }
+      }
+    }
+    __syncthreads();                              // (B2) the dS panel is complete
+
+    // ------------------------------------------------------------------ phase 2: this warp's 16 queries, dQ = dS K
+    {
+      float dq[4][4];
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) dq[dn][0] = dq[dn][1] = dq[dn][2] = dq[dn][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < NP / 16; ++ks) {
+        uint32_t ad[4], b[4];
+        ldsm4t(ad, panel_s + (uint32_t)(ks * 16) * PSTRIDE + pr_off);
+        ldsm4t(b, k_s + (uint32_t)(ks * 16) * 64u + lv_off0);
+        mma16816(dq[0], ad, b[0], b[1]);
+        mma16816(dq[1], ad, b[2], b[3]);
+        ldsm4t(b, k_s + (uint32_t)(ks * 16) * 64u + lv_off2);
+        mma16816(dq[2], ad, b[0], b[1]);
+        mma16816(dq[3], ad, b[2], b[3]);
+      }
+      uint32_t qa[2][4];
+      ldsm4(qa[0], q_s + la_off);
+      ldsm4(qa[1], q_s + (la_off ^ 32u));
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int t = half ? tokB : tokA;
+        float qh[4][2], dot = 0.f;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) {
+          const uint32_t w = qa[dn >> 1][(dn & 1) * 2 + half];
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+          qh[dn][0] = f.x; qh[dn][1] = f.y;
+          dot = fmaf(dq[dn][2 * half], f.x, dot);
+          dot = fmaf(dq[dn][2 * half + 1], f.y, dot);
+        }
+        dot = quad_sum(dot) * sc;
+        if (t < 0) continue;
+        const float invn = a.inv_norm[((int64_t)t * 2 + 0) * a.nH + p.h];     // 1 / ||q||
+        uint32_t* dqd = reinterpret_cast<uint32_t*>(a.dqkv + (int64_t)t * C3 + p.h * HD) + tq;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn)
+          dqd[dn * 4] = pack2((dq[dn][2 * half] * sc - qh[dn][0] * dot) * invn, (dq[dn][2 * half + 1] * sc - qh[dn][1] * dot) * invn);
+      }
+    }
+  }
+}
+
+template <int WS>
+int launch_mma_bwd(const MmaArgs& a, cudaStream_t st) {
+  using Cf = MCfg<WS>;
+  const size_t smem = BCfg<WS>::SMEM;
+  BSW_REQUIRE(smem <= 227 * 1024, "attn_bwd(mma): window %dx%d needs %zu bytes of shared memory", WS, WS, smem);
+  BSW_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  BSW_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel<WS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  int64_t grid = sm_count();
+  if (grid > a.nitems) grid = a.nitems;
+  attn_mma_bwd_kernel<WS><<<(unsigned)grid, Cf::THREADS, smem, st>>>(a);
+  BSW_LAUNCH_CHECK();
+  return B200SWIN_OK;
+}
+
 int fill_mma_args(MmaArgs* a, int B, int H, int W, int C, int nH, int ws, int shift) {
   BSW_REQUIRE(B > 0 && H > 0 && W > 0 && nH > 0, "attn(mma): bad dimension");
   BSW_REQUIRE(C == nH * HD, "attn(mma): head_dim must be 32 (C=%d, nH=%d)", C, nH);
@@ -418,6 +835,34 @@ int attn_fwd_mma(const void* qkv, void* out, void* out_lo, float* lse, const flo
     default: break;
   }
   set_error("attn_fwd(mma): window %dx%d not instantiated", ws, ws);
+  return B200SWIN_EINVAL;
+}
+
+bool attn_bwd_mma_supported(int ws) { return ws == 12; }
+
+// D = <dO, O> per (token, head) (attn_bwd_ws.cu)
+int attn_bwd_prep(const void* dout, const void* out, const void* out_lo, float* dvec, int64_t n, cudaStream_t st);
+
+size_t attn_bwd_mma_workspace_bytes(int B, int H, int W, int nH) { return (size_t)B * H * W * nH * sizeof(float); }
+
+int attn_bwd_mma(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
+                 const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
+                 float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH,
+                 int ws, int shift, cudaStream_t st) {
+  BSW_REQUIRE(workspace, "attn_bwd(mma): workspace for D = <dO, O> missing");
+  MmaArgs a = {};
+  int rc = fill_mma_args(&a, B, H, W, C, nH, ws, shift);
+  if (rc) return rc;
+  a.qkv = (const __nv_bfloat16*)qkv; a.dout = (const __nv_bfloat16*)dout; a.lse = const_cast<float*>(lse);
+  a.dvec = (const float*)workspace; a.inv_norm = inv_norm; a.table16 = table16; a.scale = scale; a.qpad = qpad;
+  a.vpad = vpad; a.dqkv = (__nv_bfloat16*)dqkv; a.dtable16 = dtable16; a.dscale = dscale; a.dvpad = dvpad;
+  rc = attn_bwd_prep(dout, out, out_lo, (float*)workspace, (int64_t)B * H * W * nH, st);
+  if (rc) return rc;
+  switch (ws) {
+    case 12: return launch_mma_bwd<12>(a, st);
+    default: break;
+  }
+  set_error("attn_bwd(mma): window %dx%d not instantiated", ws, ws);
   return B200SWIN_EINVAL;
 }
 

@@ -17,6 +17,12 @@ int attn_fwd_ws(const void* qkv, void* out, void* out_lo, float* lse, const floa
 bool attn_fwd_mma_supported(int ws);
 int attn_fwd_mma(const void* qkv, void* out, void* out_lo, float* lse, const float* table16, const float* scale, const float* qpad,
                  const float* vpad, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st);
+bool attn_bwd_mma_supported(int ws);
+size_t attn_bwd_mma_workspace_bytes(int B, int H, int W, int nH);
+int attn_bwd_mma(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
+                 const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
+                 float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH,
+                 int ws, int shift, cudaStream_t st);
 bool attn_bwd_ws_supported(int ws);
 size_t attn_bwd_ws_workspace_bytes(int B, int H, int W, int nH);
 int attn_bwd_ws(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
@@ -62,7 +68,8 @@ int attn_fwd_tc(const void* qkv, void* out, void* out_lo, float* lse, const floa
 }
 
 size_t attn_bwd_tc_workspace_bytes(int B, int H, int W, int nH, int ws) {
-  // both families need the same scratch: D = <dO, O> per (token, head)
+  // all families need the same scratch: D = <dO, O> per (token, head)
+  if (attn_bwd_mma_supported(ws)) return attn_bwd_mma_workspace_bytes(B, H, W, nH);
   return attn_bwd_ws_supported(ws) ? attn_bwd_ws_workspace_bytes(B, H, W, nH) : attn_bwd_flash_workspace_bytes(B, H, W, nH);
 }
 
@@ -77,6 +84,10 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* out_lo, const void
   BSW_REQUIRE(workspace && workspace_bytes >= attn_bwd_tc_workspace_bytes(B, H, W, nH, ws),
               "attn_bwd(tc): workspace too small (see b200swin_attn_bwd_workspace_bytes)");
   BSW_REQUIRE(family != kFamilyWs || attn_bwd_ws_supported(ws), "attn_bwd: no single-tile kernel for window %d", ws);
+  BSW_REQUIRE(family != kFamilyMma || attn_bwd_mma_supported(ws), "attn_bwd: no warp-MMA kernel for window %d", ws);
+  if ((family == kFamilyAuto || family == kFamilyMma) && attn_bwd_mma_supported(ws))
+    return attn_bwd_mma(qkv, out, out_lo, dout, lse, inv_norm, table16, scale, qpad, vpad, dqkv, dtable16, dscale, dvpad, workspace,
+                        B, H, W, C, nH, ws, shift, st);
   if ((family == kFamilyAuto || family == kFamilyWs) && attn_bwd_ws_supported(ws))
     return attn_bwd_ws(qkv, out, out_lo, dout, lse, inv_norm, table16, scale, qpad, vpad, dqkv, dtable16, dscale, dvpad, workspace,
                        B, H, W, C, nH, ws, shift, st);
