@@ -87,7 +87,7 @@ __device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -178,38 +178,37 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
 
   for (int r = tid; r < NP; r += Cf::THREADS) kofk[r] = r < N ? 4 * ((r / WS) * TW + (r % WS)) : 0;
 
-  // a thread copies the same two (row, 16-byte column) slots of every item: rows (tid >> 2) and (tid >> 2) + THREADS / 4
-  static_assert(NP * 4 == 2 * Cf::THREADS, "two slots per thread");
-  const int pc = tid & 3, prow0 = tid >> 2, prow1 = prow0 + Cf::THREADS / 4;
-  const int py0 = prow0 / WS, px0 = prow0 - py0 * WS, py1 = prow1 / WS, px1 = prow1 - py1 * WS;
-  const uint32_t poff0 = sw64(prow0, pc), poff1 = sw64(prow1, pc);
+  // a thread copies the same half row (32 bytes of q, k and v) of every item: row tid / 2, dims 16 (tid & 1) ...
+  static_assert(NP * 2 == Cf::THREADS, "two threads per row");
+  const int prow = tid >> 1, py = prow / WS, px = prow - py * WS;
+  const uint32_t poff = sw64(prow, (tid & 1) * 2);               // second 16 bytes: poff ^ 16
   ItemPos pp = item_pos(a, it0);                 // cursor of the prefetch stream
   auto prefetch = [&](int i) {
     const int stage = i % kFwdStages;
     unsigned char* q0 = tiles + (size_t)stage * STAGE;
     const uint32_t q0_s = tiles_s + (uint32_t)stage * STAGE;
-    const float* qp = a.qpad ? a.qpad + pp.h * HD + pc * 8 : nullptr;
-    const float* vp = a.vpad ? a.vpad + pp.h * HD + pc * 8 : nullptr;
+    int region = 0, t = -2;
+    if (!Cf::RAGGED || prow < N) t = row_token<WS>(g, pp, py, px, &region);
+    if ((tid & 1) == 0) {
+      tokm[stage * NP + prow] = t;
+      ridm[stage * NP + prow] = region;
+    }
+    if (t >= 0) {
+      const __nv_bfloat16* src = a.qkv + (int64_t)t * C3 + pp.h * HD + (tid & 1) * 16;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int row = k ? prow1 : prow0;
-      const uint32_t off = k ? poff1 : poff0;
-      int region = 0, t = -2;
-      if (!Cf::RAGGED || row < N) t = row_token<WS>(g, pp, k ? py1 : py0, k ? px1 : px0, &region);
-      if (pc == 0) {
-        tokm[stage * NP + row] = t;
-        ridm[stage * NP + row] = region;
+      for (int k = 0; k < 3; ++k) {
+        ptx::cp_async_16(q0_s + k * TILE + poff, src + k * a.C);
+        ptx::cp_async_16(q0_s + k * TILE + (poff ^ 16u), src + k * a.C + 8);
       }
-      if (t >= 0) {
-        const __nv_bfloat16* src = a.qkv + (int64_t)t * C3 + pp.h * HD + pc * 8;
-        ptx::cp_async_16(q0_s + off, src);
-        ptx::cp_async_16(q0_s + TILE + off, src + a.C);
-        ptx::cp_async_16(q0_s + 2 * TILE + off, src + 2 * a.C);
-      } else {
-        put16(q0, q0_s, off, nullptr, t == -1 ? qp : nullptr);
-        put16(q0 + TILE, q0_s + TILE, off, nullptr, nullptr);
-        put16(q0 + 2 * TILE, q0_s + 2 * TILE, off, nullptr, t == -1 ? vp : nullptr);
-      }
+    } else {
+      const float* qp = (t == -1 && a.qpad) ? a.qpad + pp.h * HD + (tid & 1) * 16 : nullptr;
+      const float* vp = (t == -1 && a.vpad) ? a.vpad + pp.h * HD + (tid & 1) * 16 : nullptr;
+      put16(q0, q0_s, poff, nullptr, qp);
+      put16(q0, q0_s, poff ^ 16u, nullptr, qp ? qp + 8 : nullptr);
+      put16(q0 + TILE, q0_s + TILE, poff, nullptr, nullptr);
+      put16(q0 + TILE, q0_s + TILE, poff ^ 16u, nullptr, nullptr);
+      put16(q0 + 2 * TILE, q0_s + 2 * TILE, poff, nullptr, vp);
+      put16(q0 + 2 * TILE, q0_s + 2 * TILE, poff ^ 16u, nullptr, vp ? vp + 8 : nullptr);
     }
     item_next(a, pp);
   };
@@ -383,7 +382,7 @@ int launch_mma_fwd(const MmaArgs& a, cudaStream_t st) {
   using Cf = MCfg<WS>;
   const size_t smem = mma_fwd_smem<WS>();
   BSW_CUDA(cudaFuncSetAttribute(attn_mma_fwd_kernel<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BSW_CUDA(cudaFuncSetAttribute(attn_mma_fwd_kernel<WS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  BSW_CUDA(cudaFuncSetAttribute(attn_mma_fwd_kernel<WS>, cudaFuncAttributePreferredSharedMemoryCarveout, 80));   // two CTAs
   int occ = (int)((227 * 1024) / (smem + 1024));
   const int occ_threads = 2048 / Cf::THREADS;
   if (occ > occ_threads) occ = occ_threads;
@@ -412,7 +411,8 @@ struct BCfg {
   static constexpr uint32_t STAGE_TILES = 4 * Cf::TILE;                       // q | k | v | dO
   static constexpr uint32_t PSTRIDE = Cf::NP * 2 + 16;                        // bytes per key row of the dS panel
   static constexpr uint32_t OFF_QMETA = kBwdStages * STAGE_TILES;             // [stages][NP] {lse, D}
-  static constexpr uint32_t OFF_TOK = OFF_QMETA + kBwdStages * Cf::NP * 8;    // [stages][NP]
+  static constexpr uint32_t OFF_INN = OFF_QMETA + kBwdStages * Cf::NP * 8;    // [stages][NP] {1 / ||q||, 1 / ||k||}
+  static constexpr uint32_t OFF_TOK = OFF_INN + kBwdStages * Cf::NP * 8;      // [stages][NP]
   static constexpr uint32_t OFF_RID = OFF_TOK + kBwdStages * Cf::NP * 4;      // [stages][NP]
   static constexpr uint32_t OFF_KOF = OFF_RID + kBwdStages * Cf::NP * 4;      // [NP]
   static constexpr uint32_t OFF_TAB = OFF_KOF + Cf::NP * 4;                   // [NTAB]
@@ -420,7 +420,7 @@ struct BCfg {
   static constexpr uint32_t OFF_RED = OFF_PANEL + Cf::NP * PSTRIDE;           // [NT] floats (+ pad to 16 B)
   // per-thread gradient sums that do not fit the register file (168 registers per thread with nine warps: three warps on
   // one SM sub-partition): the bias-gradient sums of the last DBS column tiles and the v_bias gradient, [slot][thread]
-  static constexpr int DBS = Cf::NTILES8 >= 18 ? 10 : 0;                       // column tiles (of 8 queries) kept in smem
+  static constexpr int DBS = Cf::NTILES8 >= 18 ? 12 : 0;                       // column tiles (of 8 queries) kept in smem
   static constexpr uint32_t OFF_DBS = OFF_RED + (Cf::NT * 4 + 15) / 16 * 16;  // [DBS * 2][THREADS] float2
   static constexpr uint32_t OFF_DVP = OFF_DBS + DBS * 2 * Cf::THREADS * 8;    // [8][THREADS] float
   static constexpr uint32_t SMEM = OFF_DVP + 8 * Cf::THREADS * 4 + 128;
@@ -438,6 +438,7 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
   const uint32_t base_u32 = (ptx::smem_u32(smem_dyn) + 127u) & ~127u;
   unsigned char* sm = smem_dyn + (base_u32 - ptx::smem_u32(smem_dyn));
   float2* qmeta = reinterpret_cast<float2*>(sm + Bc::OFF_QMETA);
+  float2* innorm = reinterpret_cast<float2*>(sm + Bc::OFF_INN);
   int* tokm = reinterpret_cast<int*>(sm + Bc::OFF_TOK);
   int* ridm = reinterpret_cast<int*>(sm + Bc::OFF_RID);
   int* kofk = reinterpret_cast<int*>(sm + Bc::OFF_KOF);
@@ -458,50 +459,59 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
 
   for (int r = tid; r < NP; r += Cf::THREADS) kofk[r] = r < N ? 4 * ((r / WS) * TW + (r % WS)) : 0;
 
-  static_assert(NP * 4 == 2 * Cf::THREADS, "two slots per thread");
-  const int pc = tid & 3, prow0 = tid >> 2, prow1 = prow0 + Cf::THREADS / 4;
-  const int py0 = prow0 / WS, px0 = prow0 - py0 * WS, py1 = prow1 / WS, px1 = prow1 - py1 * WS;
-  const uint32_t poff0 = sw64(prow0, pc), poff1 = sw64(prow1, pc);
+  static_assert(NP * 2 == Cf::THREADS, "two threads per row");
+  const int prow = tid >> 1, py = prow / WS, px = prow - py * WS;
+  const uint32_t poff = sw64(prow, (tid & 1) * 2);               // second 16 bytes: poff ^ 16
   ItemPos pp = item_pos(a, it0);
   auto prefetch = [&](int i) {
     const int stage = i % kBwdStages;
     unsigned char* q0 = sm + (size_t)stage * Bc::STAGE_TILES;
     const uint32_t q0_s = base_u32 + (uint32_t)stage * Bc::STAGE_TILES;
-    const float* lse_it = a.lse + (pp.win * a.nH + pp.h) * N;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int row = k ? prow1 : prow0;
-      const uint32_t off = k ? poff1 : poff0;
-      int region = 0, t = -2;
-      if (!Cf::RAGGED || row < N) t = row_token<WS>(g, pp, k ? py1 : py0, k ? px1 : px0, &region);
-      if (pc == 0) {
-        tokm[stage * NP + row] = t;
-        ridm[stage * NP + row] = region;
-        float2* qm = qmeta + stage * NP + row;
-        const uint32_t qm_s = base_u32 + Bc::OFF_QMETA + (uint32_t)(stage * NP + row) * 8u;
-        if (t >= 0) {
-          ptx::cp_async_4(qm_s, lse_it + row);
-          ptx::cp_async_4(qm_s + 4, a.dvec + (int64_t)t * a.nH + pp.h);
-        } else if (t == -1) {
-          ptx::cp_async_4(qm_s, lse_it + row);
-          qm->y = 0.f;
-        } else {
-          *qm = make_float2(INFINITY, 0.f);          // beyond the window: P = 0
-        }
-      }
+    int region = 0, t = -2;
+    if (!Cf::RAGGED || prow < N) t = row_token<WS>(g, pp, py, px, &region);
+    if ((tid & 1) == 0) {
+      // per-row scalars: {lse, D = <dO, O>} and {1 / ||q||, 1 / ||k||}
+      tokm[stage * NP + prow] = t;
+      ridm[stage * NP + prow] = region;
+      float2* qm = qmeta + stage * NP + prow;
+      float2* im = innorm + stage * NP + prow;
+      const uint32_t qm_s = base_u32 + Bc::OFF_QMETA + (uint32_t)(stage * NP + prow) * 8u;
+      const uint32_t im_s = base_u32 + Bc::OFF_INN + (uint32_t)(stage * NP + prow) * 8u;
       if (t >= 0) {
-        const __nv_bfloat16* src = a.qkv + (int64_t)t * C3 + pp.h * HD + pc * 8;
-        ptx::cp_async_16(q0_s + off, src);
-        ptx::cp_async_16(q0_s + TILE + off, src + a.C);
-        ptx::cp_async_16(q0_s + 2 * TILE + off, src + 2 * a.C);
-        ptx::cp_async_16(q0_s + 3 * TILE + off, a.dout + (int64_t)t * a.C + pp.h * HD + pc * 8);
+        ptx::cp_async_4(qm_s, a.lse + (pp.win * a.nH + pp.h) * N + prow);
+        ptx::cp_async_4(qm_s + 4, a.dvec + (int64_t)t * a.nH + pp.h);
+        ptx::cp_async_4(im_s, a.inv_norm + ((int64_t)t * 2 + 0) * a.nH + pp.h);
+        ptx::cp_async_4(im_s + 4, a.inv_norm + ((int64_t)t * 2 + 1) * a.nH + pp.h);
+      } else if (t == -1) {
+        ptx::cp_async_4(qm_s, a.lse + (pp.win * a.nH + pp.h) * N + prow);
+        qm->y = 0.f;
+        *im = make_float2(0.f, 0.f);
       } else {
-        const float* qp = (t == -1 && a.qpad) ? a.qpad + pp.h * HD + pc * 8 : nullptr;
-        const float* vp = (t == -1 && a.vpad) ? a.vpad + pp.h * HD + pc * 8 : nullptr;
-        put16(q0, q0_s, off, nullptr, qp);
-        put16(q0 + TILE, q0_s + TILE, off, nullptr, nullptr);
-        put16(q0 + 2 * TILE, q0_s + 2 * TILE, off, nullptr, vp);
-        put16(q0 + 3 * TILE, q0_s + 3 * TILE, off, nullptr, nullptr);
+        *qm = make_float2(INFINITY, 0.f);            // beyond the window: P = 0
+        *im = make_float2(0.f, 0.f);
+      }
+    }
+    if (t >= 0) {
+      const __nv_bfloat16* src = a.qkv + (int64_t)t * C3 + pp.h * HD + (tid & 1) * 16;
+      const __nv_bfloat16* gsrc = a.dout + (int64_t)t * a.C + pp.h * HD + (tid & 1) * 16;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        ptx::cp_async_16(q0_s + k * TILE + poff, src + k * a.C);
+        ptx::cp_async_16(q0_s + k * TILE + (poff ^ 16u), src + k * a.C + 8);
+      }
+      ptx::cp_async_16(q0_s + 3 * TILE + poff, gsrc);
+      ptx::cp_async_16(q0_s + 3 * TILE + (poff ^ 16u), gsrc + 8);
+    } else {
+      const float* qp = (t == -1 && a.qpad) ? a.qpad + pp.h * HD + (tid & 1) * 16 : nullptr;
+      const float* vp = (t == -1 && a.vpad) ? a.vpad + pp.h * HD + (tid & 1) * 16 : nullptr;
+      put16(q0, q0_s, poff, nullptr, qp);
+      put16(q0, q0_s, poff ^ 16u, nullptr, qp ? qp + 8 : nullptr);
+      put16(q0 + 2 * TILE, q0_s + 2 * TILE, poff, nullptr, vp);
+      put16(q0 + 2 * TILE, q0_s + 2 * TILE, poff ^ 16u, nullptr, vp ? vp + 8 : nullptr);
+#pragma unroll
+      for (int k = 1; k < 4; k += 2) {
+        put16(q0 + k * TILE, q0_s + k * TILE, poff, nullptr, nullptr);
+        put16(q0 + k * TILE, q0_s + k * TILE, poff ^ 16u, nullptr, nullptr);
       }
     }
     item_next(a, pp);
@@ -630,40 +640,91 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
         dk[dn][0] = dk[dn][1] = dk[dn][2] = dk[dn][3] = 0.f;
         dv[dn][0] = dv[dn][1] = dv[dn][2] = dv[dn][3] = 0.f;
       }
+      // S^T and dP^T of 16 queries: both k-steps of every accumulator apart from each other (a dependent HMMA pair stalls)
+      auto sdp = [&](int c, float (&st)[2][4], float (&dp)[2][4]) {
+        uint32_t bq[2][4], bg[2][4];
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          ldsm4(bq[n], q_s + (uint32_t)(c * 16 + n * 8) * 64u + lk_off);
+          ldsm4(bg[n], g_s + (uint32_t)(c * 16 + n * 8) * 64u + lk_off);
+          st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
+          dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+        }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+            mma16816(st[n], ka[ks], bq[n][2 * ks], bq[n][2 * ks + 1]);
+            mma16816(dp[n], va[ks], bg[n][2 * ks], bg[n][2 * ks + 1]);
+          }
+      };
       auto sweep = [&](auto mask_c) {
         constexpr bool MASK = decltype(mask_c)::value;
+        float stb[2][2][4], dpb[2][2][4];           // double-buffered: the MMAs of step c + 1 run under the element work of step c
+        sdp(0, stb[0], dpb[0]);
+        // Shared-memory stores of a step are issued only AFTER the loads of the next step: neither compiler can prove
+        // that the panel / gradient-sum stores do not alias the table and per-query loads, so a store that waits for
+        // the end of a step's dependency chain would hold back every later load and serialise the steps.
+        uint32_t pendD[4] = {0, 0, 0, 0};
+        float2 pendS[4];
 #pragma unroll
-        for (int c = 0; c < NT8 / 2; ++c) {         // 16 queries per step
-          float st[2][4], dp[2][4];
+        for (int c = 0; c <= NT8 / 2; ++c) {        // 16 queries per step; the extra round only drains the stores
+          const bool live = c < NT8 / 2;
+          float (&st)[2][4] = stb[c & 1];
+          float (&dp)[2][4] = dpb[c & 1];
+          uint32_t bg0[4], bg2[4], bq0[4], bq2[4];
+          float4 mm[2];
+          float bias[2][4];
+          int2 rr[2];
+          float2 sl[4];
+          if (live) {
+            if (c + 1 < NT8 / 2) sdp(c + 1, stb[(c + 1) & 1], dpb[(c + 1) & 1]);
+            // B operands of this step's dV / dK contractions: in flight during the element work
+            const uint32_t row16 = (uint32_t)(c * 16) * 64u;
+            ldsm4t(bg0, g_s + row16 + lv_off0);
+            ldsm4t(bg2, g_s + row16 + lv_off2);
+            ldsm4t(bq0, q_s + row16 + lv_off0);
+            ldsm4t(bq2, q_s + row16 + lv_off2);
 #pragma unroll
-          for (int n = 0; n < 2; ++n) {
-            st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
-            dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
-            uint32_t b[4];
-            ldsm4(b, q_s + (uint32_t)(c * 16 + n * 8) * 64u + lk_off);
-            mma16816(st[n], ka[0], b[0], b[1]);
-            mma16816(st[n], ka[1], b[2], b[3]);
-            ldsm4(b, g_s + (uint32_t)(c * 16 + n * 8) * 64u + lk_off);
-            mma16816(dp[n], va[0], b[0], b[1]);
-            mma16816(dp[n], va[1], b[2], b[3]);
+            for (int n = 0; n < 2; ++n) {
+              const int qcol = c * 16 + n * 8 + 2 * tq;
+              mm[n] = qm4[(c * 16 + n * 8) / 2 + tq];                    // {lse, D} of queries qcol, qcol + 1
+              const int2 kq = *reinterpret_cast<const int2*>(kofk + qcol);
+              const uint32_t aA0 = tabA + (uint32_t)kq.x, aB0 = tabB + (uint32_t)kq.x;
+              const uint32_t aA1 = (WS % 2 == 0) ? aA0 + 4u : tabA + (uint32_t)kq.y;
+              const uint32_t aB1 = (WS % 2 == 0) ? aB0 + 4u : tabB + (uint32_t)kq.y;
+              bias[n][0] = lds32(aA0); bias[n][1] = lds32(aA1); bias[n][2] = lds32(aB0); bias[n][3] = lds32(aB1);
+              if (MASK) rr[n] = *reinterpret_cast<const int2*>(ridS + qcol);
+              if (c * 2 + n >= NREG) {
+                sl[2 * n] = dbs[((c * 2 + n - NREG) * 2) * Cf::THREADS];
+                sl[2 * n + 1] = dbs[((c * 2 + n - NREG) * 2 + 1) * Cf::THREADS];
+              }
+            }
           }
-          uint32_t aP[4], aD[4];
+          if (c > 0) {                              // the stores of step c - 1
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+              const uint32_t col = (uint32_t)((c - 1) * 16 + n * 8) * 2u;
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(panel_s + pw_offA + col), "r"(pendD[2 * n]) : "memory");
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(panel_s + pw_offB + col), "r"(pendD[2 * n + 1]) : "memory");
+              if ((c - 1) * 2 + n >= NREG) {
+                dbs[(((c - 1) * 2 + n - NREG) * 2) * Cf::THREADS] = pendS[2 * n];
+                dbs[(((c - 1) * 2 + n - NREG) * 2 + 1) * Cf::THREADS] = pendS[2 * n + 1];
+              }
+            }
+          }
+          if (!live) break;
+          uint32_t aP[4];
 #pragma unroll
           for (int n = 0; n < 2; ++n) {
-            const int qcol = c * 16 + n * 8 + 2 * tq;
-            const float4 m = qm4[(c * 16 + n * 8) / 2 + tq];             // {lse, D} of queries qcol, qcol + 1
-            const int2 kq = *reinterpret_cast<const int2*>(kofk + qcol);
-            const uint32_t aA0 = tabA + (uint32_t)kq.x, aB0 = tabB + (uint32_t)kq.x;
-            const uint32_t aA1 = (WS % 2 == 0) ? aA0 + 4u : tabA + (uint32_t)kq.y;
-            const uint32_t aB1 = (WS % 2 == 0) ? aB0 + 4u : tabB + (uint32_t)kq.y;
-            float s2[4] = {fmaf(st[n][0], scale2, lds32(aA0)), fmaf(st[n][1], scale2, lds32(aA1)),
-                           fmaf(st[n][2], scale2, lds32(aB0)), fmaf(st[n][3], scale2, lds32(aB1))};
+            const float4 m = mm[n];
+            float s2[4] = {fmaf(st[n][0], scale2, bias[n][0]), fmaf(st[n][1], scale2, bias[n][1]),
+                           fmaf(st[n][2], scale2, bias[n][2]), fmaf(st[n][3], scale2, bias[n][3])};
             if (MASK) {
-              const int2 rr = *reinterpret_cast<const int2*>(ridS + qcol);
-              if (rr.x != ridA) s2[0] += kMaskLog2;
-              if (rr.y != ridA) s2[1] += kMaskLog2;
-              if (rr.x != ridB) s2[2] += kMaskLog2;
-              if (rr.y != ridB) s2[3] += kMaskLog2;
+              if (rr[n].x != ridA) s2[0] += kMaskLog2;
+              if (rr[n].y != ridA) s2[1] += kMaskLog2;
+              if (rr[n].x != ridB) s2[2] += kMaskLog2;
+              if (rr[n].y != ridB) s2[3] += kMaskLog2;
             }
             float pv[4], ds[4];
             pv[0] = ex2f(fmaf(m.x, -kLog2e, s2[0]));
@@ -678,39 +739,27 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
             ds[1] = pv[1] * (dp[n][1] - m.w);
             ds[2] = pv[2] * (dp[n][2] - m.y);
             ds[3] = pv[3] * (dp[n][3] - m.w);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) dsc = fmaf(ds[e], st[n][e], dsc);
             if (c * 2 + n < NREG) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) db[c * 2 + n < NREG ? c * 2 + n : 0][e] += ds[e];
             } else {
-              float2* slot = dbs + ((c * 2 + n - NREG) * 2) * Cf::THREADS;
-              float2 u = slot[0], w = slot[Cf::THREADS];
-              u.x += ds[0]; u.y += ds[1]; w.x += ds[2]; w.y += ds[3];
-              slot[0] = u; slot[Cf::THREADS] = w;
+              pendS[2 * n] = make_float2(sl[2 * n].x + ds[0], sl[2 * n].y + ds[1]);
+              pendS[2 * n + 1] = make_float2(sl[2 * n + 1].x + ds[2], sl[2 * n + 1].y + ds[3]);
             }
             aP[2 * n] = pack2(pv[0], pv[1]);
             aP[2 * n + 1] = pack2(pv[2], pv[3]);
-            aD[2 * n] = pack2(ds[0], ds[1]);
-            aD[2 * n + 1] = pack2(ds[2], ds[3]);
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(panel_s + pw_offA + (uint32_t)(c * 16 + n * 8) * 2u), "r"(aD[2 * n]) : "memory");
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(panel_s + pw_offB + (uint32_t)(c * 16 + n * 8) * 2u), "r"(aD[2 * n + 1]) : "memory");
+            pendD[2 * n] = pack2(ds[0], ds[1]);
+            pendD[2 * n + 1] = pack2(ds[2], ds[3]);
           }
-          // dV += P^T dO, dK += dS^T Q over these 16 queries
-          const uint32_t row16 = (uint32_t)(c * 16) * 64u;
-          uint32_t b[4];
-          ldsm4t(b, g_s + row16 + lv_off0);
-          mma16816(dv[0], aP, b[0], b[1]);
-          mma16816(dv[1], aP, b[2], b[3]);
-          ldsm4t(b, g_s + row16 + lv_off2);
-          mma16816(dv[2], aP, b[0], b[1]);
-          mma16816(dv[3], aP, b[2], b[3]);
-          ldsm4t(b, q_s + row16 + lv_off0);
-          mma16816(dk[0], aD, b[0], b[1]);
-          mma16816(dk[1], aD, b[2], b[3]);
-          ldsm4t(b, q_s + row16 + lv_off2);
-          mma16816(dk[2], aD, b[0], b[1]);
-          mma16816(dk[3], aD, b[2], b[3]);
+          // dV += P^T dO, dK += dS^T Q over these 16 queries (eight independent accumulators)
+          mma16816(dv[0], aP, bg0[0], bg0[1]);
+          mma16816(dv[1], aP, bg0[2], bg0[3]);
+          mma16816(dv[2], aP, bg2[0], bg2[1]);
+          mma16816(dv[3], aP, bg2[2], bg2[3]);
+          mma16816(dk[0], pendD, bq0[0], bq0[1]);
+          mma16816(dk[1], pendD, bq0[2], bq0[3]);
+          mma16816(dk[2], pendD, bq2[0], bq2[1]);
+          mma16816(dk[3], pendD, bq2[2], bq2[3]);
         }
       };
       if (need_mask) sweep(std::true_type{}); else sweep(std::false_type{});
@@ -731,7 +780,7 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
         }
         dot = quad_sum(dot) * sc;
         if (t >= 0) {
-          const float invn = a.inv_norm[((int64_t)t * 2 + 1) * a.nH + p.h];   // 1 / ||k||
+          const float invn = innorm[stage * NP + (half ? rB : rA)].y;          // 1 / ||k||
           uint32_t* dkd = reinterpret_cast<uint32_t*>(a.dqkv + (int64_t)t * C3 + a.C + p.h * HD) + tq;
           uint32_t* dvd = reinterpret_cast<uint32_t*>(a.dqkv + (int64_t)t * C3 + 2 * a.C + p.h * HD) + tq;
 #pragma unroll
@@ -781,9 +830,12 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
           dot = fmaf(dq[dn][2 * half], f.x, dot);
           dot = fmaf(dq[dn][2 * half + 1], f.y, dot);
         }
-        dot = quad_sum(dot) * sc;
+        dot = quad_sum(dot);
+        // gradient of the temperature: sum_k dS[q, k] cos[q, k] = <q_hat, sum_k dS[q, k] k_hat> = this very dot product
+        if (tq == 0) dsc += dot;
+        dot *= sc;
         if (t < 0) continue;
-        const float invn = a.inv_norm[((int64_t)t * 2 + 0) * a.nH + p.h];     // 1 / ||q||
+        const float invn = innorm[stage * NP + (half ? rB : rA)].x;            // 1 / ||q||
         uint32_t* dqd = reinterpret_cast<uint32_t*>(a.dqkv + (int64_t)t * C3 + p.h * HD) + tq;
 #pragma unroll
         for (int dn = 0; dn < 4; ++dn)
@@ -799,7 +851,7 @@ int launch_mma_bwd(const MmaArgs& a, cudaStream_t st) {
   const size_t smem = BCfg<WS>::SMEM;
   BSW_REQUIRE(smem <= 227 * 1024, "attn_bwd(mma): window %dx%d needs %zu bytes of shared memory", WS, WS, smem);
   BSW_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BSW_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel<WS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  // (no carve-out preference: the driver sizes shared memory to the request and the rest stays L1 for the few spills)
   int64_t grid = sm_count();
   if (grid > a.nitems) grid = a.nitems;
   attn_mma_bwd_kernel<WS><<<(unsigned)grid, Cf::THREADS, smem, st>>>(a);
