@@ -40,6 +40,9 @@ struct MCfg {
   static constexpr int NTILES8 = NP / 8;             // 8-key column tiles of the logits
   static constexpr int CHN = (NTILES8 % 6 == 0) ? 6 : ((NTILES8 % 4 == 0) ? 4 : 2);   // column tiles per softmax chunk
   static constexpr int NCH = NTILES8 / CHN;
+  // resident CTAs per SM the kernels are compiled for: ~18 warps forward (<= 96 registers), ~12 backward (<= 168)
+  static constexpr int FWD_CTAS = NT >= 9 ? 2 : (18 / NT > 8 ? 8 : 18 / NT);
+  static constexpr int BWD_CTAS = NT >= 9 ? 1 : (12 / NT > 8 ? 8 : 12 / NT);
 };
 
 struct MmaArgs {
@@ -154,7 +157,7 @@ __device__ __forceinline__ int row_token(const WinGeom& g, const ItemPos& p, int
 constexpr int kFwdStages = 3;
 
 template <int WS>
-__global__ void __launch_bounds__(MCfg<WS>::THREADS, (MCfg<WS>::THREADS <= 320 ? 2 : 1))
+__global__ void __launch_bounds__(MCfg<WS>::THREADS, MCfg<WS>::FWD_CTAS)
 attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
   using Cf = MCfg<WS>;
   constexpr int N = Cf::N, NP = Cf::NP, TW = Cf::TW, CHN = Cf::CHN;
@@ -377,17 +380,28 @@ size_t mma_fwd_smem() {
   return 128 + (size_t)kFwdStages * 3 * Cf::TILE + 2 * (size_t)kFwdStages * Cf::NP * 4 + (size_t)Cf::NTAB * 4 + (size_t)Cf::NP * 4;
 }
 
+// CTAs of a kernel that fit one SM: shared memory, threads and the per-sub-partition register file (warps of a CTA are
+// dealt round-robin to the four sub-partitions of 16384 registers each).  Computed here because the occupancy query
+// answers for the shared-memory carve-out of the moment (1 CTA before the first launch).
+template <typename K>
+int ctas_per_sm(K kernel, int threads, size_t smem) {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return 1;
+  const int warps = threads / 32;
+  int occ = (int)((227 * 1024) / (smem + 1024));
+  if (occ > 2048 / threads) occ = 2048 / threads;
+  const int regs_per_warp = ((fa.numRegs + 7) / 8 * 8) * 32;
+  while (occ > 1 && ((occ * warps + 3) / 4) * regs_per_warp > 16384) --occ;
+  if (occ > 8) occ = 8;
+  return occ < 1 ? 1 : occ;
+}
+
 template <int WS>
 int launch_mma_fwd(const MmaArgs& a, cudaStream_t st) {
   using Cf = MCfg<WS>;
   const size_t smem = mma_fwd_smem<WS>();
   BSW_CUDA(cudaFuncSetAttribute(attn_mma_fwd_kernel<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  BSW_CUDA(cudaFuncSetAttribute(attn_mma_fwd_kernel<WS>, cudaFuncAttributePreferredSharedMemoryCarveout, 80));   // two CTAs
-  int occ = (int)((227 * 1024) / (smem + 1024));
-  const int occ_threads = 2048 / Cf::THREADS;
-  if (occ > occ_threads) occ = occ_threads;
-  if (occ > 2) occ = 2;                               // __launch_bounds__(THREADS, 2)
-  if (occ < 1) occ = 1;
+  const int occ = ctas_per_sm(attn_mma_fwd_kernel<WS>, Cf::THREADS, smem);
   int64_t grid = (int64_t)sm_count() * occ;
   if (grid > a.nitems) grid = a.nitems;
   attn_mma_fwd_kernel<WS><<<(unsigned)grid, Cf::THREADS, smem, st>>>(a);
@@ -428,7 +442,7 @@ struct BCfg {
 };
 
 template <int WS>
-__global__ void __launch_bounds__(MCfg<WS>::THREADS, 1)
+__global__ void __launch_bounds__(MCfg<WS>::THREADS, MCfg<WS>::BWD_CTAS)
 attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
   using Cf = MCfg<WS>;
   using Bc = BCfg<WS>;
@@ -852,7 +866,7 @@ int launch_mma_bwd(const MmaArgs& a, cudaStream_t st) {
   BSW_REQUIRE(smem <= 227 * 1024, "attn_bwd(mma): window %dx%d needs %zu bytes of shared memory", WS, WS, smem);
   BSW_CUDA(cudaFuncSetAttribute(attn_mma_bwd_kernel<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // (no carve-out preference: the driver sizes shared memory to the request and the rest stays L1 for the few spills)
-  int64_t grid = sm_count();
+  int64_t grid = (int64_t)sm_count() * ctas_per_sm(attn_mma_bwd_kernel<WS>, Cf::THREADS, smem);
   if (grid > a.nitems) grid = a.nitems;
   attn_mma_bwd_kernel<WS><<<(unsigned)grid, Cf::THREADS, smem, st>>>(a);
   BSW_LAUNCH_CHECK();
@@ -873,7 +887,7 @@ int fill_mma_args(MmaArgs* a, int B, int H, int W, int C, int nH, int ws, int sh
 }
 }  // namespace
 
-bool attn_fwd_mma_supported(int ws) { return ws == 12; }
+bool attn_fwd_mma_supported(int ws) { return ws == 4 || ws == 6 || ws == 7 || ws == 8 || ws == 12; }
 
 int attn_fwd_mma(const void* qkv, void* out, void* out_lo, float* lse, const float* table16, const float* scale, const float* qpad,
                  const float* vpad, int B, int H, int W, int C, int nH, int ws, int shift, cudaStream_t st) {
@@ -883,6 +897,10 @@ int attn_fwd_mma(const void* qkv, void* out, void* out_lo, float* lse, const flo
   a.qkv = (const __nv_bfloat16*)qkv; a.out = (__nv_bfloat16*)out; a.out_lo = (__nv_bfloat16*)out_lo; a.lse = lse;
   a.table16 = table16; a.scale = scale; a.qpad = qpad; a.vpad = vpad;
   switch (ws) {
+    case 4: return launch_mma_fwd<4>(a, st);
+    case 6: return launch_mma_fwd<6>(a, st);
+    case 7: return launch_mma_fwd<7>(a, st);
+    case 8: return launch_mma_fwd<8>(a, st);
     case 12: return launch_mma_fwd<12>(a, st);
     default: break;
   }
@@ -890,7 +908,7 @@ int attn_fwd_mma(const void* qkv, void* out, void* out_lo, float* lse, const flo
   return B200SWIN_EINVAL;
 }
 
-bool attn_bwd_mma_supported(int ws) { return ws == 12; }
+bool attn_bwd_mma_supported(int ws) { return ws == 4 || ws == 6 || ws == 7 || ws == 8 || ws == 12; }
 
 // D = <dO, O> per (token, head) (attn_bwd_ws.cu)
 int attn_bwd_prep(const void* dout, const void* out, const void* out_lo, float* dvec, int64_t n, cudaStream_t st);
@@ -911,6 +929,10 @@ int attn_bwd_mma(const void* qkv, const void* out, const void* out_lo, const voi
   rc = attn_bwd_prep(dout, out, out_lo, (float*)workspace, (int64_t)B * H * W * nH, st);
   if (rc) return rc;
   switch (ws) {
+    case 4: return launch_mma_bwd<4>(a, st);
+    case 6: return launch_mma_bwd<6>(a, st);
+    case 7: return launch_mma_bwd<7>(a, st);
+    case 8: return launch_mma_bwd<8>(a, st);
     case 12: return launch_mma_bwd<12>(a, st);
     default: break;
   }
