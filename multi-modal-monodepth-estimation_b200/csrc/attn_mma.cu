@@ -256,6 +256,16 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
     uint32_t qa[2][4];
     ldsm4(qa[0], q_s + lq_off);
     ldsm4(qa[1], q_s + (lq_off ^ 32u));           // dim chunks 2, 3: bit 1 of the (swizzled) chunk index
+    // a tile of 16 pad queries (right / bottom edge of a padded map) has no output: nothing to do.  Its rows get
+    // lse = +inf so that any backward sees P = 0 for them.
+    if (__all_sync(0xffffffffu, tokS[rA] < 0 && tokS[rB] < 0)) {
+      float* lse_pad = a.lse + (p.win * a.nH + p.h) * N;
+      if (tq == 0) {
+        if (rA < N) lse_pad[rA] = INFINITY;
+        if (rB < N) lse_pad[rB] = INFINITY;
+      }
+      continue;
+    }
     float o[4][4];
 #pragma unroll
     for (int dn = 0; dn < 4; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
@@ -435,7 +445,8 @@ struct BCfg {
   // per-thread gradient sums that do not fit the register file (168 registers per thread with nine warps: three warps on
   // one SM sub-partition): the bias-gradient sums of the last DBS column tiles and the v_bias gradient, [slot][thread]
   static constexpr int DBS = Cf::NTILES8 >= 18 ? 12 : 0;                       // column tiles (of 8 queries) kept in smem
-  static constexpr uint32_t OFF_DBS = OFF_RED + (Cf::NT * 4 + 15) / 16 * 16;  // [DBS * 2][THREADS] float2
+  static constexpr uint32_t OFF_PADF = OFF_RED + (Cf::NT * 4 + 15) / 16 * 16; // [stages][NT] ints: tile of 16 rows all pad
+  static constexpr uint32_t OFF_DBS = OFF_PADF + (kBwdStages * Cf::NT * 4 + 15) / 16 * 16;  // [DBS * 2][THREADS] float2
   static constexpr uint32_t OFF_DVP = OFF_DBS + DBS * 2 * Cf::THREADS * 8;    // [8][THREADS] float
   static constexpr uint32_t SMEM = OFF_DVP + 8 * Cf::THREADS * 4 + 128;
   static_assert((Cf::NP / 2) * Cf::NP * 4 <= Cf::NP * PSTRIDE, "the flush staging lives in the panel");
@@ -459,6 +470,7 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
   float* tab = reinterpret_cast<float*>(sm + Bc::OFF_TAB);
   unsigned char* panel = sm + Bc::OFF_PANEL;
   float* red = reinterpret_cast<float*>(sm + Bc::OFF_RED);
+  int* padf = reinterpret_cast<int*>(sm + Bc::OFF_PADF);
   float2* dbs = reinterpret_cast<float2*>(sm + Bc::OFF_DBS) + threadIdx.x;   // + slot * THREADS
   float* dvps = reinterpret_cast<float*>(sm + Bc::OFF_DVP) + threadIdx.x;    // + slot * THREADS
   const uint32_t panel_s = base_u32 + Bc::OFF_PANEL;
@@ -483,6 +495,9 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
     const uint32_t q0_s = base_u32 + (uint32_t)stage * Bc::STAGE_TILES;
     int region = 0, t = -2;
     if (!Cf::RAGGED || prow < N) t = row_token<WS>(g, pp, py, px, &region);
+    // a warp copies exactly one 16-row tile: is it pad tokens only?  (pad queries have dO = 0: their dS is zero)
+    const bool tile_pad = __all_sync(0xffffffffu, t < 0);
+    if (lane == 0) padf[stage * Cf::NT + warp] = tile_pad ? 1 : 0;
     if ((tid & 1) == 0) {
       // per-row scalars: {lse, D = <dO, O>} and {1 / ||q||, 1 / ||k||}
       tokm[stage * NP + prow] = t;
@@ -631,6 +646,9 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
     ptx::cp_async_commit();
 
     const bool need_mask = g.shift > 0 && (p.wh == g.nWh - 1 || p.ww == g.nWw - 1);
+    uint32_t padmask = 0;                         // bit c: the 16 queries of step / tile c are all pad tokens (CTA-uniform)
+#pragma unroll
+    for (int w = 0; w < Cf::NT; ++w) padmask |= (uint32_t)padf[stage * Cf::NT + w] << w;
     const uint32_t q_s = base_u32 + (uint32_t)stage * Bc::STAGE_TILES, k_s = q_s + TILE, v_s = k_s + TILE, g_s = v_s + TILE;
     const int* tokS = tokm + stage * NP;
     const int* ridS = ridm + stage * NP;
@@ -674,71 +692,35 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
       };
       auto sweep = [&](auto mask_c) {
         constexpr bool MASK = decltype(mask_c)::value;
-        float stb[2][2][4], dpb[2][2][4];           // double-buffered: the MMAs of step c + 1 run under the element work of step c
-        sdp(0, stb[0], dpb[0]);
-        // Shared-memory stores of a step are issued only AFTER the loads of the next step: neither compiler can prove
-        // that the panel / gradient-sum stores do not alias the table and per-query loads, so a store that waits for
-        // the end of a step's dependency chain would hold back every later load and serialise the steps.
-        uint32_t pendD[4] = {0, 0, 0, 0};
-        float2 pendS[4];
 #pragma unroll
-        for (int c = 0; c <= NT8 / 2; ++c) {        // 16 queries per step; the extra round only drains the stores
-          const bool live = c < NT8 / 2;
-          float (&st)[2][4] = stb[c & 1];
-          float (&dp)[2][4] = dpb[c & 1];
+        for (int c = 0; c < NT8 / 2; ++c) {         // 16 queries per step
+          if ((padmask >> c) & 1u) continue;        // pad queries only (CTA-uniform): dS = 0, nothing to add anywhere
+          float st[2][4], dp[2][4];
+          sdp(c, st, dp);
+          // B operands of this step's dV / dK contractions: in flight during the element work
+          const uint32_t row16 = (uint32_t)(c * 16) * 64u;
           uint32_t bg0[4], bg2[4], bq0[4], bq2[4];
-          float4 mm[2];
-          float bias[2][4];
-          int2 rr[2];
-          float2 sl[4];
-          if (live) {
-            if (c + 1 < NT8 / 2) sdp(c + 1, stb[(c + 1) & 1], dpb[(c + 1) & 1]);
-            // B operands of this step's dV / dK contractions: in flight during the element work
-            const uint32_t row16 = (uint32_t)(c * 16) * 64u;
-            ldsm4t(bg0, g_s + row16 + lv_off0);
-            ldsm4t(bg2, g_s + row16 + lv_off2);
-            ldsm4t(bq0, q_s + row16 + lv_off0);
-            ldsm4t(bq2, q_s + row16 + lv_off2);
-#pragma unroll
-            for (int n = 0; n < 2; ++n) {
-              const int qcol = c * 16 + n * 8 + 2 * tq;
-              mm[n] = qm4[(c * 16 + n * 8) / 2 + tq];                    // {lse, D} of queries qcol, qcol + 1
-              const int2 kq = *reinterpret_cast<const int2*>(kofk + qcol);
-              const uint32_t aA0 = tabA + (uint32_t)kq.x, aB0 = tabB + (uint32_t)kq.x;
-              const uint32_t aA1 = (WS % 2 == 0) ? aA0 + 4u : tabA + (uint32_t)kq.y;
-              const uint32_t aB1 = (WS % 2 == 0) ? aB0 + 4u : tabB + (uint32_t)kq.y;
-              bias[n][0] = lds32(aA0); bias[n][1] = lds32(aA1); bias[n][2] = lds32(aB0); bias[n][3] = lds32(aB1);
-              if (MASK) rr[n] = *reinterpret_cast<const int2*>(ridS + qcol);
-              if (c * 2 + n >= NREG) {
-                sl[2 * n] = dbs[((c * 2 + n - NREG) * 2) * Cf::THREADS];
-                sl[2 * n + 1] = dbs[((c * 2 + n - NREG) * 2 + 1) * Cf::THREADS];
-              }
-            }
-          }
-          if (c > 0) {                              // the stores of step c - 1
-#pragma unroll
-            for (int n = 0; n < 2; ++n) {
-              const uint32_t col = (uint32_t)((c - 1) * 16 + n * 8) * 2u;
-              asm volatile("st.shared.b32 [%0], %1;" ::"r"(panel_s + pw_offA + col), "r"(pendD[2 * n]) : "memory");
-              asm volatile("st.shared.b32 [%0], %1;" ::"r"(panel_s + pw_offB + col), "r"(pendD[2 * n + 1]) : "memory");
-              if ((c - 1) * 2 + n >= NREG) {
-                dbs[(((c - 1) * 2 + n - NREG) * 2) * Cf::THREADS] = pendS[2 * n];
-                dbs[(((c - 1) * 2 + n - NREG) * 2 + 1) * Cf::THREADS] = pendS[2 * n + 1];
-              }
-            }
-          }
-          if (!live) break;
-          uint32_t aP[4];
+          ldsm4t(bg0, g_s + row16 + lv_off0);
+          ldsm4t(bg2, g_s + row16 + lv_off2);
+          ldsm4t(bq0, q_s + row16 + lv_off0);
+          ldsm4t(bq2, q_s + row16 + lv_off2);
+          uint32_t aP[4], aD[4];
 #pragma unroll
           for (int n = 0; n < 2; ++n) {
-            const float4 m = mm[n];
-            float s2[4] = {fmaf(st[n][0], scale2, bias[n][0]), fmaf(st[n][1], scale2, bias[n][1]),
-                           fmaf(st[n][2], scale2, bias[n][2]), fmaf(st[n][3], scale2, bias[n][3])};
+            const int qcol = c * 16 + n * 8 + 2 * tq;
+            const float4 m = qm4[(c * 16 + n * 8) / 2 + tq];             // {lse, D} of queries qcol, qcol + 1
+            const int2 kq = *reinterpret_cast<const int2*>(kofk + qcol);
+            const uint32_t aA0 = tabA + (uint32_t)kq.x, aB0 = tabB + (uint32_t)kq.x;
+            const uint32_t aA1 = (WS % 2 == 0) ? aA0 + 4u : tabA + (uint32_t)kq.y;
+            const uint32_t aB1 = (WS % 2 == 0) ? aB0 + 4u : tabB + (uint32_t)kq.y;
+            float s2[4] = {fmaf(st[n][0], scale2, lds32(aA0)), fmaf(st[n][1], scale2, lds32(aA1)),
+                           fmaf(st[n][2], scale2, lds32(aB0)), fmaf(st[n][3], scale2, lds32(aB1))};
             if (MASK) {
-              if (rr[n].x != ridA) s2[0] += kMaskLog2;
-              if (rr[n].y != ridA) s2[1] += kMaskLog2;
-              if (rr[n].x != ridB) s2[2] += kMaskLog2;
-              if (rr[n].y != ridB) s2[3] += kMaskLog2;
+              const int2 rr = *reinterpret_cast<const int2*>(ridS + qcol);
+              if (rr.x != ridA) s2[0] += kMaskLog2;
+              if (rr.y != ridA) s2[1] += kMaskLog2;
+              if (rr.x != ridB) s2[2] += kMaskLog2;
+              if (rr.y != ridB) s2[3] += kMaskLog2;
             }
             float pv[4], ds[4];
             pv[0] = ex2f(fmaf(m.x, -kLog2e, s2[0]));
@@ -757,23 +739,27 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) db[c * 2 + n < NREG ? c * 2 + n : 0][e] += ds[e];
             } else {
-              pendS[2 * n] = make_float2(sl[2 * n].x + ds[0], sl[2 * n].y + ds[1]);
-              pendS[2 * n + 1] = make_float2(sl[2 * n + 1].x + ds[2], sl[2 * n + 1].y + ds[3]);
+              float2* slot = dbs + ((c * 2 + n - NREG) * 2) * Cf::THREADS;
+              float2 u = slot[0], w = slot[Cf::THREADS];
+              u.x += ds[0]; u.y += ds[1]; w.x += ds[2]; w.y += ds[3];
+              slot[0] = u; slot[Cf::THREADS] = w;
             }
             aP[2 * n] = pack2(pv[0], pv[1]);
             aP[2 * n + 1] = pack2(pv[2], pv[3]);
-            pendD[2 * n] = pack2(ds[0], ds[1]);
-            pendD[2 * n + 1] = pack2(ds[2], ds[3]);
+            aD[2 * n] = pack2(ds[0], ds[1]);
+            aD[2 * n + 1] = pack2(ds[2], ds[3]);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(panel_s + pw_offA + (uint32_t)(c * 16 + n * 8) * 2u), "r"(aD[2 * n]) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(panel_s + pw_offB + (uint32_t)(c * 16 + n * 8) * 2u), "r"(aD[2 * n + 1]) : "memory");
           }
           // dV += P^T dO, dK += dS^T Q over these 16 queries (eight independent accumulators)
           mma16816(dv[0], aP, bg0[0], bg0[1]);
           mma16816(dv[1], aP, bg0[2], bg0[3]);
           mma16816(dv[2], aP, bg2[0], bg2[1]);
           mma16816(dv[3], aP, bg2[2], bg2[3]);
-          mma16816(dk[0], pendD, bq0[0], bq0[1]);
-          mma16816(dk[1], pendD, bq0[2], bq0[3]);
-          mma16816(dk[2], pendD, bq2[0], bq2[1]);
-          mma16816(dk[3], pendD, bq2[2], bq2[3]);
+          mma16816(dk[0], aD, bq0[0], bq0[1]);
+          mma16816(dk[1], aD, bq0[2], bq0[3]);
+          mma16816(dk[2], aD, bq2[0], bq2[1]);
+          mma16816(dk[3], aD, bq2[2], bq2[3]);
         }
       };
       if (need_mask) sweep(std::true_type{}); else sweep(std::false_type{});
@@ -814,7 +800,7 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
     __syncthreads();                              // (B2) the dS panel is complete
 
     // ------------------------------------------------------------------ phase 2: this warp's 16 queries, dQ = dS K
-    {
+    if (!((padmask >> warp) & 1u)) {
       float dq[4][4];
 #pragma unroll
       for (int dn = 0; dn < 4; ++dn) dq[dn][0] = dq[dn][1] = dq[dn][2] = dq[dn][3] = 0.f;
