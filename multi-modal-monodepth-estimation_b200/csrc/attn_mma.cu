@@ -859,6 +859,486 @@ int launch_mma_bwd(const MmaArgs& a, cudaStream_t st) {
   return B200SWIN_OK;
 }
 
+// ------------------------------------------------------------------------------ backward, warp-specialised (12x12)
+// Same two phases, but with nine warps per SM the CTA barriers between the phases and the item prologue cost a third
+// of the time (nothing else is resident to fill them).  Here the nine KEY warps run phase 1 of item after item without
+// ever meeting a CTA barrier; three HELPER warps (one on each of the SM sub-partitions that hold only two key warps)
+// gather the operands (cp.async, completion on an mbarrier per stage) and run phase 2 -- dQ = dS K from the dS panel
+// of the item, its normalisation and the temperature gradient -- one item behind.  The panel is double-buffered.
+//   full[s]   helpers -> key warps   operands of the item in stage s have landed
+//   pfull[s]  key warps -> helpers   panel s complete, stage s no longer read by phase 1
+//   pfree[s]  helpers -> key warps   panel s consumed
+template <int WS>
+struct SCfg {
+  using Cf = MCfg<WS>;
+  static constexpr int NH = 3;                                                // helper warps
+  static constexpr int KTHREADS = Cf::THREADS, HTHREADS = NH * 32, THREADS = KTHREADS + HTHREADS;
+  static constexpr uint32_t STAGE_TILES = 4 * Cf::TILE;
+  static constexpr uint32_t PSTRIDE = Cf::NP * 2 + 16;
+  static constexpr uint32_t PANEL = Cf::NP * PSTRIDE;
+  static constexpr uint32_t OFF_QMETA = 2 * STAGE_TILES;
+  static constexpr uint32_t OFF_INN = OFF_QMETA + 2 * Cf::NP * 8;
+  static constexpr uint32_t OFF_TOK = OFF_INN + 2 * Cf::NP * 8;
+  static constexpr uint32_t OFF_RID = OFF_TOK + 2 * Cf::NP * 4;
+  static constexpr uint32_t OFF_KOF = OFF_RID + 2 * Cf::NP * 4;
+  static constexpr uint32_t OFF_TAB = OFF_KOF + Cf::NP * 4;
+  static constexpr uint32_t OFF_PANEL = (OFF_TAB + Cf::NTAB * 4 + 127) / 128 * 128;   // two panels
+  static constexpr uint32_t OFF_RED = OFF_PANEL + 2 * PANEL;                  // [NT] floats
+  static constexpr uint32_t OFF_PADF = OFF_RED + (Cf::NT * 4 + 15) / 16 * 16; // [2][NT] ints
+  static constexpr uint32_t OFF_BARS = OFF_PADF + (2 * Cf::NT * 4 + 15) / 16 * 16;    // 6 mbarriers
+  static constexpr int DBS = 8;                                               // column tiles whose sums live in smem
+  static constexpr uint32_t OFF_DBS = OFF_BARS + 64;
+  static constexpr uint32_t OFF_DVP = OFF_DBS + DBS * 2 * KTHREADS * 8;
+  static constexpr uint32_t SMEM = OFF_DVP + 8 * KTHREADS * 4 + 128;
+  static_assert((Cf::NP / 2) * Cf::NP * 4 <= PANEL, "the flush staging lives in a panel");
+  static_assert(Cf::NT % NH == 0, "tiles per helper warp");
+};
+
+template <int WS>
+__global__ void __launch_bounds__(SCfg<WS>::THREADS, 1)
+attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
+  using Cf = MCfg<WS>;
+  using Sc = SCfg<WS>;
+  constexpr int N = Cf::N, NP = Cf::NP, TW = Cf::TW, NT8 = Cf::NTILES8, NT = Cf::NT;
+  constexpr int KTH = Sc::KTHREADS, HTH = Sc::HTHREADS;
+  constexpr uint32_t TILE = Cf::TILE, PSTRIDE = Sc::PSTRIDE;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base_u32 = (ptx::smem_u32(smem_dyn) + 127u) & ~127u;
+  unsigned char* sm = smem_dyn + (base_u32 - ptx::smem_u32(smem_dyn));
+  float2* qmeta = reinterpret_cast<float2*>(sm + Sc::OFF_QMETA);
+  float2* innorm = reinterpret_cast<float2*>(sm + Sc::OFF_INN);
+  int* tokm = reinterpret_cast<int*>(sm + Sc::OFF_TOK);
+  int* ridm = reinterpret_cast<int*>(sm + Sc::OFF_RID);
+  int* kofk = reinterpret_cast<int*>(sm + Sc::OFF_KOF);
+  float* tab = reinterpret_cast<float*>(sm + Sc::OFF_TAB);
+  float* red = reinterpret_cast<float*>(sm + Sc::OFF_RED);
+  int* padf = reinterpret_cast<int*>(sm + Sc::OFF_PADF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Sc::OFF_BARS);
+  uint64_t* full = bars;          // [2]
+  uint64_t* pfull = bars + 2;     // [2]
+  uint64_t* pfree = bars + 4;     // [2]
+
+  const WinGeom& g = a.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int64_t per = a.nitems / gridDim.x, rem = a.nitems % gridDim.x;
+  const int64_t it0 = (int64_t)blockIdx.x * per + min((int64_t)blockIdx.x, rem);
+  const int nit = (int)(per + ((int64_t)blockIdx.x < rem ? 1 : 0));
+  const int C3 = 3 * a.C;
+
+  for (int r = tid; r < NP; r += Sc::THREADS) kofk[r] = r < N ? 4 * ((r / WS) * TW + (r % WS)) : 0;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&full[s], 2 * HTH);          // per helper thread: its cp.async have landed + its plain stores are released
+      ptx::mbar_init(&pfull[s], NT);              // lane 0 of every key warp
+      ptx::mbar_init(&pfree[s], Sc::NH);          // lane 0 of every helper warp
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  const uint32_t lk_off = sw64(lane & 7, lane >> 3);                                            // B fragments, K-major (8 rows x 4 chunks)
+  const uint32_t lv_off0 = sw64((lane & 7) + ((lane >> 3) & 1) * 8, lane >> 4);                 // B fragments, MN-major (16 rows x chunks 0, 1)
+  const uint32_t lv_off2 = sw64((lane & 7) + ((lane >> 3) & 1) * 8, 2 + (lane >> 4));
+
+  if (warp >= NT) {
+    // ============================================================================================== helper warps
+    const int hw = warp - NT, hid = tid - KTH;
+    ItemPos pp = item_pos(a, it0);               // cursor of the gather stream
+    auto gather = [&](int i) {
+      const int stage = i & 1;
+      unsigned char* q0 = sm + (size_t)stage * Sc::STAGE_TILES;
+      const uint32_t q0_s = base_u32 + (uint32_t)stage * Sc::STAGE_TILES;
+#pragma unroll 1
+      for (int k = 0; k < NT / Sc::NH; ++k) {     // a helper warp copies the tile 3 k + hw in round k
+        const int task = k * HTH + hid, prow = task >> 1, half = task & 1;
+        const int py = prow / WS, px = prow - py * WS;
+        const uint32_t poff = sw64(prow, half * 2);
+        int region = 0, t = -2;
+        if (!Cf::RAGGED || prow < N) t = row_token<WS>(g, pp, py, px, &region);
+        const bool tile_pad = __all_sync(0xffffffffu, t < 0);
+        if (lane == 0) padf[stage * NT + k * Sc::NH + hw] = tile_pad ? 1 : 0;
+        if (half == 0) {
+          tokm[stage * NP + prow] = t;
+          ridm[stage * NP + prow] = region;
+          float2* qm = qmeta + stage * NP + prow;
+          float2* im = innorm + stage * NP + prow;
+          const uint32_t qm_s = base_u32 + Sc::OFF_QMETA + (uint32_t)(stage * NP + prow) * 8u;
+          const uint32_t im_s = base_u32 + Sc::OFF_INN + (uint32_t)(stage * NP + prow) * 8u;
+          if (t >= 0) {
+            ptx::cp_async_4(qm_s, a.lse + (pp.win * a.nH + pp.h) * N + prow);
+            ptx::cp_async_4(qm_s + 4, a.dvec + (int64_t)t * a.nH + pp.h);
+            ptx::cp_async_4(im_s, a.inv_norm + ((int64_t)t * 2 + 0) * a.nH + pp.h);
+            ptx::cp_async_4(im_s + 4, a.inv_norm + ((int64_t)t * 2 + 1) * a.nH + pp.h);
+          } else {
+            *qm = make_float2(INFINITY, 0.f);        // pad query (dO = 0) or beyond the window: P = 0, dS = 0
+            *im = make_float2(0.f, 0.f);
+          }
+        }
+        if (t >= 0) {
+          const __nv_bfloat16* src = a.qkv + (int64_t)t * C3 + pp.h * HD + half * 16;
+          const __nv_bfloat16* gsrc = a.dout + (int64_t)t * a.C + pp.h * HD + half * 16;
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) {
+            ptx::cp_async_16(q0_s + kk * TILE + poff, src + kk * a.C);
+            ptx::cp_async_16(q0_s + kk * TILE + (poff ^ 16u), src + kk * a.C + 8);
+          }
+          ptx::cp_async_16(q0_s + 3 * TILE + poff, gsrc);
+          ptx::cp_async_16(q0_s + 3 * TILE + (poff ^ 16u), gsrc + 8);
+        } else {
+          const float* qp = (t == -1 && a.qpad) ? a.qpad + pp.h * HD + half * 16 : nullptr;
+          const float* vp = (t == -1 && a.vpad) ? a.vpad + pp.h * HD + half * 16 : nullptr;
+          put16(q0, q0_s, poff, nullptr, qp);
+          put16(q0, q0_s, poff ^ 16u, nullptr, qp ? qp + 8 : nullptr);
+          put16(q0 + 2 * TILE, q0_s + 2 * TILE, poff, nullptr, vp);
+          put16(q0 + 2 * TILE, q0_s + 2 * TILE, poff ^ 16u, nullptr, vp ? vp + 8 : nullptr);
+#pragma unroll
+          for (int kk = 1; kk < 4; kk += 2) {
+            put16(q0 + kk * TILE, q0_s + kk * TILE, poff, nullptr, nullptr);
+            put16(q0 + kk * TILE, q0_s + kk * TILE, poff ^ 16u, nullptr, nullptr);
+          }
+        }
+      }
+      ptx::cp_async_mbar_arrive_noinc(&full[stage]);
+      ptx::mbar_arrive(&full[stage]);
+      item_next(a, pp);
+    };
+    if (nit > 0) gather(0);
+    if (nit > 1) gather(1);
+
+    ItemPos p = item_pos(a, it0);
+    int cur_h = -1;
+    float dsc = 0.f;
+    auto flush_dsc = [&](int h) {
+      const float s = warp_sum(dsc);
+      dsc = 0.f;
+      if (lane == 0 && s != 0.f) atomicAdd(a.dscale + h, s);
+    };
+#pragma unroll 1
+    for (int i = 0; i < nit; ++i, item_next(a, p)) {
+      const int stage = i & 1;
+      const uint32_t par = (uint32_t)(i >> 1) & 1u;
+      if (p.h != cur_h) {
+        if (cur_h >= 0) flush_dsc(cur_h);
+        cur_h = p.h;
+      }
+      const float sc = a.scale[p.h];
+      ptx::mbar_wait(&pfull[stage], par);          // panel complete (implies: this stage's operands landed long ago)
+      const uint32_t q_s = base_u32 + (uint32_t)stage * Sc::STAGE_TILES, k_s = q_s + TILE;
+      const uint32_t panel_s = base_u32 + Sc::OFF_PANEL + (uint32_t)stage * Sc::PANEL;
+      const int* tokS = tokm + stage * NP;
+#pragma unroll 1
+      for (int k = 0; k < NT / Sc::NH; ++k) {
+        const int tile = k * Sc::NH + hw;
+        if (padf[stage * NT + tile]) continue;     // pad queries only: dQ rows of tokens that do not exist
+        const int rA = tile * 16 + gq, rB = rA + 8;
+        const uint32_t la_off = sw64(tile * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, lane >> 4);
+        const uint32_t pr_off = (uint32_t)((lane & 7) + (lane >> 4) * 8) * PSTRIDE + (uint32_t)(tile * 16 + ((lane >> 3) & 1) * 8) * 2u;
+        float dq[4][4];
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) dq[dn][0] = dq[dn][1] = dq[dn][2] = dq[dn][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < NP / 16; ++ks) {
+          uint32_t ad[4], b0[4], b2[4];
+          ldsm4t(ad, panel_s + (uint32_t)(ks * 16) * PSTRIDE + pr_off);
+          ldsm4t(b0, k_s + (uint32_t)(ks * 16) * 64u + lv_off0);
+          ldsm4t(b2, k_s + (uint32_t)(ks * 16) * 64u + lv_off2);
+          mma16816(dq[0], ad, b0[0], b0[1]);
+          mma16816(dq[1], ad, b0[2], b0[3]);
+          mma16816(dq[2], ad, b2[0], b2[1]);
+          mma16816(dq[3], ad, b2[2], b2[3]);
+        }
+        uint32_t qa[2][4];
+        ldsm4(qa[0], q_s + la_off);
+        ldsm4(qa[1], q_s + (la_off ^ 32u));
+        const int tokA = tokS[rA], tokB = tokS[rB];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int t = half ? tokB : tokA;
+          float qh[4][2], dot = 0.f;
+#pragma unroll
+          for (int dn = 0; dn < 4; ++dn) {
+            const uint32_t w = qa[dn >> 1][(dn & 1) * 2 + half];
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+            qh[dn][0] = f.x; qh[dn][1] = f.y;
+            dot = fmaf(dq[dn][2 * half], f.x, dot);
+            dot = fmaf(dq[dn][2 * half + 1], f.y, dot);
+          }
+          dot = quad_sum(dot);
+          // gradient of the temperature: sum_k dS[q, k] cos[q, k] = <q_hat, sum_k dS[q, k] k_hat> = this very dot product
+          if (tq == 0) dsc += dot;
+          dot *= sc;
+          if (t < 0) continue;
+          const float invn = innorm[stage * NP + (half ? rB : rA)].x;            // 1 / ||q||
+          uint32_t* dqd = reinterpret_cast<uint32_t*>(a.dqkv + (int64_t)t * C3 + p.h * HD) + tq;
+#pragma unroll
+          for (int dn = 0; dn < 4; ++dn)
+            dqd[dn * 4] = pack2((dq[dn][2 * half] * sc - qh[dn][0] * dot) * invn, (dq[dn][2 * half + 1] * sc - qh[dn][1] * dot) * invn);
+        }
+      }
+      // every helper is done with panel / stage `stage`: hand the panel back and refill the stage
+      ptx::named_bar_sync(2, HTH);
+      if (lane == 0) ptx::mbar_arrive(&pfree[stage]);
+      if (i + 2 < nit) gather(i + 2);
+    }
+    if (cur_h >= 0) flush_dsc(cur_h);
+    ptx::cp_async_wait<0>();
+    return;
+  }
+
+  // ================================================================================================== key warps
+  float2* dbs = reinterpret_cast<float2*>(sm + Sc::OFF_DBS) + tid;           // + slot * KTH
+  float* dvps = reinterpret_cast<float*>(sm + Sc::OFF_DVP) + tid;            // + slot * KTH
+  constexpr int DBS = Sc::DBS, NREG = NT8 - DBS;
+  int cur_h = -1;
+  float sc = 0.f, scale2 = 0.f;
+  const int rA = warp * 16 + gq, rB = rA + 8;
+  ItemPos p = item_pos(a, it0);
+  const uint32_t la_off = sw64(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, lane >> 4);
+  const uint32_t pw_offA = (uint32_t)rA * PSTRIDE + (uint32_t)tq * 4u, pw_offB = pw_offA + 8u * PSTRIDE;
+
+  float db[NREG][4];
+#pragma unroll
+  for (int n = 0; n < NREG; ++n) db[n][0] = db[n][1] = db[n][2] = db[n][3] = 0.f;
+#pragma unroll
+  for (int n = 0; n < DBS * 2; ++n) dbs[n * KTH] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) dvps[e * KTH] = 0.f;
+
+  auto flush_head = [&](int h, unsigned char* panel) {
+    // key warps only (named barrier 1); `panel` is a panel the helpers have handed back
+    if (a.dvpad) {
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float v = dvps[(dn * 2 + e) * KTH];
+          dvps[(dn * 2 + e) * KTH] = 0.f;
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (gq == 0 && v != 0.f) atomicAdd(a.dvpad + h * HD + dn * 8 + 2 * tq + e, v);
+        }
+    }
+    float* stg = reinterpret_cast<float*>(panel);   // [NP / 2][NP]
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int lo = half * (NP / 2);
+      ptx::named_bar_sync(1, KTH);
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int r = rr ? rB : rA;
+        if (r >= lo && r < lo + NP / 2) {
+#pragma unroll
+          for (int n = 0; n < NREG; ++n)
+            *reinterpret_cast<float2*>(stg + (r - lo) * NP + n * 8 + 2 * tq) = make_float2(db[n][2 * rr], db[n][2 * rr + 1]);
+#pragma unroll
+          for (int n = 0; n < DBS; ++n)
+            *reinterpret_cast<float2*>(stg + (r - lo) * NP + (NREG + n) * 8 + 2 * tq) = dbs[(n * 2 + rr) * KTH];
+        }
+      }
+      ptx::named_bar_sync(1, KTH);
+      for (int r = tid; r < Cf::NTAB; r += KTH) {
+        const int dy = r / TW - (WS - 1), dx = r % TW - (WS - 1);
+        float sum = 0.f;
+        for (int key = lo; key < lo + NP / 2 && key < N; ++key) {
+          const int yk = key / WS, xk = key - yk * WS;
+          const int yq = yk + dy, xq = xk + dx;
+          if (yq >= 0 && yq < WS && xq >= 0 && xq < WS) sum += stg[(key - lo) * NP + yq * WS + xq];
+        }
+        if (sum != 0.f) atomicAdd(a.dtable16 + (int64_t)r * a.nH + h, sum);
+      }
+    }
+    ptx::named_bar_sync(1, KTH);
+#pragma unroll
+    for (int n = 0; n < NREG; ++n) db[n][0] = db[n][1] = db[n][2] = db[n][3] = 0.f;
+#pragma unroll
+    for (int n = 0; n < DBS * 2; ++n) dbs[n * KTH] = make_float2(0.f, 0.f);
+  };
+
+#pragma unroll 1
+  for (int i = 0;; ++i, item_next(a, p)) {        // one extra round after the last item: the final flush (single call site)
+    const int stage = i & 1;
+    const uint32_t par = (uint32_t)(i >> 1) & 1u;
+    const bool done = i >= nit;
+    // panel `stage` is free once the helpers have consumed item i - 2 (a fresh barrier passes the wait on parity 1)
+    ptx::mbar_wait(&pfree[stage], par ^ 1u);
+    unsigned char* panel = sm + Sc::OFF_PANEL + (size_t)stage * Sc::PANEL;
+    const uint32_t panel_s = base_u32 + Sc::OFF_PANEL + (uint32_t)stage * Sc::PANEL;
+    if (done || p.h != cur_h) {                   // uniform over the key warps
+      if (cur_h >= 0) flush_head(cur_h, panel);
+      if (done) break;
+      ptx::named_bar_sync(1, KTH);                // nobody still reads the old table
+      for (int t = tid; t < Cf::NTAB; t += KTH) tab[t] = a.table16[(int64_t)t * a.nH + p.h] * kLog2e;
+      sc = a.scale[p.h];
+      scale2 = sc * kLog2e;
+      cur_h = p.h;
+      ptx::named_bar_sync(1, KTH);
+    }
+    ptx::mbar_wait(&full[stage], par);            // the operands of item i have landed
+
+    const bool need_mask = g.shift > 0 && (p.wh == g.nWh - 1 || p.ww == g.nWw - 1);
+    uint32_t padmask = 0;                         // bit c: the 16 queries of step / tile c are all pad tokens
+#pragma unroll
+    for (int w = 0; w < NT; ++w) padmask |= (uint32_t)padf[stage * NT + w] << w;
+    const uint32_t q_s = base_u32 + (uint32_t)stage * Sc::STAGE_TILES, k_s = q_s + TILE, v_s = k_s + TILE, g_s = v_s + TILE;
+    const int* tokS = tokm + stage * NP;
+    const int* ridS = ridm + stage * NP;
+    const float4* qm4 = reinterpret_cast<const float4*>(qmeta + stage * NP);
+    const int tokA = tokS[rA], tokB = tokS[rB];
+    // bias entry of (query, key) = tab[kof(query) - kof(key) + (WS-1)(TW+1)]
+    const uint32_t tab_s = ptx::smem_u32(tab) + 4u * (uint32_t)((WS - 1) * (TW + 1));
+    const uint32_t tabA = tab_s - (uint32_t)kofk[rA], tabB = tab_s - (uint32_t)kofk[rB];
+    const int ridA = ridS[rA], ridB = ridS[rB];
+    uint32_t ka[2][4], va[2][4];
+    ldsm4(ka[0], k_s + la_off);
+    ldsm4(ka[1], k_s + (la_off ^ 32u));
+    ldsm4(va[0], v_s + la_off);
+    ldsm4(va[1], v_s + (la_off ^ 32u));
+    float dk[4][4], dv[4][4];
+#pragma unroll
+    for (int dn = 0; dn < 4; ++dn) {
+      dk[dn][0] = dk[dn][1] = dk[dn][2] = dk[dn][3] = 0.f;
+      dv[dn][0] = dv[dn][1] = dv[dn][2] = dv[dn][3] = 0.f;
+    }
+    auto sdp = [&](int c, float (&st)[2][4], float (&dp)[2][4]) {
+      uint32_t bq[2][4], bg[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        ldsm4(bq[n], q_s + (uint32_t)(c * 16 + n * 8) * 64u + lk_off);
+        ldsm4(bg[n], g_s + (uint32_t)(c * 16 + n * 8) * 64u + lk_off);
+        st[n][0] = st[n][1] = st[n][2] = st[n][3] = 0.f;
+        dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          mma16816(st[n], ka[ks], bq[n][2 * ks], bq[n][2 * ks + 1]);
+          mma16816(dp[n], va[ks], bg[n][2 * ks], bg[n][2 * ks + 1]);
+        }
+    };
+    auto sweep = [&](auto mask_c) {
+      constexpr bool MASK = decltype(mask_c)::value;
+#pragma unroll
+      for (int c = 0; c < NT8 / 2; ++c) {         // 16 queries per step
+        if ((padmask >> c) & 1u) continue;        // pad queries only: dS = 0, nothing to add anywhere
+        float st[2][4], dp[2][4];
+        sdp(c, st, dp);
+        const uint32_t row16 = (uint32_t)(c * 16) * 64u;
+        uint32_t bg0[4], bg2[4], bq0[4], bq2[4];
+        ldsm4t(bg0, g_s + row16 + lv_off0);
+        ldsm4t(bg2, g_s + row16 + lv_off2);
+        ldsm4t(bq0, q_s + row16 + lv_off0);
+        ldsm4t(bq2, q_s + row16 + lv_off2);
+        uint32_t aP[4], aD[4];
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const int qcol = c * 16 + n * 8 + 2 * tq;
+          const float4 m = qm4[(c * 16 + n * 8) / 2 + tq];             // {lse, D} of queries qcol, qcol + 1
+          const int2 kq = *reinterpret_cast<const int2*>(kofk + qcol);
+          const uint32_t aA0 = tabA + (uint32_t)kq.x, aB0 = tabB + (uint32_t)kq.x;
+          const uint32_t aA1 = (WS % 2 == 0) ? aA0 + 4u : tabA + (uint32_t)kq.y;
+          const uint32_t aB1 = (WS % 2 == 0) ? aB0 + 4u : tabB + (uint32_t)kq.y;
+          float s2[4] = {fmaf(st[n][0], scale2, lds32(aA0)), fmaf(st[n][1], scale2, lds32(aA1)),
+                         fmaf(st[n][2], scale2, lds32(aB0)), fmaf(st[n][3], scale2, lds32(aB1))};
+          if (MASK) {
+            const int2 rr = *reinterpret_cast<const int2*>(ridS + qcol);
+            if (rr.x != ridA) s2[0] += kMaskLog2;
+            if (rr.y != ridA) s2[1] += kMaskLog2;
+            if (rr.x != ridB) s2[2] += kMaskLog2;
+            if (rr.y != ridB) s2[3] += kMaskLog2;
+          }
+          float pv[4], ds[4];
+          pv[0] = ex2f(fmaf(m.x, -kLog2e, s2[0]));
+          pv[1] = ex2f(fmaf(m.z, -kLog2e, s2[1]));
+          pv[2] = ex2f(fmaf(m.x, -kLog2e, s2[2]));
+          pv[3] = ex2f(fmaf(m.z, -kLog2e, s2[3]));
+          if (Cf::RAGGED) {
+            if (rA >= N) pv[0] = pv[1] = 0.f;
+            if (rB >= N) pv[2] = pv[3] = 0.f;
+          }
+          ds[0] = pv[0] * (dp[n][0] - m.y);
+          ds[1] = pv[1] * (dp[n][1] - m.w);
+          ds[2] = pv[2] * (dp[n][2] - m.y);
+          ds[3] = pv[3] * (dp[n][3] - m.w);
+          if (c * 2 + n < NREG) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) db[c * 2 + n < NREG ? c * 2 + n : 0][e] += ds[e];
+          } else {
+            float2* slot = dbs + ((c * 2 + n - NREG) * 2) * KTH;
+            float2 u = slot[0], w = slot[KTH];
+            u.x += ds[0]; u.y += ds[1]; w.x += ds[2]; w.y += ds[3];
+            slot[0] = u; slot[KTH] = w;
+          }
+          aP[2 * n] = pack2(pv[0], pv[1]);
+          aP[2 * n + 1] = pack2(pv[2], pv[3]);
+          aD[2 * n] = pack2(ds[0], ds[1]);
+          aD[2 * n + 1] = pack2(ds[2], ds[3]);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(panel_s + pw_offA + (uint32_t)(c * 16 + n * 8) * 2u), "r"(aD[2 * n]) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(panel_s + pw_offB + (uint32_t)(c * 16 + n * 8) * 2u), "r"(aD[2 * n + 1]) : "memory");
+        }
+        mma16816(dv[0], aP, bg0[0], bg0[1]);
+        mma16816(dv[1], aP, bg0[2], bg0[3]);
+        mma16816(dv[2], aP, bg2[0], bg2[1]);
+        mma16816(dv[3], aP, bg2[2], bg2[3]);
+        mma16816(dk[0], aD, bq0[0], bq0[1]);
+        mma16816(dk[1], aD, bq0[2], bq0[3]);
+        mma16816(dk[2], aD, bq2[0], bq2[1]);
+        mma16816(dk[3], aD, bq2[2], bq2[3]);
+      }
+    };
+    if (need_mask) sweep(std::true_type{}); else sweep(std::false_type{});
+
+    // ---- dV, dK of the warp's 16 keys.  k_hat of row g / g + 8 sits in the A fragments at the accumulator's columns.
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int t = half ? tokB : tokA;
+      float kh[4][2], dot = 0.f;
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) {
+        const uint32_t w = ka[dn >> 1][(dn & 1) * 2 + half];
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+        kh[dn][0] = f.x; kh[dn][1] = f.y;
+        dot = fmaf(dk[dn][2 * half], f.x, dot);
+        dot = fmaf(dk[dn][2 * half + 1], f.y, dot);
+      }
+      dot = quad_sum(dot) * sc;
+      if (t >= 0) {
+        const float invn = innorm[stage * NP + (half ? rB : rA)].y;          // 1 / ||k||
+        uint32_t* dkd = reinterpret_cast<uint32_t*>(a.dqkv + (int64_t)t * C3 + a.C + p.h * HD) + tq;
+        uint32_t* dvd = reinterpret_cast<uint32_t*>(a.dqkv + (int64_t)t * C3 + 2 * a.C + p.h * HD) + tq;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) {
+          dkd[dn * 4] = pack2((dk[dn][2 * half] * sc - kh[dn][0] * dot) * invn, (dk[dn][2 * half + 1] * sc - kh[dn][1] * dot) * invn);
+          dvd[dn * 4] = pack2(dv[dn][2 * half], dv[dn][2 * half + 1]);
+        }
+      } else if (t == -1) {
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) {
+          dvps[(dn * 2) * KTH] += dv[dn][2 * half];
+          dvps[(dn * 2 + 1) * KTH] += dv[dn][2 * half + 1];
+        }
+      }
+    }
+    // this warp's part of the panel is written and it no longer reads stage `stage`
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&pfull[stage]);
+  }
+}
+
+template <int WS>
+int launch_mma_bwd_spec(const MmaArgs& a, cudaStream_t st) {
+  using Sc = SCfg<WS>;
+  const size_t smem = Sc::SMEM;
+  BSW_REQUIRE(smem <= 227 * 1024, "attn_bwd(mma): window %dx%d needs %zu bytes of shared memory", WS, WS, smem);
+  BSW_CUDA(cudaFuncSetAttribute(attn_mma_bwd_spec_kernel<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = sm_count();
+  if (grid > a.nitems) grid = a.nitems;
+  attn_mma_bwd_spec_kernel<WS><<<(unsigned)grid, Sc::THREADS, smem, st>>>(a);
+  BSW_LAUNCH_CHECK();
+  return B200SWIN_OK;
+}
+
 int fill_mma_args(MmaArgs* a, int B, int H, int W, int C, int nH, int ws, int shift) {
   BSW_REQUIRE(B > 0 && H > 0 && W > 0 && nH > 0, "attn(mma): bad dimension");
   BSW_REQUIRE(C == nH * HD, "attn(mma): head_dim must be 32 (C=%d, nH=%d)", C, nH);
@@ -904,7 +1384,7 @@ size_t attn_bwd_mma_workspace_bytes(int B, int H, int W, int nH) { return (size_
 int attn_bwd_mma(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
                  const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
                  float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH,
-                 int ws, int shift, cudaStream_t st) {
+                 int ws, int shift, bool spec, cudaStream_t st) {
   BSW_REQUIRE(workspace, "attn_bwd(mma): workspace for D = <dO, O> missing");
   MmaArgs a = {};
   int rc = fill_mma_args(&a, B, H, W, C, nH, ws, shift);
@@ -919,7 +1399,7 @@ int attn_bwd_mma(const void* qkv, const void* out, const void* out_lo, const voi
     case 6: return launch_mma_bwd<6>(a, st);
     case 7: return launch_mma_bwd<7>(a, st);
     case 8: return launch_mma_bwd<8>(a, st);
-    case 12: return launch_mma_bwd<12>(a, st);
+    case 12: return spec ? launch_mma_bwd_spec<12>(a, st) : launch_mma_bwd<12>(a, st);
     default: break;
   }
   set_error("attn_bwd(mma): window %dx%d not instantiated", ws, ws);

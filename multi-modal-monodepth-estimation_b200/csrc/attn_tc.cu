@@ -22,7 +22,7 @@ size_t attn_bwd_mma_workspace_bytes(int B, int H, int W, int nH);
 int attn_bwd_mma(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
                  const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
                  float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH,
-                 int ws, int shift, cudaStream_t st);
+                 int ws, int shift, bool spec, cudaStream_t st);
 bool attn_bwd_ws_supported(int ws);
 size_t attn_bwd_ws_workspace_bytes(int B, int H, int W, int nH);
 int attn_bwd_ws(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
@@ -87,7 +87,7 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* out_lo, const void
   BSW_REQUIRE(family != kFamilyMma || attn_bwd_mma_supported(ws), "attn_bwd: no warp-MMA kernel for window %d", ws);
   if ((family == kFamilyAuto || family == kFamilyMma) && attn_bwd_mma_supported(ws))
     return attn_bwd_mma(qkv, out, out_lo, dout, lse, inv_norm, table16, scale, qpad, vpad, dqkv, dtable16, dscale, dvpad, workspace,
-                        B, H, W, C, nH, ws, shift, st);
+                        B, H, W, C, nH, ws, shift, /*spec=*/family == kFamilyAuto, st);
   if ((family == kFamilyAuto || family == kFamilyWs) && attn_bwd_ws_supported(ws))
     return attn_bwd_ws(qkv, out, out_lo, dout, lse, inv_norm, table16, scale, qpad, vpad, dqkv, dtable16, dscale, dvpad, workspace,
                        B, H, W, C, nH, ws, shift, st);
