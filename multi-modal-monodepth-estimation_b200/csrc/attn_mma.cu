@@ -115,6 +115,17 @@ __device__ __forceinline__ void put16(unsigned char* tile, uint32_t tile_s, uint
   }
 }
 
+// Byte offset 4 (y TW + x) into the bias table of in-window token q0 + 2 tq, q0 a compile-time multiple of 8 (even windows:
+// the pair (q, q + 1) shares a window row, the second entry is the first + 4 bytes).  Replaces a shared-memory table
+// read per column tile: the kernels are bound by shared-memory wavefronts, not by integer issue slots.
+template <int WS>
+__device__ __forceinline__ int kof_pair(int q0, int tq) {
+  constexpr int TW = 2 * WS - 1;
+  int y = q0 / WS, x = q0 % WS + 2 * tq;          // q0 / WS and q0 % WS fold at compile time when q0 does
+  if (x >= WS) { x -= WS; ++y; }
+  return 4 * (y * TW + x);
+}
+
 // window of an item and the source token of in-window row r: >= 0 flat token, -1 pad token, -2 row beyond the window
 struct ItemPos {
   int h, b, wh, ww;
@@ -709,7 +720,9 @@ attn_mma_bwd_kernel(const __grid_constant__ MmaArgs a) {
           for (int n = 0; n < 2; ++n) {
             const int qcol = c * 16 + n * 8 + 2 * tq;
             const float4 m = qm4[(c * 16 + n * 8) / 2 + tq];             // {lse, D} of queries qcol, qcol + 1
-            const int2 kq = *reinterpret_cast<const int2*>(kofk + qcol);
+            int2 kq;
+            if (WS % 2 == 0) kq.x = kof_pair<WS>(c * 16 + n * 8, tq), kq.y = kq.x + 4;
+            else kq = *reinterpret_cast<const int2*>(kofk + qcol);
             const uint32_t aA0 = tabA + (uint32_t)kq.x, aB0 = tabB + (uint32_t)kq.x;
             const uint32_t aA1 = (WS % 2 == 0) ? aA0 + 4u : tabA + (uint32_t)kq.y;
             const uint32_t aB1 = (WS % 2 == 0) ? aB0 + 4u : tabB + (uint32_t)kq.y;
@@ -1026,53 +1039,68 @@ attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
       const uint32_t q_s = base_u32 + (uint32_t)stage * Sc::STAGE_TILES, k_s = q_s + TILE;
       const uint32_t panel_s = base_u32 + Sc::OFF_PANEL + (uint32_t)stage * Sc::PANEL;
       const int* tokS = tokm + stage * NP;
-#pragma unroll 1
-      for (int k = 0; k < NT / Sc::NH; ++k) {
-        const int tile = k * Sc::NH + hw;
-        if (padf[stage * NT + tile]) continue;     // pad queries only: dQ rows of tokens that do not exist
-        const int rA = tile * 16 + gq, rB = rA + 8;
-        const uint32_t la_off = sw64(tile * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, lane >> 4);
-        const uint32_t pr_off = (uint32_t)((lane & 7) + (lane >> 4) * 8) * PSTRIDE + (uint32_t)(tile * 16 + ((lane >> 3) & 1) * 8) * 2u;
-        float dq[4][4];
+      {
+        constexpr int TPH = NT / Sc::NH;           // query tiles of this helper warp: hw, hw + NH, ...
+        bool live[TPH];
+        uint32_t pr_off[TPH];
+        float dq[TPH][4][4];
 #pragma unroll
-        for (int dn = 0; dn < 4; ++dn) dq[dn][0] = dq[dn][1] = dq[dn][2] = dq[dn][3] = 0.f;
+        for (int k = 0; k < TPH; ++k) {
+          const int tile = k * Sc::NH + hw;
+          live[k] = !padf[stage * NT + tile];      // pad queries only: dQ rows of tokens that do not exist
+          pr_off[k] = (uint32_t)((lane & 7) + (lane >> 4) * 8) * PSTRIDE + (uint32_t)(tile * 16 + ((lane >> 3) & 1) * 8) * 2u;
 #pragma unroll
-        for (int ks = 0; ks < NP / 16; ++ks) {
-          uint32_t ad[4], b0[4], b2[4];
-          ldsm4t(ad, panel_s + (uint32_t)(ks * 16) * PSTRIDE + pr_off);
+          for (int dn = 0; dn < 4; ++dn) dq[k][dn][0] = dq[k][dn][1] = dq[k][dn][2] = dq[k][dn][3] = 0.f;
+        }
+#pragma unroll
+        for (int ks = 0; ks < NP / 16; ++ks) {     // one load of the K fragments of 16 keys serves all tiles
+          uint32_t b0[4], b2[4];
           ldsm4t(b0, k_s + (uint32_t)(ks * 16) * 64u + lv_off0);
           ldsm4t(b2, k_s + (uint32_t)(ks * 16) * 64u + lv_off2);
-          mma16816(dq[0], ad, b0[0], b0[1]);
-          mma16816(dq[1], ad, b0[2], b0[3]);
-          mma16816(dq[2], ad, b2[0], b2[1]);
-          mma16816(dq[3], ad, b2[2], b2[3]);
-        }
-        uint32_t qa[2][4];
-        ldsm4(qa[0], q_s + la_off);
-        ldsm4(qa[1], q_s + (la_off ^ 32u));
-        const int tokA = tokS[rA], tokB = tokS[rB];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int t = half ? tokB : tokA;
-          float qh[4][2], dot = 0.f;
-#pragma unroll
-          for (int dn = 0; dn < 4; ++dn) {
-            const uint32_t w = qa[dn >> 1][(dn & 1) * 2 + half];
-            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
-            qh[dn][0] = f.x; qh[dn][1] = f.y;
-            dot = fmaf(dq[dn][2 * half], f.x, dot);
-            dot = fmaf(dq[dn][2 * half + 1], f.y, dot);
+          for (int k = 0; k < TPH; ++k) {
+            if (!live[k]) continue;
+            uint32_t ad[4];
+            ldsm4t(ad, panel_s + (uint32_t)(ks * 16) * PSTRIDE + pr_off[k]);
+            mma16816(dq[k][0], ad, b0[0], b0[1]);
+            mma16816(dq[k][1], ad, b0[2], b0[3]);
+            mma16816(dq[k][2], ad, b2[0], b2[1]);
+            mma16816(dq[k][3], ad, b2[2], b2[3]);
           }
-          dot = quad_sum(dot);
-          // gradient of the temperature: sum_k dS[q, k] cos[q, k] = <q_hat, sum_k dS[q, k] k_hat> = this very dot product
-          if (tq == 0) dsc += dot;
-          dot *= sc;
-          if (t < 0) continue;
-          const float invn = innorm[stage * NP + (half ? rB : rA)].x;            // 1 / ||q||
-          uint32_t* dqd = reinterpret_cast<uint32_t*>(a.dqkv + (int64_t)t * C3 + p.h * HD) + tq;
+        }
 #pragma unroll
-          for (int dn = 0; dn < 4; ++dn)
-            dqd[dn * 4] = pack2((dq[dn][2 * half] * sc - qh[dn][0] * dot) * invn, (dq[dn][2 * half + 1] * sc - qh[dn][1] * dot) * invn);
+        for (int k = 0; k < TPH; ++k) {
+          if (!live[k]) continue;
+          const int tile = k * Sc::NH + hw;
+          const int rA = tile * 16 + gq, rB = rA + 8;
+          const uint32_t la_off = sw64(tile * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, lane >> 4);
+          uint32_t qa[2][4];
+          ldsm4(qa[0], q_s + la_off);
+          ldsm4(qa[1], q_s + (la_off ^ 32u));
+          const int tokA = tokS[rA], tokB = tokS[rB];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int t = half ? tokB : tokA;
+            float qh[4][2], dot = 0.f;
+#pragma unroll
+            for (int dn = 0; dn < 4; ++dn) {
+              const uint32_t w = qa[dn >> 1][(dn & 1) * 2 + half];
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+              qh[dn][0] = f.x; qh[dn][1] = f.y;
+              dot = fmaf(dq[k][dn][2 * half], f.x, dot);
+              dot = fmaf(dq[k][dn][2 * half + 1], f.y, dot);
+            }
+            dot = quad_sum(dot);
+            // gradient of the temperature: sum_k dS[q, k] cos[q, k] = <q_hat, sum_k dS[q, k] k_hat> = this very dot product
+            if (tq == 0) dsc += dot;
+            dot *= sc;
+            if (t < 0) continue;
+            const float invn = innorm[stage * NP + (half ? rB : rA)].x;            // 1 / ||q||
+            uint32_t* dqd = reinterpret_cast<uint32_t*>(a.dqkv + (int64_t)t * C3 + p.h * HD) + tq;
+#pragma unroll
+            for (int dn = 0; dn < 4; ++dn)
+              dqd[dn * 4] = pack2((dq[k][dn][2 * half] * sc - qh[dn][0] * dot) * invn, (dq[k][dn][2 * half + 1] * sc - qh[dn][1] * dot) * invn);
+          }
         }
       }
       // every helper is done with panel / stage `stage`: hand the panel back and refill the stage
@@ -1235,7 +1263,9 @@ attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
         for (int n = 0; n < 2; ++n) {
           const int qcol = c * 16 + n * 8 + 2 * tq;
           const float4 m = qm4[(c * 16 + n * 8) / 2 + tq];             // {lse, D} of queries qcol, qcol + 1
-          const int2 kq = *reinterpret_cast<const int2*>(kofk + qcol);
+          int2 kq;
+          if (WS % 2 == 0) kq.x = kof_pair<WS>(c * 16 + n * 8, tq), kq.y = kq.x + 4;
+          else kq = *reinterpret_cast<const int2*>(kofk + qcol);
           const uint32_t aA0 = tabA + (uint32_t)kq.x, aB0 = tabB + (uint32_t)kq.x;
           const uint32_t aA1 = (WS % 2 == 0) ? aA0 + 4u : tabA + (uint32_t)kq.y;
           const uint32_t aB1 = (WS % 2 == 0) ? aB0 + 4u : tabB + (uint32_t)kq.y;
