@@ -151,9 +151,12 @@ int b200swin_cpb_bwd(const float* coords, const float* w0, const float* b0, cons
  * 1/max(|k|,1e-12)) and dv; plus float32 accumulators that the caller zero-initialises:
  * dtable16 [(2ws-1)^2, nH], dscale [nH] (= sum dS*cos), dvpad [C] (gradient reaching v_bias through
  * pad tokens).  impl: 0 = fp32 CUDA-core kernel (any dtype, reference precision),
- * 1 = tcgen05 tensor-core kernels (bf16 storage only; any window up to 32x32: single-tile kernels for windows
- * 4/6/7/8/12, KV-blocked kernels otherwise), 2 = the KV-blocked tcgen05 kernels whatever the window.
- * head_dim must be 32 (every Swin-V2 variant).
+ * 1 = tensor-core kernels, chosen by window size (bf16 storage only; any window up to 32x32: register-resident
+ * warp-level MMA kernels for windows 4/6/7/8/12 -- a window is 1..9 tiles of 16 rows, no 128-row tile to fill --
+ * KV-blocked tcgen05 kernels otherwise), 2 = the KV-blocked tcgen05 kernels whatever the window, 3 = the single-tile
+ * tcgen05 kernels (windows 4/6/7/8/12 forward, 4/6/7/12 backward), 4 = the warp-level MMA kernels without warp
+ * specialisation (2-4 exist for A/B timing and cross-checks).  head_dim must be 32 (every Swin-V2 variant).
+ * lse of a query row that is a pad token may be +inf (its output row does not exist).
  * out_lo (nullable; tensor-core implementations only): bf16 tensor of out's shape that receives the rounding residual
  * O - bf16(O).  Given back to the backward it makes D = <dO, O> accurate to ~2^-17; the bias-table and temperature
  * gradients are sums of dS = P (dP - D) that cancel row by row, and the 2^-9 rounding of O alone would put an error

@@ -102,7 +102,7 @@ def _wrap(name, fn):
         n = per_call
         if name == "b200swin_gemm_bf16" and args[18] > 1:
             n += 1
-        if name == "b200swin_attn_bwd" and args[24] in (1, 2) and (args[24] == 2 or args[21] not in (4, 6, 7, 12)):
+        if name == "b200swin_attn_bwd" and args[24] in (1, 2) and (args[24] == 2 or args[21] not in (4, 6, 7, 8, 12)):
             n += 1                                     # KV-blocked backward: prep + dQ pass + dK/dV pass
         COUNTERS["launches"] += n
         COUNTERS["calls"][name] = COUNTERS["calls"].get(name, 0) + 1

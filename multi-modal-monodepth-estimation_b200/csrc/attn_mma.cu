@@ -180,7 +180,8 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
   int* tokm = reinterpret_cast<int*>(tiles + kFwdStages * STAGE);         // [stages][NP] source token of a row
   int* ridm = tokm + kFwdStages * NP;                                     // [stages][NP] shift-mask region id
   int* kofk = ridm + kFwdStages * NP;                                     // [NP] byte offset 4 (y TW + x) of a window row
-  float* tab = reinterpret_cast<float*>(kofk + NP);                       // [NTAB] bias table of the head, log2 units
+  float* tab = reinterpret_cast<float*>(kofk + NP);                       // [NTAB] bias table of the head, log2 units, minus the softmax offset
+  float* tred = tab + Cf::NTAB;                                           // [2 NT] per-warp max / min of the table
   const uint32_t tiles_s = base_u32;
 
   const WinGeom& g = a.g;
@@ -233,7 +234,8 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
   ptx::cp_async_commit();
 
   int cur_h = -1;
-  float scale2 = 0.f;
+  float scale2 = 0.f, boff = 0.f;
+  bool fixed_off = false;
   const int rA = warp * 16 + gq, rB = rA + 8;
   ItemPos p = item_pos(a, it0);                  // cursor of the compute stream
   // lane-constant parts of the ldmatrix addresses (the swizzle term only sees the low row bits)
@@ -250,8 +252,28 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
     if (i + 2 < nit) prefetch(i + 2);             // into the stage item i - 1 has just released
     ptx::cp_async_commit();
     if (p.h != cur_h) {                           // CTA-uniform
-      for (int t = tid; t < Cf::NTAB; t += Cf::THREADS) tab[t] = a.table16[(int64_t)t * a.nH + p.h] * kLog2e;
+      // Bias table of the head and the softmax offset.  Logits are cos * scale + bias with |cos| <= 1 (+ bf16 rounding):
+      // when 2 scale + (range of the table) stays below 2^100 in the exponent, a FIXED offset scale + max(bias) makes
+      // every P <= ~1 and no row sum can underflow -- the row maximum, the rescale and the subtraction per logit
+      // disappear.  Heads whose temperature is too large for that (the clamp allows 100) take the online-softmax path.
+      float tmx = -INFINITY, tmn = INFINITY;
+      for (int t = tid; t < Cf::NTAB; t += Cf::THREADS) {
+        const float v = a.table16[(int64_t)t * a.nH + p.h] * kLog2e;
+        tmx = fmaxf(tmx, v);
+        tmn = fminf(tmn, v);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        tmx = fmaxf(tmx, __shfl_xor_sync(0xffffffffu, tmx, o));
+        tmn = fminf(tmn, __shfl_xor_sync(0xffffffffu, tmn, o));
+      }
+      if (lane == 0) { tred[2 * warp] = tmx; tred[2 * warp + 1] = tmn; }
+      __syncthreads();
+      for (int w = 0; w < Cf::NT; ++w) { tmx = fmaxf(tmx, tred[2 * w]); tmn = fminf(tmn, tred[2 * w + 1]); }
       scale2 = a.scale[p.h] * kLog2e;
+      fixed_off = 2.02f * scale2 + (tmx - tmn) < 100.f;
+      boff = fixed_off ? 1.01f * scale2 + tmx : 0.f;
+      for (int t = tid; t < Cf::NTAB; t += Cf::THREADS) tab[t] = a.table16[(int64_t)t * a.nH + p.h] * kLog2e - boff;
       cur_h = p.h;
       __syncthreads();
     }
@@ -277,13 +299,14 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
       }
       continue;
     }
-    float o[4][4];
+    float o[4][4], ol[4] = {0.f, 0.f, 0.f, 0.f};  // O and, as a fifth column tile against a ones operand, the row sums of P
 #pragma unroll
     for (int dn = 0; dn < 4; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
-    float mA = -INFINITY, mB = -INFINITY, lA = 0.f, lB = 0.f;
+    float mA = fixed_off ? 0.f : -INFINITY, mB = mA;           // reference maximum of the rows, relative to boff
+    constexpr uint32_t kOnes = 0x3f803f80u;       // bf16 (1, 1)
 
-    auto chunk = [&](int c, auto mask_c) {
-      constexpr bool MASK = decltype(mask_c)::value;
+    auto chunk = [&](int c, auto mask_c, auto fixed_c) {
+      constexpr bool MASK = decltype(mask_c)::value, FIXED = decltype(fixed_c)::value;
       const int key0 = c * CHN * 8;
       float s[CHN][4];
 #pragma unroll
@@ -314,31 +337,33 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
           if (kcol >= N) s[n][0] = s[n][2] = -INFINITY;
           if (kcol + 1 >= N) s[n][1] = s[n][3] = -INFINITY;
         }
-        mxA = fmaxf(mxA, fmaxf(s[n][0], s[n][1]));
-        mxB = fmaxf(mxB, fmaxf(s[n][2], s[n][3]));
-      }
-      // lazy rescale: the reference maximum of a row only moves when a chunk exceeds it by more than 2^8 (P <= 256 is
-      // harmless in fp32 / bf16), so after the first chunk the accumulators are almost never touched
-      mxA = quad_max(mxA);
-      mxB = quad_max(mxB);
-      const float mnA = mxA > mA + kLazy ? mxA : mA, mnB = mxB > mB + kLazy ? mxB : mB;
-      if (__any_sync(0xffffffffu, mnA != mA || mnB != mB)) {
-        const float cA = ex2f(mA - mnA), cB = ex2f(mB - mnB);
-        lA *= cA; lB *= cB;
-#pragma unroll
-        for (int dn = 0; dn < 4; ++dn) {
-          o[dn][0] *= cA; o[dn][1] *= cA; o[dn][2] *= cB; o[dn][3] *= cB;
+        if (!FIXED) {
+          mxA = fmaxf(mxA, fmaxf(s[n][0], s[n][1]));
+          mxB = fmaxf(mxB, fmaxf(s[n][2], s[n][3]));
         }
-        mA = mnA; mB = mnB;
+      }
+      if (!FIXED) {
+        // lazy rescale: the reference maximum of a row only moves when a chunk exceeds it by more than 2^8 (P <= 256 is
+        // harmless in fp32 / bf16), so after the first chunk the accumulators are almost never touched
+        mxA = quad_max(mxA);
+        mxB = quad_max(mxB);
+        const float mnA = mxA > mA + kLazy ? mxA : mA, mnB = mxB > mB + kLazy ? mxB : mB;
+        if (__any_sync(0xffffffffu, mnA != mA || mnB != mB)) {
+          const float cA = ex2f(mA - mnA), cB = ex2f(mB - mnB);
+          ol[0] *= cA; ol[1] *= cA; ol[2] *= cB; ol[3] *= cB;
+#pragma unroll
+          for (int dn = 0; dn < 4; ++dn) {
+            o[dn][0] *= cA; o[dn][1] *= cA; o[dn][2] *= cB; o[dn][3] *= cB;
+          }
+          mA = mnA; mB = mnB;
+        }
       }
 #pragma unroll
       for (int n = 0; n < CHN; ++n) {
-        s[n][0] = ex2f(s[n][0] - mnA);
-        s[n][1] = ex2f(s[n][1] - mnA);
-        s[n][2] = ex2f(s[n][2] - mnB);
-        s[n][3] = ex2f(s[n][3] - mnB);
-        lA += s[n][0] + s[n][1];
-        lB += s[n][2] + s[n][3];
+        s[n][0] = ex2f(FIXED ? s[n][0] : s[n][0] - mA);
+        s[n][1] = ex2f(FIXED ? s[n][1] : s[n][1] - mA);
+        s[n][2] = ex2f(FIXED ? s[n][2] : s[n][2] - mB);
+        s[n][3] = ex2f(FIXED ? s[n][3] : s[n][3] - mB);
       }
       // O += P V: the accumulator layout of two adjacent column tiles is the A layout of one 16-key step
 #pragma unroll
@@ -353,19 +378,31 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
         ldsm4t(vb, vrow_s + lv_off2);
         mma16816(o[2], pa, vb[0], vb[1]);
         mma16816(o[3], pa, vb[2], vb[3]);
+        mma16816(ol, pa, kOnes, kOnes);           // row sums of the (rounded) P: the weights O is built from
       }
     };
-    if (need_mask) {
+    if (fixed_off) {
+      if (need_mask) {
 #pragma unroll 1
-      for (int c = 0; c < Cf::NCH; ++c) chunk(c, std::true_type{});
+        for (int c = 0; c < Cf::NCH; ++c) chunk(c, std::true_type{}, std::true_type{});
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < Cf::NCH; ++c) chunk(c, std::false_type{}, std::true_type{});
+      }
     } else {
+      if (need_mask) {
 #pragma unroll 1
-      for (int c = 0; c < Cf::NCH; ++c) chunk(c, std::false_type{});
+        for (int c = 0; c < Cf::NCH; ++c) chunk(c, std::true_type{}, std::false_type{});
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < Cf::NCH; ++c) chunk(c, std::false_type{}, std::false_type{});
+      }
     }
 
     // ---- epilogue: normalise, store O (+ its bf16 residual) and the row's log-sum-exp
-    lA = quad_sum(lA);
-    lB = quad_sum(lB);
+    const float lA = ol[0], lB = ol[2];
+    mA += boff;
+    mB += boff;
     const int tokA = tokS[rA], tokB = tokS[rB];
     float* lse_it = a.lse + (p.win * a.nH + p.h) * N;
     if (tq == 0) {
@@ -398,7 +435,8 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
 template <int WS>
 size_t mma_fwd_smem() {
   using Cf = MCfg<WS>;
-  return 128 + (size_t)kFwdStages * 3 * Cf::TILE + 2 * (size_t)kFwdStages * Cf::NP * 4 + (size_t)Cf::NTAB * 4 + (size_t)Cf::NP * 4;
+  return 128 + (size_t)kFwdStages * 3 * Cf::TILE + 2 * (size_t)kFwdStages * Cf::NP * 4 + (size_t)Cf::NTAB * 4 + (size_t)Cf::NP * 4 +
+         2 * (size_t)Cf::NT * 4 + 16;
 }
 
 // CTAs of a kernel that fit one SM: shared memory, threads and the per-sub-partition register file (warps of a CTA are

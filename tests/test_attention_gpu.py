@@ -256,6 +256,30 @@ def _inputs(B, H, W, C, nH, ws, seed):
     return q, k, v, table, scale, qb, vb, cot
 
 
+@pytest.mark.parametrize("ws,H,shift", [(12, 30, 6), (6, 15, 3), (8, 20, 0)])
+def test_attention_large_temperature_takes_the_online_softmax_path(ws, H, shift):
+    """Temperatures up to the reference's clamp (exp(logit_scale) <= 100, swin_transformer_v2.py:294).  The warp-MMA forward
+    uses a fixed softmax offset only while 2 scale + range(bias) cannot underflow a row sum; these heads must take its
+    online-softmax path, and one head per case stays on the fixed-offset path."""
+    from b200swin import ops
+    B, C, nH = 2, 128, 4
+    q, k, v, table, scale, qb, vb, cot = _inputs(B, H, H, C, nH, ws, 77 + ws)
+    scale = torch.tensor([100.0, 61.0, 33.0, 7.0])
+    args = (q, k, v, table, scale, qb, vb, cot)
+    oref, gref = _oracle_core(*args, B, H, H, C, nH, ws, shift)
+    ops.ATTN_IMPL["mode"] = ops.ATTN_IMPL["bwd_mode"] = "tc"
+    try:
+        out, g = _run_core(*args, B, H, H, C, nH, ws, shift, torch.bfloat16)
+    finally:
+        ops.ATTN_IMPL["mode"] = ops.ATTN_IMPL["bwd_mode"] = "auto"
+    assert torch.isfinite(out.float()).all()
+    # sharp softmaxes (scale 100): bf16 q_hat / k_hat move a logit by up to 100 * 2^-8, so the bar is the bf16 one on the
+    # output and looser on the gradients that pass through P (1 - P)
+    assert _relerr(out, oref) < 4e-2
+    for nm, a, r in zip(["dq", "dk", "dv", "dtable"], g[:4], gref[:4]):
+        assert _relerr(a, r) < 1e-1, nm
+
+
 @pytest.mark.parametrize("B,H,W,C,nH,ws,shift,dtype,impl", [
     (2, 24, 24, 128, 4, 12, 6, torch.float32, "simt"), (1, 30, 30, 64, 2, 12, 6, torch.float32, "simt"),
     (2, 16, 20, 96, 3, 8, 4, torch.bfloat16, "simt"), (1, 15, 15, 64, 2, 6, 3, torch.float32, "simt"),
@@ -277,7 +301,17 @@ def _inputs(B, H, W, C, nH, ws, seed):
     (2, 32, 32, 64, 2, 16, 0, torch.bfloat16, "tc"), (1, 40, 24, 96, 3, 16, 8, torch.bfloat16, "tc"),
     (1, 30, 50, 64, 2, 24, 12, torch.bfloat16, "tc"), (1, 48, 48, 128, 4, 24, 0, torch.bfloat16, "tc"),
     (1, 40, 40, 64, 2, 30, 15, torch.bfloat16, "tc"), (2, 30, 30, 32, 1, 30, 0, torch.bfloat16, "tc"),
-    (1, 40, 70, 32, 1, 32, 16, torch.bfloat16, "tc")])
+    (1, 40, 70, 32, 1, 32, 16, torch.bfloat16, "tc"),
+    # long item streams per CTA for the warp-specialised backward (mbarrier pipeline over many items, head changes in
+    # the middle of a CTA's range, pad-only query tiles on the right / bottom edge)
+    (16, 36, 36, 128, 4, 12, 6, torch.bfloat16, "tc"), (12, 30, 30, 64, 2, 12, 6, torch.bfloat16, "tc"),
+    (12, 30, 30, 64, 2, 12, 0, torch.bfloat16, "tc"),
+    # the kernel families "auto" no longer picks for these windows stay covered: single-tile tcgen05 ("ws") and the
+    # warp-level MMA kernels without warp specialisation ("mma")
+    (2, 24, 24, 128, 4, 12, 6, torch.bfloat16, "ws"), (1, 30, 30, 64, 2, 12, 6, torch.bfloat16, "ws"),
+    (1, 15, 15, 64, 2, 6, 3, torch.bfloat16, "ws"), (1, 21, 14, 64, 2, 7, 3, torch.bfloat16, "ws"),
+    (2, 24, 24, 128, 4, 12, 6, torch.bfloat16, "mma"), (1, 30, 30, 64, 2, 12, 0, torch.bfloat16, "mma"),
+    (1, 21, 14, 64, 2, 7, 3, torch.bfloat16, "mma"), (2, 16, 20, 96, 3, 8, 4, torch.bfloat16, "mma")])
 def test_attention_core_vs_oracle(B, H, W, C, nH, ws, shift, dtype, impl):
     """The core kernel alone (natural-order qkv in, natural-order out), forward and every gradient, against the
     oracle's gather -> dense attention -> scatter in float64.  Bars: fp32 1e-4 (2e-4 on the long parameter-gradient
