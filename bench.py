@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--workload", default="c2_ws12", choices=sorted(BL.WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0, help="frame pairs per GPU (default: the workload's, BASELINE: 24)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--attn", default="auto", choices=["auto", "simt", "tc", "flash"])
+    ap.add_argument("--attn", default="auto", choices=["auto", "simt", "tc", "flash", "ws", "mma"])
     ap.add_argument("--cpu-sample-pairs", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip full_step / reference_cuda_eager / cpu_baseline")

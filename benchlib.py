@@ -305,7 +305,9 @@ def rooflines_from_events(events, steps, pk):
 def attn_evidence():
     """Tensor-pipe utilisation of the window-attention kernels from the committed ncu captures (profiles/*.json)."""
     out = {}
-    for key, name in (("fwd", "r02_ncu_attn_fwd_ws12"), ("bwd", "r02_ncu_attn_bwd_ws12"), ("fwd_r01", "r01_ncu_attn"),
+    for key, name in (("fwd", "r02_ncu_attn_mma_fwd_ws12"), ("bwd", "r02_ncu_attn_mma_bwd_ws12"),
+                      ("fwd_single_tile_tcgen05", "r02_ncu_attn_fwd_ws12"), ("bwd_single_tile_tcgen05", "r02_ncu_attn_bwd_ws12"),
+                      ("fwd_r01", "r01_ncu_attn"),
                       ("bwd_r01", "r01_ncu_attn_bwd"), ("fwd_kv_blocked_ws24", "r02_ncu_attn_flash_fwd_ws24"),
                       ("bwd_kv_blocked_ws24", "r02_ncu_attn_flash_bwd_ws24")):
         d = committed_ncu(name)
