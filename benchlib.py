@@ -264,14 +264,15 @@ def rooflines_from_events(events, steps, pk):
                    {0: "", 1: "+gelu", 2: "+qkvnorm", 3: "*gelu'", 4: "+residual"}[a[9]]
             add("gemm." + kind, ms, fl)
         elif name in ("b200swin_attn_fwd", "b200swin_attn_bwd"):
-            off = 10 if name.endswith("fwd") else 16
+            off = 10 if name.endswith("fwd") else 17
             B, H, W, C, nH, ws = a[off:off + 6]
             Tp = B * ((H + ws - 1) // ws * ws) * ((W + ws - 1) // ws * ws)
             T, N = B * H * W, ws * ws
             if name.endswith("fwd"):
                 add("attn_fwd", ms, 4.0 * Tp * N * C, 8.0 * T * C, float(Tp) * N * nH)
             else:
-                add("attn_bwd", ms, 10.0 * Tp * N * C, 16.0 * T * C, float(Tp) * N * nH)
+                # one exp2 per logit in the single-pass backward (windows 4 - 12), two in the KV-blocked two-pass backward
+                add("attn_bwd", ms, 10.0 * Tp * N * C, 16.0 * T * C, float(Tp) * N * nH * (1.0 if ws in (4, 6, 7, 8, 12) else 2.0))
         elif name == "b200swin_ln_fwd":
             rows, C = a[9], a[10]
             es = 2 if a[12] == 1 else 4
@@ -295,7 +296,7 @@ def rooflines_from_events(events, steps, pk):
             d["gbs"] = f["bytes"] / steps / (ms / 1e3) / 1e9
             d["frac_of_hbm_peak"] = d["gbs"] / pk["hbm_gbs"]
         if f["exps"]:
-            floor_ms = f["exps"] / steps / (16.0 * n_sm * sm_hz) * 1e3 * (2.0 if k == "attn_bwd" else 1.0)
+            floor_ms = f["exps"] / steps / (16.0 * n_sm * sm_hz) * 1e3
             d["mufu_floor_ms_per_step"] = floor_ms
             d["frac_of_mufu_floor"] = floor_ms / ms if ms > 0 else None
         out[k] = d

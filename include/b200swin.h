@@ -170,9 +170,14 @@ size_t b200swin_attn_bwd_workspace_bytes(int B, int H, int W, int nH, int ws, in
 int b200swin_attn_bwd(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse,
                       const float* inv_norm,
                       const float* table16, const float* scale, const float* qpad, const float* vpad,
-                      const float* mask, int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, int B,
-                      int H, int W, int C, int nH, int ws, int shift, int dtype, int impl, void* workspace,
-                      size_t workspace_bytes, void* stream);
+                      const float* mask, int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad,
+                      float* dqkv_colsum, int B, int H, int W, int C, int nH, int ws, int shift, int dtype, int impl,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* 1 when b200swin_attn_bwd for this window / dtype / impl can also add the column sums of dq and dv -- the gradients of
+ * q_bias and v_bias that flow through real tokens -- to dqkv_colsum [3C] float32 (zero-initialised by the caller; the
+ * middle C entries, k has no bias, are not touched).  The rows are in registers in the backward's epilogue; without it the
+ * caller makes one more pass over dqkv (b200swin_colsum).  dqkv_colsum must be NULL where this returns 0. */
+int b200swin_attn_bwd_colsum_supported(int ws, int dtype, int impl);
 
 /* ------------------------------------------------------------------------------------------
  * Dense contraction on tcgen05 tensor cores:  out[M,N] = epilogue( A[M,K] . B[N,K]^T ).

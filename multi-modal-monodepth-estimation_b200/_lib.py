@@ -43,7 +43,8 @@ SIGNATURES = {
     "b200swin_ln_bwd": (I, [P, P, P, P, P, P, L, P, P, P, P, L, I, I, P, Z, P]),
     "b200swin_attn_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P]),
     "b200swin_attn_bwd_workspace_bytes": (Z, [I, I, I, I, I, I, I]),
-    "b200swin_attn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, I, I, I, I, I, I, I, I, I, P, Z, P]),
+    "b200swin_attn_bwd_colsum_supported": (I, [I, I, I]),
+    "b200swin_attn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, Z, P]),
     "b200swin_gemm_splits": (I, [L, L, L]),
     "b200swin_gemm_workspace_bytes": (Z, [L, L, I]),
     "b200swin_gemm_bf16": (I, [P, P, I, P, P, I, L, L, L, I, P, P, P, P, P, I, P, I, I, P, Z, P]),
@@ -102,7 +103,7 @@ def _wrap(name, fn):
         n = per_call
         if name == "b200swin_gemm_bf16" and args[18] > 1:
             n += 1
-        if name == "b200swin_attn_bwd" and args[24] in (1, 2) and (args[24] == 2 or args[21] not in (4, 6, 7, 8, 12)):
+        if name == "b200swin_attn_bwd" and args[25] in (1, 2) and (args[25] == 2 or args[22] not in (4, 6, 7, 8, 12)):
             n += 1                                     # KV-blocked backward: prep + dQ pass + dK/dV pass
         COUNTERS["launches"] += n
         COUNTERS["calls"][name] = COUNTERS["calls"].get(name, 0) + 1

@@ -61,6 +61,7 @@ struct MmaArgs {
   float* dtable16;
   float* dscale;
   float* dvpad;
+  float* dcol;                // optional [3C]: column sums of dq (first C) and dv (last C) = q_bias / v_bias gradients
   WinGeom g;
   int C, nH;
   int64_t nwin, nitems;       // item = head * nwin + window
@@ -940,7 +941,8 @@ struct SCfg {
   static constexpr int DBS = 8;                                               // column tiles whose sums live in smem
   static constexpr uint32_t OFF_DBS = OFF_BARS + 64;
   static constexpr uint32_t OFF_DVP = OFF_DBS + DBS * 2 * KTHREADS * 8;
-  static constexpr uint32_t SMEM = OFF_DVP + 8 * KTHREADS * 4 + 128;
+  static constexpr uint32_t OFF_DVS = OFF_DVP + 8 * KTHREADS * 4;              // [8][KTHREADS] float: column sums of dV
+  static constexpr uint32_t SMEM = OFF_DVS + 8 * KTHREADS * 4 + 128;
   static_assert((Cf::NP / 2) * Cf::NP * 4 <= PANEL, "the flush staging lives in a panel");
   static_assert(Cf::NT % NH == 0, "tiles per helper warp");
 };
@@ -1059,10 +1061,26 @@ attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
     ItemPos p = item_pos(a, it0);
     int cur_h = -1;
     float dsc = 0.f;
+    float dqs[4][2];                              // column sums of dq over this warp's rows (gradient of q_bias)
+#pragma unroll
+    for (int dn = 0; dn < 4; ++dn) dqs[dn][0] = dqs[dn][1] = 0.f;
     auto flush_dsc = [&](int h) {
       const float s = warp_sum(dsc);
       dsc = 0.f;
       if (lane == 0 && s != 0.f) atomicAdd(a.dscale + h, s);
+      if (a.dcol) {
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            float v = dqs[dn][e];
+            dqs[dn][e] = 0.f;
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (gq == 0 && v != 0.f) atomicAdd(a.dcol + h * HD + dn * 8 + 2 * tq + e, v);
+          }
+      }
     };
 #pragma unroll 1
     for (int i = 0; i < nit; ++i, item_next(a, p)) {
@@ -1136,8 +1154,13 @@ attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
             const float invn = innorm[stage * NP + (half ? rB : rA)].x;            // 1 / ||q||
             uint32_t* dqd = reinterpret_cast<uint32_t*>(a.dqkv + (int64_t)t * C3 + p.h * HD) + tq;
 #pragma unroll
-            for (int dn = 0; dn < 4; ++dn)
-              dqd[dn * 4] = pack2((dq[k][dn][2 * half] * sc - qh[dn][0] * dot) * invn, (dq[k][dn][2 * half + 1] * sc - qh[dn][1] * dot) * invn);
+            for (int dn = 0; dn < 4; ++dn) {
+              const float g0 = (dq[k][dn][2 * half] * sc - qh[dn][0] * dot) * invn;
+              const float g1 = (dq[k][dn][2 * half + 1] * sc - qh[dn][1] * dot) * invn;
+              dqd[dn * 4] = pack2(g0, g1);
+              dqs[dn][0] += g0;
+              dqs[dn][1] += g1;
+            }
           }
         }
       }
@@ -1154,6 +1177,7 @@ attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
   // ================================================================================================== key warps
   float2* dbs = reinterpret_cast<float2*>(sm + Sc::OFF_DBS) + tid;           // + slot * KTH
   float* dvps = reinterpret_cast<float*>(sm + Sc::OFF_DVP) + tid;            // + slot * KTH
+  float* dvs = reinterpret_cast<float*>(sm + Sc::OFF_DVS) + tid;             // + slot * KTH
   constexpr int DBS = Sc::DBS, NREG = NT8 - DBS;
   int cur_h = -1;
   float sc = 0.f, scale2 = 0.f;
@@ -1168,10 +1192,23 @@ attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
 #pragma unroll
   for (int n = 0; n < DBS * 2; ++n) dbs[n * KTH] = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int e = 0; e < 8; ++e) dvps[e * KTH] = 0.f;
+  for (int e = 0; e < 8; ++e) dvps[e * KTH] = dvs[e * KTH] = 0.f;
 
   auto flush_head = [&](int h, unsigned char* panel) {
     // key warps only (named barrier 1); `panel` is a panel the helpers have handed back
+    if (a.dcol) {
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float v = dvs[(dn * 2 + e) * KTH];
+          dvs[(dn * 2 + e) * KTH] = 0.f;
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (gq == 0 && v != 0.f) atomicAdd(a.dcol + 2 * a.C + h * HD + dn * 8 + 2 * tq + e, v);
+        }
+    }
     if (a.dvpad) {
 #pragma unroll
       for (int dn = 0; dn < 4; ++dn)
@@ -1380,6 +1417,13 @@ attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
           dkd[dn * 4] = pack2((dk[dn][2 * half] * sc - kh[dn][0] * dot) * invn, (dk[dn][2 * half + 1] * sc - kh[dn][1] * dot) * invn);
           dvd[dn * 4] = pack2(dv[dn][2 * half], dv[dn][2 * half + 1]);
         }
+        if (a.dcol) {
+#pragma unroll
+          for (int dn = 0; dn < 4; ++dn) {
+            dvs[(dn * 2) * KTH] += dv[dn][2 * half];
+            dvs[(dn * 2 + 1) * KTH] += dv[dn][2 * half + 1];
+          }
+        }
       } else if (t == -1) {
 #pragma unroll
         for (int dn = 0; dn < 4; ++dn) {
@@ -1451,15 +1495,16 @@ size_t attn_bwd_mma_workspace_bytes(int B, int H, int W, int nH) { return (size_
 
 int attn_bwd_mma(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
                  const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
-                 float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH,
-                 int ws, int shift, bool spec, cudaStream_t st) {
+                 float* dtable16, float* dscale, float* dvpad, float* dcol, void* workspace, int B, int H, int W, int C,
+                 int nH, int ws, int shift, bool spec, cudaStream_t st) {
   BSW_REQUIRE(workspace, "attn_bwd(mma): workspace for D = <dO, O> missing");
+  BSW_REQUIRE(!dcol || (spec && ws == 12), "attn_bwd(mma): column sums come only from the warp-specialised 12x12 kernel");
   MmaArgs a = {};
   int rc = fill_mma_args(&a, B, H, W, C, nH, ws, shift);
   if (rc) return rc;
   a.qkv = (const __nv_bfloat16*)qkv; a.dout = (const __nv_bfloat16*)dout; a.lse = const_cast<float*>(lse);
   a.dvec = (const float*)workspace; a.inv_norm = inv_norm; a.table16 = table16; a.scale = scale; a.qpad = qpad;
-  a.vpad = vpad; a.dqkv = (__nv_bfloat16*)dqkv; a.dtable16 = dtable16; a.dscale = dscale; a.dvpad = dvpad;
+  a.vpad = vpad; a.dqkv = (__nv_bfloat16*)dqkv; a.dtable16 = dtable16; a.dscale = dscale; a.dvpad = dvpad; a.dcol = dcol;
   rc = attn_bwd_prep(dout, out, out_lo, (float*)workspace, (int64_t)B * H * W * nH, st);
   if (rc) return rc;
   switch (ws) {

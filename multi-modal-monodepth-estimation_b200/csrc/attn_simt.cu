@@ -472,9 +472,10 @@ int attn_fwd_tc(const void* qkv, void* out, void* out_lo, float* lse, const floa
                 int family, cudaStream_t st);
 int attn_bwd_tc(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
                 const float* table16, const float* scale, const float* qpad, const float* vpad, const float* mask,
-                int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, void* workspace,
+                int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, float* dcol, void* workspace,
                 size_t workspace_bytes, int B, int H, int W, int C, int nH, int ws, int shift, int family,
                 cudaStream_t st);
+bool attn_bwd_tc_colsum_supported(int ws, int family);
 size_t attn_bwd_tc_workspace_bytes(int B, int H, int W, int nH, int ws);
 
 }  // namespace b200swin
@@ -507,11 +508,16 @@ extern "C" size_t b200swin_attn_bwd_workspace_bytes(int B, int H, int W, int nH,
   return attn_bwd_tc_workspace_bytes(B, H, W, nH, ws);
 }
 
+extern "C" int b200swin_attn_bwd_colsum_supported(int ws, int dtype, int impl) {
+  return (dtype == B200SWIN_BF16 && impl >= 1 && impl <= 4 && attn_bwd_tc_colsum_supported(ws, impl - 1)) ? 1 : 0;
+}
+
 extern "C" int b200swin_attn_bwd(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse,
                                  const float* inv_norm, const float* table16, const float* scale, const float* qpad,
                                  const float* vpad, const float* mask, int nWm, void* dqkv, float* dtable16,
-                                 float* dscale, float* dvpad, int B, int H, int W, int C, int nH, int ws, int shift,
-                                 int dtype, int impl, void* workspace, size_t workspace_bytes, void* stream) {
+                                 float* dscale, float* dvpad, float* dqkv_colsum, int B, int H, int W, int C, int nH,
+                                 int ws, int shift, int dtype, int impl, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
   BSW_REQUIRE(qkv && out && dout && lse && inv_norm && table16 && scale && dqkv && dtable16 && dscale,
               "attn_bwd: null pointer");
   BSW_REQUIRE(dtype == B200SWIN_F32 || dtype == B200SWIN_BF16, "attn_bwd: bad dtype %d", dtype);
@@ -519,9 +525,10 @@ extern "C" int b200swin_attn_bwd(const void* qkv, const void* out, const void* o
   if (impl >= 1 && impl <= 4) {
     BSW_REQUIRE(dtype == B200SWIN_BF16, "attn_bwd: the tensor-core path stores bf16");
     return attn_bwd_tc(qkv, out, out_lo, dout, lse, inv_norm, table16, scale, qpad, vpad, mask, nWm, dqkv, dtable16, dscale,
-                       dvpad, workspace, workspace_bytes, B, H, W, C, nH, ws, shift, impl - 1, st);
+                       dvpad, dqkv_colsum, workspace, workspace_bytes, B, H, W, C, nH, ws, shift, impl - 1, st);
   }
   BSW_REQUIRE(impl == 0, "attn_bwd: unknown impl %d", impl);
+  BSW_REQUIRE(!dqkv_colsum, "attn_bwd: the CUDA-core kernels do not produce the column sums");
   (void)out_lo;
   AttnDims d;
   int threads;

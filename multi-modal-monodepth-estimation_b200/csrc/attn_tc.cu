@@ -21,8 +21,8 @@ bool attn_bwd_mma_supported(int ws);
 size_t attn_bwd_mma_workspace_bytes(int B, int H, int W, int nH);
 int attn_bwd_mma(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
                  const float* table16, const float* scale, const float* qpad, const float* vpad, void* dqkv,
-                 float* dtable16, float* dscale, float* dvpad, void* workspace, int B, int H, int W, int C, int nH,
-                 int ws, int shift, bool spec, cudaStream_t st);
+                 float* dtable16, float* dscale, float* dvpad, float* dcol, void* workspace, int B, int H, int W, int C,
+                 int nH, int ws, int shift, bool spec, cudaStream_t st);
 bool attn_bwd_ws_supported(int ws);
 size_t attn_bwd_ws_workspace_bytes(int B, int H, int W, int nH);
 int attn_bwd_ws(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
@@ -67,6 +67,9 @@ int attn_fwd_tc(const void* qkv, void* out, void* out_lo, float* lse, const floa
   return attn_fwd_flash(qkv, out, out_lo, lse, table16, scale, qpad, vpad, B, H, W, C, nH, ws, shift, st);
 }
 
+// whether the backward for this window adds the column sums of dq / dv (q_bias / v_bias gradients) to `dqkv_colsum`
+bool attn_bwd_tc_colsum_supported(int ws, int family) { return family == kFamilyAuto && ws == 12 && attn_bwd_mma_supported(ws); }
+
 size_t attn_bwd_tc_workspace_bytes(int B, int H, int W, int nH, int ws) {
   // all families need the same scratch: D = <dO, O> per (token, head)
   if (attn_bwd_mma_supported(ws)) return attn_bwd_mma_workspace_bytes(B, H, W, nH);
@@ -75,7 +78,7 @@ size_t attn_bwd_tc_workspace_bytes(int B, int H, int W, int nH, int ws) {
 
 int attn_bwd_tc(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse, const float* inv_norm,
                 const float* table16, const float* scale, const float* qpad, const float* vpad, const float* mask,
-                int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, void* workspace,
+                int nWm, void* dqkv, float* dtable16, float* dscale, float* dvpad, float* dcol, void* workspace,
                 size_t workspace_bytes, int B, int H, int W, int C, int nH, int ws, int shift, int family,
                 cudaStream_t st) {
   (void)nWm;
@@ -86,8 +89,9 @@ int attn_bwd_tc(const void* qkv, const void* out, const void* out_lo, const void
   BSW_REQUIRE(family != kFamilyWs || attn_bwd_ws_supported(ws), "attn_bwd: no single-tile kernel for window %d", ws);
   BSW_REQUIRE(family != kFamilyMma || attn_bwd_mma_supported(ws), "attn_bwd: no warp-MMA kernel for window %d", ws);
   if ((family == kFamilyAuto || family == kFamilyMma) && attn_bwd_mma_supported(ws))
-    return attn_bwd_mma(qkv, out, out_lo, dout, lse, inv_norm, table16, scale, qpad, vpad, dqkv, dtable16, dscale, dvpad, workspace,
-                        B, H, W, C, nH, ws, shift, /*spec=*/family == kFamilyAuto, st);
+    return attn_bwd_mma(qkv, out, out_lo, dout, lse, inv_norm, table16, scale, qpad, vpad, dqkv, dtable16, dscale, dvpad, dcol,
+                        workspace, B, H, W, C, nH, ws, shift, /*spec=*/family == kFamilyAuto, st);
+  BSW_REQUIRE(!dcol, "attn_bwd: this kernel family does not produce the column sums (see b200swin_attn_bwd_colsum_supported)");
   if ((family == kFamilyAuto || family == kFamilyWs) && attn_bwd_ws_supported(ws))
     return attn_bwd_ws(qkv, out, out_lo, dout, lse, inv_norm, table16, scale, qpad, vpad, dqkv, dtable16, dscale, dvpad, workspace,
                        B, H, W, C, nH, ws, shift, st);

@@ -603,10 +603,31 @@ class _QKV(torch.autograd.Function):
         dw = _wgrad(do, Operand(xhi, xlo), M, N, K).to(weight.dtype)
         dqb = dvb = None
         if ctx.has_bias:
-            cs = colsum(d2)                    # one pass over all 3C columns (two launches) instead of two over C each
+            cs = _take_colsum(dqkv)            # from the attention backward's epilogue when it provides them
+            if cs is None:
+                cs = colsum(d2)                # one pass over all 3C columns (two launches) instead of two over C each
             dqb = cs[:C].to(ctx.bdtype)
             dvb = cs[2 * C:].to(ctx.bdtype)
         return dx, dw, dqb, dvb, None, None
+
+
+# Column sums of dqkv handed from _AttnCore.backward to _QKV.backward.  Autograd re-wraps the gradient (a view in
+# between), so the hand-over is keyed by the data pointer; the entry keeps the gradient tensor alive until it is taken, so
+# the address cannot be reused by another tensor meanwhile.  Unclaimed entries (a qkv that needs no gradient) are dropped.
+_DQKV_COLSUM = {}
+
+
+def _stash_colsum(dqkv, sums):
+    if len(_DQKV_COLSUM) >= 8:
+        _DQKV_COLSUM.clear()
+    _DQKV_COLSUM[dqkv.data_ptr()] = (dqkv, sums)
+
+
+def _take_colsum(dqkv):
+    ent = _DQKV_COLSUM.pop(dqkv.data_ptr(), None)
+    if ent is None or ent[0].shape.numel() != dqkv.shape.numel() or ent[0].dtype != dqkv.dtype:
+        return None
+    return ent[1]
 
 
 def qkv_project(x, weight, q_bias, v_bias, nH, passthrough=False):
@@ -731,18 +752,24 @@ class _AttnCore(torch.autograd.Function):
             dout = dout.to(qkv.dtype)
         with torch.cuda.device_of(qkv):
             dqkv = torch.empty_like(qkv)
-            acc = torch.zeros(t16.numel() + nH + C, dtype=torch.float32, device=qkv.device)
+            # column sums of dq / dv (q_bias / v_bias gradients) straight from the backward's epilogue where the kernel
+            # can: saves the qkv projection's backward a pass over dqkv
+            want_cs = bool(lib.b200swin_attn_bwd_colsum_supported(ws, L.dtype_code(qkv), ctx.impl_bwd))
+            acc = torch.zeros(t16.numel() + nH + C + (3 * C if want_cs else 0), dtype=torch.float32, device=qkv.device)
             dt16 = acc[:t16.numel()].view_as(t16)
             dsc = acc[t16.numel():t16.numel() + nH]
-            dvp = acc[t16.numel() + nH:]
+            dvp = acc[t16.numel() + nH:t16.numel() + nH + C]
+            dcs = acc[t16.numel() + nH + C:] if want_cs else None
             ws_bytes = lib.b200swin_attn_bwd_workspace_bytes(B, H, W, nH, ws, L.dtype_code(qkv), ctx.impl_bwd)
             wsp = torch.empty(ws_bytes, dtype=torch.uint8, device=qkv.device) if ws_bytes else None
             L.check(lib.b200swin_attn_bwd(qkv.data_ptr(), out.data_ptr(), L.ptr(out_lo) if ctx.impl_bwd != 0 else 0,
                                           dout.data_ptr(), lse.data_ptr(),
                                           inv_norm.data_ptr(), t16.data_ptr(), sc.data_ptr(), L.ptr(qp), L.ptr(vp),
                                           L.ptr(mk), ctx.nWm, dqkv.data_ptr(), dt16.data_ptr(), dsc.data_ptr(),
-                                          dvp.data_ptr(), B, H, W, C, nH, ws, shift, L.dtype_code(qkv), ctx.impl_bwd,
-                                          L.ptr(wsp), ws_bytes, L.stream_of(qkv)), "attn_bwd")
+                                          dvp.data_ptr(), L.ptr(dcs), B, H, W, C, nH, ws, shift, L.dtype_code(qkv),
+                                          ctx.impl_bwd, L.ptr(wsp), ws_bytes, L.stream_of(qkv)), "attn_bwd")
+        if want_cs:
+            _stash_colsum(dqkv, dcs)
         tdt, sdt, vdt = ctx.dtypes
         return (dqkv, None, dt16.to(tdt), dsc.view(sc.shape).to(sdt), None,
                 dvp.to(vdt) if vdt is not None else None, None, None)

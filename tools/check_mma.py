@@ -43,12 +43,20 @@ def run(impl, bwd):
         wsp = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
         dqkv = torch.zeros(T, 3 * C, device=dev, dtype=torch.bfloat16)
         acc = torch.zeros(tab.numel() + nH + C, device=dev)
+        cs_ok = bool(lib.b200swin_attn_bwd_colsum_supported(ws, 1, impl))
+        dcol = torch.zeros(3 * C, device=dev) if cs_ok else None
         L.check(lib.b200swin_attn_bwd(qkv.data_ptr(), out.data_ptr(), out_lo.data_ptr(), dout.data_ptr(), lse.data_ptr(), inv_norm.data_ptr(),
                                       tab.data_ptr(), scale.data_ptr(), qpad.data_ptr(), vpad.data_ptr(), None, 0, dqkv.data_ptr(),
                                       acc.data_ptr(), acc.data_ptr() + 4 * tab.numel(), acc.data_ptr() + 4 * (tab.numel() + nH),
+                                      dcol.data_ptr() if cs_ok else None,
                                       B, H, W, C, nH, ws, a.shift, 1, impl, wsp.data_ptr(), wsb, st), "bwd")
         res += [dqkv[:, :C].float(), dqkv[:, C:2 * C].float(), dqkv[:, 2 * C:].float(), acc[:tab.numel()].clone(),
                 acc[tab.numel():tab.numel() + nH].clone(), acc[tab.numel() + nH:].clone()]
+        if cs_ok:
+            ref_q, ref_v = dqkv[:, :C].float().sum(0), dqkv[:, 2 * C:].float().sum(0)
+            eq = ((dcol[:C] - ref_q).norm() / ref_q.norm()).item()
+            ev = ((dcol[2 * C:] - ref_v).norm() / ref_v.norm()).item()
+            print(f"impl {impl}: column sums from the kernel vs sum over dqkv rows: dq {eq:.2e}  dv {ev:.2e}  (k part untouched: {float(dcol[C:2 * C].abs().max()):.1e})")
     return res
 
 def timeit(impl, bwd):
@@ -72,7 +80,7 @@ def timeit(impl, bwd):
         if bwd:
             lib.b200swin_attn_bwd(qkv.data_ptr(), out.data_ptr(), out_lo.data_ptr(), dout.data_ptr(), lse.data_ptr(), inv_norm.data_ptr(),
                                   tab.data_ptr(), scale.data_ptr(), qpad.data_ptr(), vpad.data_ptr(), None, 0, dqkv.data_ptr(),
-                                  acc.data_ptr(), acc.data_ptr() + 4 * tab.numel(), acc.data_ptr() + 4 * (tab.numel() + nH),
+                                  acc.data_ptr(), acc.data_ptr() + 4 * tab.numel(), acc.data_ptr() + 4 * (tab.numel() + nH), None,
                                   B, H, W, C, nH, ws, a.shift, 1, impl, wsp.data_ptr(), wsb, st)
         e2.record()
         torch.cuda.synchronize()

@@ -53,7 +53,7 @@ def bwd():
     L.check(lib.b200swin_attn_bwd(qkv.data_ptr(), out.data_ptr(), out_lo.data_ptr(), dout.data_ptr(), lse.data_ptr(), inv.data_ptr(),
                                   tab.data_ptr(), sc.data_ptr(), qpad.data_ptr(), vpad.data_ptr(), None, 0,
                                   dqkv.data_ptr(), acc.data_ptr(), acc.data_ptr() + 4 * tab.numel(),
-                                  acc.data_ptr() + 4 * (tab.numel() + nH), B, H, W, C, nH, ws, a.shift, 1, a.impl,
+                                  acc.data_ptr() + 4 * (tab.numel() + nH), None, B, H, W, C, nH, ws, a.shift, 1, a.impl,
                                   wsp.data_ptr(), wsb, st), "bwd")
 
 
