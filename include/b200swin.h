@@ -84,6 +84,17 @@ int b200swin_patch_merge(const void* in, void* out, int B, int H, int W, int C, 
 int b200swin_patchify(const void* x, int x_dtype, void* cols, int cols_dtype, int B, int Cin, int H, int W, int ph,
                       int pw, void* stream);
 
+/* Depthwise 3x3 convolution (stride 1, zero padding 1, no bias) in the token layout: the conv_proj of ConvMlp
+ * (models/swin_transformer_v2.py:98-111, mlp_type='conv' / 'conv_ln'), without the NHWC <-> NCHW permutes around cuDNN.
+ *   x, y [B,H,W,C] (dtype), weight [C,1,3,3] float32 (nn.Conv2d layout):  y[b,i,j,c] = sum_uv w[c,u,v] x[b,i+u-1,j+v-1,c]
+ * transpose = 1 applies the adjoint (taps flipped): dx from dy.  wgrad: dweight [C,1,3,3] float32, deterministic
+ * (per-CTA partials in `workspace`, fixed-order reduce).  C % 4 == 0. */
+int b200swin_dwconv3x3(const void* x, const float* weight, void* y, int B, int H, int W, int C, int dtype, int transpose,
+                       void* stream);
+size_t b200swin_dwconv3x3_wgrad_workspace_bytes(int B, int H, int W, int C);
+int b200swin_dwconv3x3_wgrad(const void* x, const void* dy, float* dweight, int B, int H, int W, int C, int dtype,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * LayerNorm (+ DropPath scale + residual).  Replaces LayerNormFP32.forward
  * (models/swin_transformer_v2.py:41-47) and the post-norm residual adds (:472-474, :482-483):
@@ -165,6 +176,10 @@ int b200swin_cpb_bwd(const float* coords, const float* w0, const float* b0, cons
 int b200swin_attn_fwd(const void* qkv, void* out, void* out_lo, float* lse, const float* table16, const float* scale,
                       const float* qpad, const float* vpad, const float* mask, int nWm, int B, int H, int W,
                       int C, int nH, int ws, int shift, int dtype, int impl, void* stream);
+/* attn_type='normal' (models/swin_transformer_v2.py:296-298): q and k are NOT normalised (the caller projects with
+ * B200SWIN_EPI_NONE), scale[h] = qk_scale or head_dim^-0.5 for every head, qpad = q_bias as it is, and the backward is
+ * called with inv_norm = NULL: dq, dk are then the plain gradients (no F.normalize backward).  Served by impl 0 and 2
+ * (the warp-MMA forward drops the row maximum under the cosine bound |q.k| <= 1, which does not hold here). */
 /* bytes of caller-owned scratch the backward needs for this shape / implementation (0: none) */
 size_t b200swin_attn_bwd_workspace_bytes(int B, int H, int W, int nH, int ws, int dtype, int impl);
 int b200swin_attn_bwd(const void* qkv, const void* out, const void* out_lo, const void* dout, const float* lse,
@@ -178,6 +193,29 @@ int b200swin_attn_bwd(const void* qkv, const void* out, const void* out_lo, cons
  * middle C entries, k has no bias, are not touched).  The rows are in registers in the backward's epilogue; without it the
  * caller makes one more pass over dqkv (b200swin_colsum).  dqkv_colsum must be NULL where this returns 0. */
 int b200swin_attn_bwd_colsum_supported(int ws, int dtype, int impl);
+
+/* ------------------------------------------------------------------------------------------
+ * Global multi-head attention core (no windows, no bias, no mask):  out = softmax(scale * q k^T) v  per (batch, head).
+ * Replaces the scaled-dot-product inside nn.MultiheadAttention as Transformer_Encoder.forward uses it
+ * (models/cnn_transformer.py:192-216: hidden 512 = 8 heads x 64 over the 30x40 = 1200 tokens of a 480x640 frame; 4 x 64
+ * for hidden 256).  q [B,Nq,ldq], k [B,Nk,ldk], v [B,Nk,ldv], out [B,Nq,ldo]: rows with a stride given in ELEMENTS, head h
+ * in columns h*head_dim ..., so the operands may be slices of one packed projection buffer; the projected q is NOT
+ * pre-scaled (scale, normally head_dim^-0.5, is applied to the logits).  lse [B,nH,Nq] float32 is saved for the backward.
+ * head_dim 32 or 64.  bf16: warp-level MMA kernels (forward; backward = D prep + dK/dV pass + dQ pass, deterministic);
+ * float32: CUDA-core kernels at reference precision.  Backward workspace: B*Nq*nH floats (D = <dout, out>).
+ * mha_avg_weights: weights[B,Nq,Nk] (tensor dtype) = mean over heads of the attention probabilities, the second return
+ * value of nn.MultiheadAttention.forward(need_weights=True) that the reference receives (and drops) at :201.
+ * ------------------------------------------------------------------------------------------ */
+int b200swin_mha_fwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, void* out,
+                     int64_t ldo, float* lse, int B, int Nq, int Nk, int nH, int head_dim, float scale, int dtype,
+                     void* stream);
+size_t b200swin_mha_bwd_workspace_bytes(int B, int Nq, int nH);
+int b200swin_mha_bwd(const void* q, const void* k, const void* v, int64_t ldq, int64_t ldk, int64_t ldv, const void* out,
+                     int64_t ldo, const void* dout, int64_t lddo, const float* lse, void* dq, void* dk, void* dv,
+                     int64_t lddq, int64_t lddk, int64_t lddv, int B, int Nq, int Nk, int nH, int head_dim, float scale,
+                     int dtype, void* workspace, size_t workspace_bytes, void* stream);
+int b200swin_mha_avg_weights(const void* q, const void* k, int64_t ldq, int64_t ldk, const float* lse, void* weights, int B,
+                             int Nq, int Nk, int nH, int head_dim, float scale, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense contraction on tcgen05 tensor cores:  out[M,N] = epilogue( A[M,K] . B[N,K]^T ).

@@ -35,6 +35,9 @@ SIGNATURES = {
     "b200swin_shift_mask": (I, [P, I, I, I, I, P]),
     "b200swin_patch_merge": (I, [P, P, I, I, I, I, I, I, P]),
     "b200swin_patchify": (I, [P, I, P, I, I, I, I, I, I, I, P]),
+    "b200swin_dwconv3x3": (I, [P, P, P, I, I, I, I, I, I, P]),
+    "b200swin_dwconv3x3_wgrad_workspace_bytes": (Z, [I, I, I, I]),
+    "b200swin_dwconv3x3_wgrad": (I, [P, P, P, I, I, I, I, I, P, Z, P]),
     "b200swin_cpb_fwd": (I, [P, P, P, P, P, P, P, I, I, I, P]),
     "b200swin_cpb_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "b200swin_ln_fwd": (I, [P, P, P, P, P, L, P, P, P, L, I, F, I, P]),
@@ -45,6 +48,10 @@ SIGNATURES = {
     "b200swin_attn_bwd_workspace_bytes": (Z, [I, I, I, I, I, I, I]),
     "b200swin_attn_bwd_colsum_supported": (I, [I, I, I]),
     "b200swin_attn_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, Z, P]),
+    "b200swin_mha_fwd": (I, [P, P, P, L, L, L, P, L, P, I, I, I, I, I, F, I, P]),
+    "b200swin_mha_bwd_workspace_bytes": (Z, [I, I, I]),
+    "b200swin_mha_bwd": (I, [P, P, P, L, L, L, P, L, P, L, P, P, P, P, L, L, L, I, I, I, I, I, F, I, P, Z, P]),
+    "b200swin_mha_avg_weights": (I, [P, P, L, L, P, P, I, I, I, I, I, F, I, P]),
     "b200swin_gemm_splits": (I, [L, L, L]),
     "b200swin_gemm_workspace_bytes": (Z, [L, L, I]),
     "b200swin_gemm_bf16": (I, [P, P, I, P, P, I, L, L, L, I, P, P, P, P, P, I, P, I, I, P, Z, P]),
@@ -87,7 +94,8 @@ KERNELS_PER_CALL = {
     "b200swin_silog_fwd": 2, "b200swin_silog_bwd": 1, "b200swin_window_gather": 1, "b200swin_window_scatter": 1,
     "b200swin_shift_mask": 1, "b200swin_patch_merge": 1, "b200swin_patchify": 1, "b200swin_cpb_fwd": 1, "b200swin_cpb_bwd": 1, "b200swin_ln_fwd": 1, "b200swin_ln_fwd_stream32": 1, "b200swin_ln_bwd": 2, "b200swin_attn_fwd": 1,
     "b200swin_attn_bwd": 2, "b200swin_gemm_bf16": 1, "b200swin_split_bf16": 1, "b200swin_colsum": 2,
-    "b200swin_adamw_step": 1,
+    "b200swin_adamw_step": 1, "b200swin_mha_fwd": 1, "b200swin_mha_bwd": 3, "b200swin_mha_avg_weights": 1,
+    "b200swin_dwconv3x3": 1, "b200swin_dwconv3x3_wgrad": 2,
 }
 
 COUNTERS = {"launches": 0, "calls": {}}
@@ -105,6 +113,8 @@ def _wrap(name, fn):
             n += 1
         if name == "b200swin_attn_bwd" and args[25] in (1, 2) and (args[25] == 2 or args[22] not in (4, 6, 7, 8, 12)):
             n += 1                                     # KV-blocked backward: prep + dQ pass + dK/dV pass
+        if name == "b200swin_mha_bwd" and args[23] == F32:
+            n += 1                                     # CUDA-core backward: prep + dQ + dK + dV
         COUNTERS["launches"] += n
         COUNTERS["calls"][name] = COUNTERS["calls"].get(name, 0) + 1
         if TIMING["name"] == name or TIMING["name"] == "*":

@@ -133,7 +133,8 @@ __device__ __forceinline__ void put16(unsigned char* tile, uint32_t tile_s, uint
   }
 }
 
-// F.normalize backward of one gradient row held in registers: d = (g*sc - x_hat <g*sc, x_hat>) * inv_norm
+// F.normalize backward of one gradient row held in registers: d = (g*sc - x_hat <g*sc, x_hat>) * inv_norm.
+// invn == 0 stands for "q / k were not normalised" (attn_type='normal', no inv_norm tensor): d = g*sc.
 __device__ __forceinline__ void normalize_bwd_store(const float (&gacc)[HD], const unsigned char* tile, int r, float sc,
                                                     float invn, __nv_bfloat16* dst) {
   float xh[HD];
@@ -152,6 +153,7 @@ __device__ __forceinline__ void normalize_bwd_store(const float (&gacc)[HD], con
 #pragma unroll
   for (int c = 0; c < HD; ++c) dot = fmaf(gacc[c], xh[c], dot);
   dot *= sc;
+  if (invn == 0.f) { dot = 0.f; invn = 1.f; }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint32_t pk[4];
@@ -663,7 +665,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
       }
     } else if (MODE == MODE_DQ) {
       if (t_st >= 0)
-        normalize_bwd_store(acc0, xt, r_loc, sc, a.inv_norm[((int64_t)t_st * 2 + 0) * a.nH + h],
+        normalize_bwd_store(acc0, xt, r_loc, sc, a.inv_norm ? a.inv_norm[((int64_t)t_st * 2 + 0) * a.nH + h] : 0.f,
                             a.dqkv + (int64_t)t_st * C3 + h * HD);
     } else {
       if (t_st >= 0) {
@@ -672,7 +674,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
         for (int c = 0; c < 4; ++c)
           dst[c] = make_uint4(pack_bf16(acc0[c * 8 + 0], acc0[c * 8 + 1]), pack_bf16(acc0[c * 8 + 2], acc0[c * 8 + 3]),
                               pack_bf16(acc0[c * 8 + 4], acc0[c * 8 + 5]), pack_bf16(acc0[c * 8 + 6], acc0[c * 8 + 7]));
-        normalize_bwd_store(acc1, xt, r_loc, sc, a.inv_norm[((int64_t)t_st * 2 + 1) * a.nH + h],
+        normalize_bwd_store(acc1, xt, r_loc, sc, a.inv_norm ? a.inv_norm[((int64_t)t_st * 2 + 1) * a.nH + h] : 0.f,
                             a.dqkv + (int64_t)t_st * C3 + a.C + h * HD);
       }
       // pad keys carry v = v_bias: their dV rows are gradient of v_bias (one atomic per column and warp)

@@ -269,7 +269,9 @@ attn_bwd_dq_simt_kernel(const T* __restrict__ qkv, const T* __restrict__ out, co
     float dotq = 0.f;
 #pragma unroll
     for (int c = 0; c < HD; ++c) { dq[c] *= sc; dotq = fmaf(dq[c], q[c], dotq); }
-    const float invn = inv_norm[((int64_t)ti * 2 + 0) * d.nH + h];
+    // no inv_norm tensor: q / k were not normalised (attn_type='normal'), the gradient passes through
+    const float invn = inv_norm ? inv_norm[((int64_t)ti * 2 + 0) * d.nH + h] : 1.f;
+    if (!inv_norm) dotq = 0.f;
 #pragma unroll
     for (int c = 0; c < HD; ++c) dq[c] = (dq[c] - q[c] * dotq) * invn;
     store_row32(dqkv + (int64_t)ti * C3 + h * HD, dq);
@@ -391,7 +393,8 @@ attn_bwd_dkv_simt_kernel(const T* __restrict__ qkv, const T* __restrict__ out, c
       float dotk = 0.f;
 #pragma unroll
       for (int c = 0; c < HD; ++c) { dk[c] *= sc; dotk = fmaf(dk[c], k[c], dotk); }
-      const float invn = inv_norm[((int64_t)tj * 2 + 1) * d.nH + h];
+      const float invn = inv_norm ? inv_norm[((int64_t)tj * 2 + 1) * d.nH + h] : 1.f;
+      if (!inv_norm) dotk = 0.f;
 #pragma unroll
       for (int c = 0; c < HD; ++c) dk[c] = (dk[c] - k[c] * dotk) * invn;
       store_row32(dqkv + (int64_t)tj * C3 + C + h * HD, dk);
@@ -518,8 +521,9 @@ extern "C" int b200swin_attn_bwd(const void* qkv, const void* out, const void* o
                                  float* dscale, float* dvpad, float* dqkv_colsum, int B, int H, int W, int C, int nH,
                                  int ws, int shift, int dtype, int impl, void* workspace, size_t workspace_bytes,
                                  void* stream) {
-  BSW_REQUIRE(qkv && out && dout && lse && inv_norm && table16 && scale && dqkv && dtable16 && dscale,
-              "attn_bwd: null pointer");
+  BSW_REQUIRE(qkv && out && dout && lse && table16 && scale && dqkv && dtable16 && dscale, "attn_bwd: null pointer");
+  BSW_REQUIRE(inv_norm || impl == 0 || impl == 2,
+              "attn_bwd: inv_norm = NULL (un-normalised q, k: attn_type='normal') is served by impl 0 and 2 only");
   BSW_REQUIRE(dtype == B200SWIN_F32 || dtype == B200SWIN_BF16, "attn_bwd: bad dtype %d", dtype);
   cudaStream_t st = (cudaStream_t)stream;
   if (impl >= 1 && impl <= 4) {

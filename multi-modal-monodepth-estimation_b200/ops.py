@@ -727,6 +727,9 @@ class _AttnCore(torch.autograd.Function):
         nwin = B * (Hp // ws) * (Wp // ws)
         impl = _pick_impl(qkv.dtype, ws, mask)
         ctx.impl_bwd = _pick_impl(qkv.dtype, ws, mask, backward=True)
+        if inv_norm is None:
+            # un-normalised q, k (attn_type='normal'): the KV-blocked kernels (true row maximum) or the CUDA-core ones
+            impl = ctx.impl_bwd = 2 if (impl != 0 and ctx.impl_bwd != 0) else 0
         nWm = mask.shape[0] if mask is not None else 0
         with torch.cuda.device_of(qkv):
             out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
@@ -764,7 +767,7 @@ class _AttnCore(torch.autograd.Function):
             wsp = torch.empty(ws_bytes, dtype=torch.uint8, device=qkv.device) if ws_bytes else None
             L.check(lib.b200swin_attn_bwd(qkv.data_ptr(), out.data_ptr(), L.ptr(out_lo) if ctx.impl_bwd != 0 else 0,
                                           dout.data_ptr(), lse.data_ptr(),
-                                          inv_norm.data_ptr(), t16.data_ptr(), sc.data_ptr(), L.ptr(qp), L.ptr(vp),
+                                          L.ptr(inv_norm), t16.data_ptr(), sc.data_ptr(), L.ptr(qp), L.ptr(vp),
                                           L.ptr(mk), ctx.nWm, dqkv.data_ptr(), dt16.data_ptr(), dsc.data_ptr(),
                                           dvp.data_ptr(), L.ptr(dcs), B, H, W, C, nH, ws, shift, L.dtype_code(qkv),
                                           ctx.impl_bwd, L.ptr(wsp), ws_bytes, L.stream_of(qkv)), "attn_bwd")
@@ -777,3 +780,174 @@ class _AttnCore(torch.autograd.Function):
 
 def attention_core(qkv, inv_norm, table16, scale, qpad, vpad, mask, B, H, W, C, nH, ws, shift):
     return _AttnCore.apply(qkv, inv_norm, table16, scale, qpad, vpad, mask, (B, H, W, C, nH, ws, shift))
+
+
+# ------------------------------------------------------------------------------ global multi-head attention
+def _mha_rows(t: torch.Tensor, what: str) -> torch.Tensor:
+    """[B, N, E] with unit column stride and B*N rows at ONE row stride (a column slice of a packed projection
+    buffer qualifies); anything else is made contiguous."""
+    if t.dim() != 3:
+        raise ValueError(f"mha: {what} must be [batch, tokens, channels]")
+    ok = (t.stride(2) == 1 and t.stride(1) % 8 == 0 and t.stride(0) == t.shape[1] * t.stride(1)
+          and t.data_ptr() % 16 == 0)
+    return t if ok else t.contiguous()
+
+
+class _MhaCore(torch.autograd.Function):
+    """out = softmax(scale * q k^T) v per (batch, head) over whole sequences -- the scaled-dot-product inside
+    nn.MultiheadAttention (reference: Transformer_Encoder.forward, models/cnn_transformer.py:198-201).
+    `packed` says how the projected operands arrive, so that their gradients leave in the same buffers (no slicing
+    copies on either side):  'qkv' a = [B,N,3E];  'qk_v' a = [B,N,2E] (q | k), b = v;  'q_k_v' three tensors."""
+
+    @staticmethod
+    def forward(ctx, a, b, c, packed, nH, scale):
+        L.require_cuda(a, b, c)
+        lib = L.load()
+        if packed == 'qkv':
+            a = _mha_rows(a, 'qkv')
+            E = a.shape[2] // 3
+            q, k, v = a[..., :E], a[..., E:2 * E], a[..., 2 * E:]
+        elif packed == 'qk_v':
+            a, b = _mha_rows(a, 'qk'), _mha_rows(b, 'v')
+            E = a.shape[2] // 2
+            q, k, v = a[..., :E], a[..., E:], b
+        else:
+            a, b, c = _mha_rows(a, 'q'), _mha_rows(b, 'k'), _mha_rows(c, 'v')
+            E = a.shape[2]
+            q, k, v = a, b, c
+        if not (q.dtype == k.dtype == v.dtype):
+            raise TypeError("mha: q, k, v must share a dtype")
+        if E % nH or E // nH not in (32, 64):
+            raise NotImplementedError("mha: head_dim must be 32 or 64")
+        B, Nq, Nk, hd = q.shape[0], q.shape[1], k.shape[1], E // nH
+        if k.shape[0] != B or v.shape[0] != B or v.shape[1] != Nk or k.shape[2] != E or v.shape[2] != E:
+            raise ValueError("mha: inconsistent q / k / v shapes")
+        with torch.cuda.device_of(q):
+            out = torch.empty((B, Nq, E), dtype=q.dtype, device=q.device)
+            lse = torch.empty((B, nH, Nq), dtype=torch.float32, device=q.device)
+            L.check(lib.b200swin_mha_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(1), k.stride(1), v.stride(1),
+                                         out.data_ptr(), E, lse.data_ptr(), B, Nq, Nk, nH, hd, float(scale),
+                                         L.dtype_code(q), L.stream_of(q)), "mha_fwd")
+        ctx.save_for_backward(a, b, c, out, lse)
+        ctx.packed, ctx.nH, ctx.scale, ctx.E = packed, nH, float(scale), E
+        ctx.mark_non_differentiable(lse)
+        ctx.set_materialize_grads(False)
+        return out, lse
+
+    @staticmethod
+    def backward(ctx, dout, _dlse=None):
+        a, b, c, out, lse = ctx.saved_tensors
+        lib = L.load()
+        E, nH, packed = ctx.E, ctx.nH, ctx.packed
+        if packed == 'qkv':
+            q, k, v = a[..., :E], a[..., E:2 * E], a[..., 2 * E:]
+        elif packed == 'qk_v':
+            q, k, v = a[..., :E], a[..., E:], b
+        else:
+            q, k, v = a, b, c
+        B, Nq, Nk, hd = q.shape[0], q.shape[1], k.shape[1], E // nH
+        if dout is None:
+            dout = torch.zeros_like(out)
+        dout = dout.contiguous()
+        if dout.dtype != q.dtype:
+            dout = dout.to(q.dtype)
+        with torch.cuda.device_of(q):
+            if packed == 'qkv':
+                da = torch.empty(a.shape, dtype=a.dtype, device=a.device)
+                dq, dk, dv = da[..., :E], da[..., E:2 * E], da[..., 2 * E:]
+                grads = (da, None, None)
+            elif packed == 'qk_v':
+                da = torch.empty(a.shape, dtype=a.dtype, device=a.device)
+                dq, dk = da[..., :E], da[..., E:]
+                dv = torch.empty(v.shape, dtype=v.dtype, device=v.device)
+                grads = (da, dv, None)
+            else:
+                dq = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+                dk = torch.empty(k.shape, dtype=k.dtype, device=k.device)
+                dv = torch.empty(v.shape, dtype=v.dtype, device=v.device)
+                grads = (dq, dk, dv)
+            ws_bytes = lib.b200swin_mha_bwd_workspace_bytes(B, Nq, nH)
+            wsp = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+            L.check(lib.b200swin_mha_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), q.stride(1), k.stride(1), v.stride(1),
+                                         out.data_ptr(), E, dout.data_ptr(), E, lse.data_ptr(), dq.data_ptr(), dk.data_ptr(),
+                                         dv.data_ptr(), dq.stride(1), dk.stride(1), dv.stride(1), B, Nq, Nk, nH, hd,
+                                         ctx.scale, L.dtype_code(q), wsp.data_ptr(), ws_bytes, L.stream_of(q)), "mha_bwd")
+        return grads + (None, None, None)
+
+
+def mha_core(q, k, v, nH, scale=None, packed='q_k_v'):
+    """(out [B,Nq,E], lse [B,nH,Nq]).  packed='qkv': q is the [B,N,3E] projection; 'qk_v': q is [B,N,2E], k is v."""
+    if packed == 'qkv':
+        E, args = q.shape[2] // 3, (q, None, None)
+    elif packed == 'qk_v':
+        E, args = q.shape[2] // 2, (q, k, None)
+    else:
+        E, args = q.shape[2], (q, k, v)
+    if scale is None:
+        scale = (E // nH) ** -0.5
+    return _MhaCore.apply(*args, packed, nH, scale)
+
+
+def mha_avg_weights(q, k, lse, nH, scale=None):
+    """Head-averaged attention probabilities [B,Nq,Nk] (need_weights=True of nn.MultiheadAttention); no gradient."""
+    L.require_cuda(q, k, lse)
+    lib = L.load()
+    q, k = _mha_rows(q.detach(), 'q'), _mha_rows(k.detach(), 'k')
+    B, Nq, E = q.shape
+    Nk = k.shape[1]
+    if scale is None:
+        scale = (E // nH) ** -0.5
+    with torch.cuda.device_of(q):
+        w = torch.empty((B, Nq, Nk), dtype=q.dtype, device=q.device)
+        L.check(lib.b200swin_mha_avg_weights(q.data_ptr(), k.data_ptr(), q.stride(1), k.stride(1),
+                                             lse.contiguous().data_ptr(), w.data_ptr(), B, Nq, Nk, nH, E // nH,
+                                             float(scale), L.dtype_code(q), L.stream_of(q)), "mha_avg_weights")
+    return w
+
+
+# ------------------------------------------------------------------------------ depthwise 3x3 conv (ConvMlp.conv_proj)
+class _DwConv3x3(torch.autograd.Function):
+    """y = depthwise_conv3x3(x) on [B,H,W,C] tokens (reference: ConvMlp.conv_proj, swin_transformer_v2.py:98-111)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        L.require_cuda(x, weight)
+        lib = L.load()
+        B, H, W, C = x.shape
+        xc = x.contiguous()
+        w32 = weight.detach().contiguous().float()
+        with torch.cuda.device_of(xc):
+            y = torch.empty_like(xc)
+            L.check(lib.b200swin_dwconv3x3(xc.data_ptr(), w32.data_ptr(), y.data_ptr(), B, H, W, C, L.dtype_code(xc), 0,
+                                           L.stream_of(xc)), "dwconv3x3")
+        ctx.save_for_backward(xc, w32)
+        ctx.wdtype = weight.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, w32 = ctx.saved_tensors
+        lib = L.load()
+        B, H, W, C = xc.shape
+        dyc = dy.contiguous()
+        if dyc.dtype != xc.dtype:
+            dyc = dyc.to(xc.dtype)
+        dx = dw = None
+        with torch.cuda.device_of(xc):
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(xc)
+                L.check(lib.b200swin_dwconv3x3(dyc.data_ptr(), w32.data_ptr(), dx.data_ptr(), B, H, W, C, L.dtype_code(xc), 1,
+                                               L.stream_of(xc)), "dwconv3x3 (adjoint)")
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty((C, 1, 3, 3), dtype=torch.float32, device=xc.device)
+                ws_bytes = lib.b200swin_dwconv3x3_wgrad_workspace_bytes(B, H, W, C)
+                wsp = torch.empty(ws_bytes, dtype=torch.uint8, device=xc.device)
+                L.check(lib.b200swin_dwconv3x3_wgrad(xc.data_ptr(), dyc.data_ptr(), dw.data_ptr(), B, H, W, C,
+                                                     L.dtype_code(xc), wsp.data_ptr(), ws_bytes, L.stream_of(xc)),
+                        "dwconv3x3_wgrad")
+                dw = dw.to(ctx.wdtype)
+        return dx, dw
+
+
+def dwconv3x3(x, weight):
+    return _DwConv3x3.apply(x, weight)

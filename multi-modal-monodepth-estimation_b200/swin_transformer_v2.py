@@ -15,9 +15,10 @@ unchanged.  Every tensor op on the path runs in hand-written sm_100a kernels beh
       -> LayerNorm + DropPath scale + residual add (one kernel)
       -> fc1 GEMM (+GELU epilogue) -> fc2 GEMM -> LayerNorm + DropPath + residual (one kernel)
 
-Non-default variants of the reference file (ConvMlp, ConvPatchMerging, ResNetDLNPatchEmbed, ape,
-endnorm, mlpfp32, attn_type='normal', strid16) are outside the hot path and raise
-NotImplementedError.
+Variants of the reference file that no shipped config sets but SURVEY.md section 8f-4 lists are built on the same
+kernels: ``attn_type='normal'`` (plain scaled dot product, :296-298), ``relative_coords_table_type='none'`` (learned
+bias table, :241-244), ``mlp_type='conv' / 'conv_ln'`` (ConvMlp, :92-117, depthwise conv on the token layout) and the
+pre-norm block.  ConvPatchMerging, ResNetDLNPatchEmbed, ape, endnorm, mlpfp32 and strid16 raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -108,6 +109,41 @@ class Mlp(nn.Module):
         return ops.mlp(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, b2, passthrough)
 
 
+class LayerNorm2D(nn.Module):
+    """LayerNorm over the channels of an NCHW tensor (reference :26-38)."""
+
+    def __init__(self, normalized_shape, norm_layer=None):
+        super().__init__()
+        self.ln = norm_layer(normalized_shape) if norm_layer is not None else nn.Identity()
+
+    def forward(self, x):
+        return self.ln(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+
+class ConvMlp(nn.Module):
+    """Depthwise 3x3 conv (+ optional LayerNorm) in front of the MLP (reference :92-117; mlp_type 'conv' / 'conv_ln').
+    The conv runs on the token layout (csrc/dwconv.cu): no NHWC <-> NCHW permutes."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.,
+                 norm_layer=None, mlpfp32=False, proj_ln=False):
+        super().__init__()
+        self.mlp = Mlp(in_features=in_features, hidden_features=hidden_features, out_features=out_features,
+                       act_layer=act_layer, drop=drop, norm_layer=norm_layer, mlpfp32=mlpfp32)
+        self.conv_proj = nn.Conv2d(in_features, in_features, kernel_size=3, padding=1, stride=1, bias=False,
+                                   groups=in_features)
+        self.proj_ln = LayerNorm2D(in_features, LayerNormFP32) if proj_ln else None
+
+    def forward(self, x, H, W, fc2_bias_grad_elsewhere=False, passthrough=False):
+        B, L, C = x.shape
+        assert L == H * W
+        y = ops.dwconv3x3(x.view(B, H, W, C), self.conv_proj.weight).view(B, L, C)
+        if self.proj_ln is not None:
+            ln = self.proj_ln.ln
+            y = ops.layer_norm_residual(y, ln.weight, ln.bias, ln.eps)
+        m = self.mlp(y, H, W, fc2_bias_grad_elsewhere)
+        return (m, x) if passthrough else m
+
+
 def window_partition(x, window_size):
     """(B, H, W, C) -> (num_windows*B, ws, ws, C)   (reference :120-131), one gather kernel."""
     B, H, W, C = x.shape
@@ -143,9 +179,9 @@ class WindowAttention(nn.Module):
                  relative_coords_table_type='norm8_log', rpe_hidden_dim=512, rpe_output_type='normal',
                  attn_type='normal', mlpfp32=False, pretrain_window_size=-1):
         super().__init__()
-        if attn_type != 'cosine_mh':
-            raise NotImplementedError("b200swin.WindowAttention: attn_type='cosine_mh' only (SwinTransformerV2 default)")
-        if relative_coords_table_type not in ('norm8_log_bylayer', 'norm8_log', 'linear', 'linear_bylayer'):
+        if attn_type not in ('cosine_mh', 'normal'):
+            raise NotImplementedError(f"attn_type={attn_type!r}")
+        if relative_coords_table_type not in ('norm8_log_bylayer', 'norm8_log', 'linear', 'linear_bylayer', 'none'):
             raise NotImplementedError(f"relative_coords_table_type={relative_coords_table_type!r}")
         if rpe_output_type not in ('sigmoid', 'normal'):
             raise NotImplementedError(f"rpe_output_type={rpe_output_type!r}")
@@ -163,24 +199,31 @@ class WindowAttention(nn.Module):
         self.rpe_output_type = rpe_output_type
         self.relative_coords_table_type = relative_coords_table_type
 
-        self.logit_scale = nn.Parameter(torch.log(10 * torch.ones((num_heads, 1, 1))), requires_grad=True)
-        self.rpe_mlp = nn.Sequential(nn.Linear(2, rpe_hidden_dim, bias=True), nn.ReLU(inplace=True),
-                                     LinearFP32(rpe_hidden_dim, num_heads, bias=False))
+        if attn_type == 'cosine_mh':
+            self.logit_scale = nn.Parameter(torch.log(10 * torch.ones((num_heads, 1, 1))), requires_grad=True)
+        else:                                   # plain scaled dot product (reference :178-180, :296-298)
+            self.scale = qk_scale or (dim // num_heads) ** -0.5
         Wh, Ww = self.window_size
-        # relative_coords_table: offsets in [-(ws-1), ws-1]^2, normalised and log-spaced (reference :190-239)
-        rh = torch.arange(-(Wh - 1), Wh, dtype=torch.float32)
-        rw = torch.arange(-(Ww - 1), Ww, dtype=torch.float32)
-        table = torch.stack(torch.meshgrid(rh, rw, indexing='ij'), dim=-1).unsqueeze(0).contiguous()
-        if relative_coords_table_type in ('linear', 'norm8_log'):
-            den = (Wh - 1, Ww - 1)
-        else:
-            den = (pretrain_window_size - 1, pretrain_window_size - 1)
-        table[..., 0] /= den[0]
-        table[..., 1] /= den[1]
-        if relative_coords_table_type.startswith('norm8_log'):
-            table *= 8
-            table = torch.sign(table) * torch.log2(torch.abs(table) + 1.0) / np.log2(8)
-        self.register_buffer("relative_coords_table", table)
+        if relative_coords_table_type != 'none':
+            self.rpe_mlp = nn.Sequential(nn.Linear(2, rpe_hidden_dim, bias=True), nn.ReLU(inplace=True),
+                                         LinearFP32(rpe_hidden_dim, num_heads, bias=False))
+            # relative_coords_table: offsets in [-(ws-1), ws-1]^2, normalised and log-spaced (reference :190-239)
+            rh = torch.arange(-(Wh - 1), Wh, dtype=torch.float32)
+            rw = torch.arange(-(Ww - 1), Ww, dtype=torch.float32)
+            table = torch.stack(torch.meshgrid(rh, rw, indexing='ij'), dim=-1).unsqueeze(0).contiguous()
+            if relative_coords_table_type in ('linear', 'norm8_log'):
+                den = (Wh - 1, Ww - 1)
+            else:
+                den = (pretrain_window_size - 1, pretrain_window_size - 1)
+            table[..., 0] /= den[0]
+            table[..., 1] /= den[1]
+            if relative_coords_table_type.startswith('norm8_log'):
+                table *= 8
+                table = torch.sign(table) * torch.log2(torch.abs(table) + 1.0) / np.log2(8)
+            self.register_buffer("relative_coords_table", table)
+        else:                                   # the Swin-V1 learned table (reference :241-244)
+            self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * Wh - 1) * (2 * Ww - 1), num_heads))
+            trunc_normal_(self.relative_position_bias_table, std=.02)
         # pair-wise relative position index (reference :249-259)
         ys = torch.arange(Wh).repeat_interleave(Ww)
         xs = torch.arange(Ww).repeat(Wh)
@@ -201,12 +244,17 @@ class WindowAttention(nn.Module):
 
     # -- small host-side pieces (a few kFLOP; autograd carries their gradients) ---------------------
     def _fused_small_ops(self):
+        if self.relative_coords_table_type == 'none' or self.attn_type != 'cosine_mh':
+            return False
         l2 = self.rpe_mlp[2]
         return (self.rpe_output_type == 'sigmoid' and self.relative_coords_table.is_cuda and l2.bias is None
                 and self.num_heads <= 64)
 
     def _bias_table(self):
-        """[(2ws-1)^2, nH] fp32: rpe_mlp(coords) then 16*sigmoid (reference :304-313)."""
+        """[(2ws-1)^2, nH] fp32: rpe_mlp(coords) then 16*sigmoid (reference :304-313), or the learned table."""
+        if self.relative_coords_table_type == 'none':
+            t = self.relative_position_bias_table.float()
+            return 16 * torch.sigmoid(t) if self.rpe_output_type == 'sigmoid' else t
         l0, l2 = self.rpe_mlp[0], self.rpe_mlp[2]
         if self._fused_small_ops():
             # one kernel forward, one backward (the PyTorch graph below is ~15 latency-bound launches per block)
@@ -218,7 +266,10 @@ class WindowAttention(nn.Module):
         return t
 
     def _scale(self):
-        """exp(min(logit_scale, ln 100)) per head (reference :294, without its hard-coded cuda:0)."""
+        """exp(min(logit_scale, ln 100)) per head (reference :294, without its hard-coded cuda:0); the constant
+        qk_scale for attn_type='normal'."""
+        if self.attn_type == 'normal':
+            return torch.full((self.num_heads,), float(self.scale), dtype=torch.float32, device=self.qkv.weight.device)
         return torch.clamp(self.logit_scale.float(), max=_LOGIT_MAX).exp().view(self.num_heads)
 
     def _table_and_scale(self):
@@ -231,6 +282,8 @@ class WindowAttention(nn.Module):
     def _pads(self, needed):
         if not needed or self.q_bias is None:
             return None, None
+        if self.attn_type == 'normal':                             # pad tokens: q = q_bias as it is, k = 0, v = v_bias
+            return self.q_bias.detach(), self.v_bias
         if getattr(self, '_qpad_pre', None) is not None:       # normalised for the whole stage by BasicLayer.forward
             return self._qpad_pre, self.v_bias
         with torch.no_grad():
@@ -242,6 +295,8 @@ class WindowAttention(nn.Module):
         rolled) grid, proj GEMM.  proj_bias_grad_elsewhere: the caller's LayerNorm backward returns proj.bias'
         gradient (ops.layer_norm_residual(..., producer_bias=...))."""
         C, nH, ws = self.dim, self.num_heads, self.window_size[0]
+        if self.attn_type == 'normal':
+            return self._attend_normal(x, B, H, W, shift, mask, proj_bias_grad_elsewhere, passthrough)
         x_alias = None
         if passthrough:        # alias of x for the caller's residual branch: its gradient is added in the qkv dgrad epilogue
             qkv, inv_norm, x_alias = ops.qkv_project(x, self.qkv.weight, self.q_bias, self.v_bias, nH, True)
@@ -254,6 +309,22 @@ class WindowAttention(nn.Module):
         pb = self.proj.bias.detach() if (proj_bias_grad_elsewhere and self.proj.bias is not None) else self.proj.bias
         y = ops.linear(o.view(B, H * W, C), self.proj.weight, pb)
         return (y, x_alias) if passthrough else y
+
+    def _attend_normal(self, x, B, H, W, shift, mask, proj_bias_grad_elsewhere, passthrough):
+        """attn_type='normal' (reference :296-298): q * scale . k, no normalisation, no learnable temperature.  The same
+        attention kernels with the un-normalised projection, a constant scale and the plain backward (inv_norm = None:
+        KV-blocked tcgen05 kernels for bf16, CUDA-core kernels for fp32 or an explicit mask)."""
+        C, nH, ws = self.dim, self.num_heads, self.window_size[0]
+        bias = None
+        if self.q_bias is not None:
+            bias = torch.cat((self.q_bias, torch.zeros_like(self.v_bias, requires_grad=False), self.v_bias))
+        qkv = ops.linear(x, self.qkv.weight, bias)
+        qpad, vpad = self._pads(H % ws != 0 or W % ws != 0)
+        o = ops.attention_core(qkv.view(B, H, W, 3 * C), None, self._bias_table(), self._scale(), qpad, vpad, mask,
+                               B, H, W, C, nH, ws, shift)
+        pb = self.proj.bias.detach() if (proj_bias_grad_elsewhere and self.proj.bias is not None) else self.proj.bias
+        y = ops.linear(o.view(B, H * W, C), self.proj.weight, pb)
+        return (y, x) if passthrough else y
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C) window-major; mask: (nW, N, N) additive or None  (reference :275-336)."""
@@ -275,8 +346,8 @@ class _SwinBlockBase(nn.Module):
     def _init_common(self, dim, num_heads, window_size, shift_size, mlp_ratio, qkv_bias, qk_scale, drop, attn_drop,
                      drop_path, use_mlp_norm, endnorm, act_layer, norm_layer, relative_coords_table_type,
                      rpe_hidden_dim, rpe_output_type, attn_type, mlp_type, mlpfp32, pretrain_window_size):
-        if use_mlp_norm or endnorm or mlpfp32 or mlp_type != 'normal':
-            raise NotImplementedError("b200swin block: use_mlp_norm / endnorm / mlpfp32 / conv MLP variants are not built")
+        if use_mlp_norm or endnorm or mlpfp32 or mlp_type not in ('normal', 'conv', 'conv_ln'):
+            raise NotImplementedError("b200swin block: use_mlp_norm / endnorm / mlpfp32 variants are not built")
         self.dim, self.num_heads = dim, num_heads
         self.window_size, self.shift_size, self.mlp_ratio = window_size, shift_size, mlp_ratio
         self.use_mlp_norm, self.endnorm, self.mlpfp32 = use_mlp_norm, endnorm, mlpfp32
@@ -289,7 +360,11 @@ class _SwinBlockBase(nn.Module):
                                     attn_type=attn_type, mlpfp32=mlpfp32, pretrain_window_size=pretrain_window_size)
         self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
         self.norm2 = norm_layer(dim)
-        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        if mlp_type == 'normal':
+            self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        else:                                   # reference :404-409
+            self.mlp = ConvMlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop,
+                               proj_ln=mlp_type == 'conv_ln')
         self.enorm = None
         self.H = None
         self.W = None
@@ -306,6 +381,9 @@ class _SwinBlockBase(nn.Module):
                                   proj_bias_grad_elsewhere)
             return ops.window_scatter(aw, B, H, W, self.window_size, self.shift_size).view(B, L, C)
         return self.attn.attend(x, B, H, W, self.shift_size, None, proj_bias_grad_elsewhere)
+
+    def _fc2(self):
+        return self.mlp.mlp.fc2 if isinstance(self.mlp, ConvMlp) else self.mlp.fc2
 
     def _drop_scale(self, x):
         return self.drop_path.sample_scale(x) if isinstance(self.drop_path, DropPath) else None
@@ -349,7 +427,7 @@ class SwinTransformerBlockPost(_SwinBlockBase):
         m, xr = self.mlp(x, self.H, self.W, fuse, True)
         y = ops.layer_norm_residual(m, self.norm2.weight, self.norm2.bias, self.norm2.eps, residual=xr,
                                     row_scale=self._drop_scale(x), rows_per_scale=L,
-                                    producer_bias=self.mlp.fc2.bias if fuse else None, residual32=x32, stream32=stream)
+                                    producer_bias=self._fc2().bias if fuse else None, residual32=x32, stream32=stream)
         return ops.attach_stream(*y) if stream else y
 
 

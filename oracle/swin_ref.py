@@ -50,6 +50,23 @@ def mlp(x: torch.Tensor, sd: Mapping[str, torch.Tensor]) -> torch.Tensor:
     return F.linear(h, sd["fc2.weight"], sd["fc2.bias"])
 
 
+def conv_mlp(x: torch.Tensor, sd: Mapping[str, torch.Tensor], H: int, W: int) -> torch.Tensor:
+    """ConvMlp.forward (swin_transformer_v2.py:107-117): depthwise 3x3 conv on the [B,C,H,W] view, optional
+    LayerNorm2D(LayerNormFP32, default eps 1e-5) when the state_dict holds proj_ln, then the Mlp."""
+    B, L, C = x.shape
+    y = x.view(B, H, W, C).permute(0, 3, 1, 2)
+    y = F.conv2d(y, sd["conv_proj.weight"], None, stride=1, padding=1, groups=C)      # :98-104, :110
+    y = y.permute(0, 2, 3, 1)
+    if "proj_ln.ln.weight" in sd:                                                     # :112-113
+        y = layer_norm_fp32(y, sd["proj_ln.ln.weight"], sd["proj_ln.ln.bias"], 1e-5)
+    return mlp(y.reshape(B, L, C), _sub(sd, "mlp"))
+
+
+def any_mlp(x: torch.Tensor, sd: Mapping[str, torch.Tensor], H: int, W: int) -> torch.Tensor:
+    """mlp_type 'normal' or 'conv' / 'conv_ln' (swin_transformer_v2.py:401-409), told apart by the state_dict keys."""
+    return conv_mlp(x, sd, H, W) if "conv_proj.weight" in sd else mlp(x, sd)
+
+
 def cpb_table(sd: Mapping[str, torch.Tensor]) -> torch.Tensor:
     """rpe_mlp(relative_coords_table) -> [(2ws-1)^2, nH]  (swin_transformer_v2.py:185-187, 304).
     Linear(2,512,bias) -> ReLU -> Linear(512,nH,no bias, fp32)."""
@@ -59,13 +76,15 @@ def cpb_table(sd: Mapping[str, torch.Tensor]) -> torch.Tensor:
     return out.reshape(-1, out.shape[-1])
 
 
-def cpb_bias(sd: Mapping[str, torch.Tensor], N: int) -> torch.Tensor:
+def cpb_bias(sd: Mapping[str, torch.Tensor], N: int, rpe_output_type: str = "sigmoid") -> torch.Tensor:
     """bias[h, i, j] = 16 * sigmoid(table[relative_position_index[i, j], h])
-    (swin_transformer_v2.py:307-313) -> [nH, N, N]."""
-    table = cpb_table(sd)
+    (swin_transformer_v2.py:302-313) -> [nH, N, N]; the table is the learned relative_position_bias_table when the
+    module was built with relative_coords_table_type='none' (:241-244, :305-306); rpe_output_type 'normal' skips the
+    sigmoid (:309-310)."""
+    table = sd["relative_position_bias_table"] if "relative_position_bias_table" in sd else cpb_table(sd)
     idx = sd["relative_position_index"].reshape(-1).long()
     b = table[idx].reshape(N, N, -1).permute(2, 0, 1)
-    return 16.0 * torch.sigmoid(b)
+    return 16.0 * torch.sigmoid(b) if rpe_output_type == "sigmoid" else b
 
 
 def logit_scale_eff(logit_scale: torch.Tensor) -> torch.Tensor:
@@ -74,21 +93,29 @@ def logit_scale_eff(logit_scale: torch.Tensor) -> torch.Tensor:
 
 
 def window_attention(x: torch.Tensor, sd: Mapping[str, torch.Tensor], num_heads: int,
-                     mask: torch.Tensor | None = None, return_aux: bool = False):
-    """WindowAttention.forward for attn_type='cosine_mh', rpe 'sigmoid', qkv_bias=True
-    (swin_transformer_v2.py:275-336).  x: [B_, N, C]; mask: [nW, N, N] or None."""
+                     mask: torch.Tensor | None = None, return_aux: bool = False, rpe_output_type: str = "sigmoid",
+                     qk_scale: float | None = None):
+    """WindowAttention.forward with qkv_bias=True (swin_transformer_v2.py:275-336).  attn_type is 'cosine_mh' when the
+    state_dict holds logit_scale, else 'normal' (:296-298: q * scale . k with scale = qk_scale or head_dim^-0.5).
+    x: [B_, N, C]; mask: [nW, N, N] or None."""
     B_, N, C = x.shape
     hd = C // num_heads
     qkv_bias = torch.cat((sd["q_bias"], torch.zeros_like(sd["v_bias"]), sd["v_bias"]))   # :283-285
     qkv = F.linear(x, sd["qkv.weight"], qkv_bias)                                        # :286
     qkv = qkv.reshape(B_, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)                    # :287
     q, k, v = qkv[0], qkv[1], qkv[2]
-    qn = F.normalize(q, dim=-1)                                                          # :292 (eps 1e-12)
-    kn = F.normalize(k, dim=-1)                                                          # :293
-    scale = logit_scale_eff(sd["logit_scale"])                                           # :294
-    cos = qn @ kn.transpose(-2, -1)
-    attn = cos * scale                                                                   # :295
-    bias = cpb_bias(sd, N)
+    if "logit_scale" in sd:
+        qn = F.normalize(q, dim=-1)                                                      # :292 (eps 1e-12)
+        kn = F.normalize(k, dim=-1)                                                      # :293
+        scale = logit_scale_eff(sd["logit_scale"])                                       # :294
+        cos = qn @ kn.transpose(-2, -1)
+        attn = cos * scale                                                               # :295
+    else:
+        qn, kn = q, k
+        scale = torch.tensor(qk_scale or hd ** -0.5, dtype=x.dtype)                      # :178-180
+        cos = q @ k.transpose(-2, -1)
+        attn = (q * scale) @ k.transpose(-2, -1)                                         # :297-298
+    bias = cpb_bias(sd, N, rpe_output_type)
     attn = attn + bias.unsqueeze(0)                                                      # :317
     if mask is not None:                                                                 # :319-322
         nW = mask.shape[0]
@@ -172,7 +199,8 @@ def shift_mask(H: int, W: int, ws: int, shift: int, dtype=torch.float32) -> torc
 # --------------------------------------------------------------------------- blocks
 def block_post(x: torch.Tensor, sd: Mapping[str, torch.Tensor], H: int, W: int, num_heads: int,
                ws: int, shift: int, eps: float = 1e-6,
-               drop_scale1: torch.Tensor | None = None, drop_scale2: torch.Tensor | None = None):
+               drop_scale1: torch.Tensor | None = None, drop_scale2: torch.Tensor | None = None,
+               rpe_output_type: str = "sigmoid"):
     """SwinTransformerBlockPost.forward (swin_transformer_v2.py:419-488), post-norm:
     x = sc + DropPath(LN(attn(x)));  x = x + DropPath(LN(mlp(x))).
     ``drop_scale*`` are optional per-sample DropPath multipliers [B] (mask/keep_prob)."""
@@ -181,13 +209,13 @@ def block_post(x: torch.Tensor, sd: Mapping[str, torch.Tensor], H: int, W: int, 
     shortcut = x
     xw = gather_windows(x, H, W, ws, shift)
     mask = shift_mask(H, W, ws, shift, x.dtype) if shift > 0 else None              # :437-442
-    aw = window_attention(xw, _sub(sd, "attn"), num_heads, mask)
+    aw = window_attention(xw, _sub(sd, "attn"), num_heads, mask, rpe_output_type=rpe_output_type)
     a = scatter_windows(aw, B, H, W, ws, shift)
     a = layer_norm_fp32(a, sd["norm1.weight"], sd["norm1.bias"], eps)                # :472
     if drop_scale1 is not None:
         a = a * drop_scale1.view(B, 1, 1)
     x = shortcut + a                                                                 # :473
-    m = mlp(x, _sub(sd, "mlp"))                                                      # :477
+    m = any_mlp(x, _sub(sd, "mlp"), H, W)                                            # :477
     m = layer_norm_fp32(m, sd["norm2.weight"], sd["norm2.bias"], eps)                # :482
     if drop_scale2 is not None:
         m = m * drop_scale2.view(B, 1, 1)
@@ -195,7 +223,7 @@ def block_post(x: torch.Tensor, sd: Mapping[str, torch.Tensor], H: int, W: int, 
 
 
 def block_pre(x: torch.Tensor, sd: Mapping[str, torch.Tensor], H: int, W: int, num_heads: int,
-              ws: int, shift: int, eps: float = 1e-6):
+              ws: int, shift: int, eps: float = 1e-6, rpe_output_type: str = "sigmoid"):
     """SwinTransformerBlockPre.forward (swin_transformer_v2.py:561-630), pre-norm with
     optional gamma_1/gamma_2 (scalars 1.0 when init_values is None)."""
     B, L, C = x.shape
@@ -203,12 +231,12 @@ def block_pre(x: torch.Tensor, sd: Mapping[str, torch.Tensor], H: int, W: int, n
     y = layer_norm_fp32(x, sd["norm1.weight"], sd["norm1.bias"], eps)                # :567
     xw = gather_windows(y, H, W, ws, shift)
     mask = shift_mask(H, W, ws, shift, x.dtype) if shift > 0 else None
-    aw = window_attention(xw, _sub(sd, "attn"), num_heads, mask)
+    aw = window_attention(xw, _sub(sd, "attn"), num_heads, mask, rpe_output_type=rpe_output_type)
     a = scatter_windows(aw, B, H, W, ws, shift)
     g1 = sd.get("gamma_1", 1.0)
     g2 = sd.get("gamma_2", 1.0)
     x = shortcut + g1 * a                                                            # :614-615
-    m = mlp(layer_norm_fp32(x, sd["norm2.weight"], sd["norm2.bias"], eps), _sub(sd, "mlp"))
+    m = any_mlp(layer_norm_fp32(x, sd["norm2.weight"], sd["norm2.bias"], eps), _sub(sd, "mlp"), H, W)
     return x + g2 * m                                                                # :624-625
 
 
@@ -232,13 +260,13 @@ def patch_merging(x: torch.Tensor, sd: Mapping[str, torch.Tensor], H: int, W: in
 
 def basic_layer(x: torch.Tensor, sd: Mapping[str, torch.Tensor], H: int, W: int, depth: int,
                 num_heads: int, ws: int, use_shift: bool = True, downsample: bool = True,
-                postnorm: bool = True, eps: float = 1e-6):
+                postnorm: bool = True, eps: float = 1e-6, rpe_output_type: str = "sigmoid"):
     """BasicLayer.forward (swin_transformer_v2.py:866-908) -> (x, H, W, x_down, Wh, Ww)."""
     shift = ws // 2
     for i in range(depth):
         s = 0 if (i % 2 == 0 or not use_shift) else shift                          # :814
         fn = block_post if postnorm else block_pre
-        x = fn(x, _sub(sd, f"blocks.{i}"), H, W, num_heads, ws, s, eps)
+        x = fn(x, _sub(sd, f"blocks.{i}"), H, W, num_heads, ws, s, eps, rpe_output_type=rpe_output_type)
     if downsample:
         xd = patch_merging(x, _sub(sd, "downsample"), H, W, eps, postnorm)
         return x, H, W, xd, (H + 1) // 2, (W + 1) // 2

@@ -93,6 +93,17 @@ def load_swin():
     return mod
 
 
+def load_cnn_transformer():
+    """Return the reference ``models.cnn_transformer`` module object (imports torchvision, which the image has)."""
+    if "cnn" not in _CACHE:
+        spec = importlib.util.spec_from_file_location("_ref_cnn_transformer",
+                                                      os.path.join(REF_ROOT, "models", "cnn_transformer.py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+        _CACHE["cnn"] = m
+    return _CACHE["cnn"]
+
+
 def load_criterion():
     spec = importlib.util.spec_from_file_location("_ref_criterion", os.path.join(REF_ROOT, "utils", "criterion.py"))
     m = importlib.util.module_from_spec(spec)

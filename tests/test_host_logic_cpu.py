@@ -84,3 +84,47 @@ def test_pad_queries_are_normalised_once_per_stage():
         assert batched.shape == own.shape == (a.dim,)
         assert torch.allclose(batched, own, rtol=0, atol=1e-7)
         assert a._pads(False) == (None, None)
+
+
+def test_cnn_transformer_dropins_share_the_reference_state_dict_keys():
+    """b200swin.cnn_transformer.Transformer_Encoder / MultiheadAttention expose the keys of the reference's
+    Transformer_Encoder (golden fixture generated from models/cnn_transformer.py:176-216) and of torch's
+    nn.MultiheadAttention, with the same shapes."""
+    import types
+    import numpy as np
+    import torch
+    from conftest import load_golden
+    from b200swin.cnn_transformer import MultiheadAttention, Transformer_Encoder
+    g = load_golden("tenc_h256_n130")
+    B, N, E, nH, ff = g["meta.cfg"].tolist()
+    enc = Transformer_Encoder(types.SimpleNamespace(transformer_ff_dim=ff), hidden_dim=E)
+    ref = {k[3:]: g[k].shape for k in g.files if k.startswith("sd.")}
+    mine = {k: tuple(v.shape) for k, v in enc.state_dict().items()}
+    assert mine == ref
+    assert enc.self_attn.num_heads == nH
+    t = torch.nn.MultiheadAttention(512, 8, batch_first=True)
+    m = MultiheadAttention(512, 8, batch_first=True)
+    assert {k: v.shape for k, v in t.state_dict().items()} == {k: v.shape for k, v in m.state_dict().items()}
+    m.load_state_dict(t.state_dict(), strict=True)
+
+
+def test_variant_constructors_build_the_reference_keys():
+    """attn_type='normal' / relative_coords_table_type='none' / mlp_type='conv_ln': same state_dict keys as the reference
+    modules that produced the golden fixtures."""
+    from functools import partial
+    from conftest import load_golden
+    from b200swin import swin_transformer_v2 as S
+    for name in ["layer_post_convln_c64_ws4_pad", "layer_pre_conv_normal_c64_ws4"]:
+        g = load_golden(name)
+        dim, nH, ws, _, H, W, B, depth, down, post, shift, Wh, Ww = g["meta.cfg"].tolist()
+        at, rct, rot, mt = [str(s) for s in g["meta.types"]]
+        layer = S.BasicLayer(dim=dim, depth=depth, num_heads=nH, window_size=ws, norm_layer=partial(S.LayerNormFP32, eps=1e-6),
+                             downsample=S.PatchMerging, use_shift=True, init_values=0.5 if not post else None,
+                             relative_coords_table_type=rct, rpe_output_type=rot, attn_type=at, mlp_type=mt,
+                             postnorm=bool(post), pretrain_window_size=ws)
+        assert {k: tuple(v.shape) for k, v in layer.state_dict().items()} == \
+            {k[3:]: g[k].shape for k in g.files if k.startswith("sd.")}
+    g = load_golden("wattn_normal_none_c96_h3_ws6")
+    C, nH, ws = g["meta.cfg"].tolist()[:3]
+    wa = S.WindowAttention(C, (ws, ws), nH, attn_type="normal", relative_coords_table_type="none", rpe_output_type="sigmoid")
+    assert {k: tuple(v.shape) for k, v in wa.state_dict().items()} == {k[3:]: g[k].shape for k in g.files if k.startswith("sd.")}
