@@ -22,7 +22,7 @@ through the encoder / s.  The JSON line also carries:
 
 Other workloads (one JSON line each): c2_ws24, c2_ws30 (the reference's default windows), c1_swinT, kitti_train,
 void_train, c4_swinL_kitti_infer (inference, batch-sharded, no collective), c5_micro (attention half-block micro-bench vs
-the reference modules on the same GPU), c3_void_silog.  `--impl reference` runs the UNMODIFIED reference (staged copy,
+the reference modules on the same GPU), c3_void_silog, c3_void_encoder (config 3's global-attention encoder layers).  `--impl reference` runs the UNMODIFIED reference (staged copy,
 stock code path) on the host cores for the same metric and config.
 """
 from __future__ import annotations
@@ -826,6 +826,154 @@ def run_silog(args, w, name):
         "gpu_launches": 3 * args.steps}))
 
 
+def run_mha(args, w, name):
+    """BASELINE config 3's transformer encoder (the part of cnn_transformer that is attention): `layers` x
+    Transformer_Encoder on [frames, 1200, 512] feature / position maps, batched inference under bf16 autocast, through the
+    b200swin drop-in (global-attention kernels + tcgen05 GEMMs + LayerNorm kernels), beside the reference's own
+    Transformer_Encoder modules on the same GPU (eager: nn.MultiheadAttention with need_weights=True as the reference
+    calls it) and on the host cores."""
+    import types
+    from b200swin import _lib
+    from b200swin.cnn_transformer import Transformer_Encoder
+    world, rank, local = env()
+    if rank != 0:
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    F, E, nH, FF, NL = w["frames"], w["hidden"], w["heads"], w["ff"], w["layers"]
+    N = (w["img"][0] // 16) * (w["img"][1] // 16)
+    amp = args.dtype == "bf16"
+    cargs = types.SimpleNamespace(transformer_ff_dim=FF)
+    torch.manual_seed(0)
+    layers = torch.nn.ModuleList([Transformer_Encoder(cargs, hidden_dim=E) for _ in range(NL)]).to(dev).eval()
+    g = torch.Generator().manual_seed(1234)
+    feat_h = torch.randn(F, N, E, generator=g).pin_memory()
+    pos_h = torch.randn(F, N, E, generator=g).pin_memory()
+    feat, pos = feat_h.to(dev), pos_h.to(dev)
+
+    def fwd(mods, f, p):
+        with torch.autocast("cuda", torch.bfloat16, enabled=amp):
+            for m in mods:
+                f = m(f, p)
+        return f
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream), torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            y = fwd(layers, feat, pos)
+        torch.cuda.synchronize()
+        _lib.reset_counters()
+        _lib.TIMING.update(name="*", events=[])
+        fwd(layers, feat, pos)
+        torch.cuda.synchronize()
+        _lib.TIMING["name"] = None
+        launches = _lib.COUNTERS["launches"]
+        fam = {}
+        for e0, e1, sym, _a in _lib.TIMING["events"]:
+            fam[sym] = fam.get(sym, 0.0) + e0.elapsed_time(e1)
+        graph = None
+        if not args.no_graph:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                y = fwd(layers, feat, pos)
+        run = (lambda: graph.replay()) if graph is not None else (lambda: fwd(layers, feat, pos))
+        run()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def timed(fn, n):
+            tot = 0.0
+            for _ in range(n):
+                flush.zero_()                         # L2 flush between timed iterations (256 MB > 126 MB)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            return tot / n
+        clk_path = os.path.join(tempfile.gettempdir(), "b200swin_clocks_0.csv")
+        sampler = BL.clocks_sampler(clk_path)
+        ms = timed(run, args.steps)
+        out_host = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+
+        def e2e_once():
+            feat.copy_(feat_h, non_blocking=True)
+            pos.copy_(pos_h, non_blocking=True)
+            run()
+            out_host.copy_(y, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        e2e_once()
+        ms_e2e = timed(e2e_once, args.steps)
+        sampler.terminate()
+        # the reference's own layers on the same GPU, same weights
+        ref = {}
+        import baseline
+        if baseline.available():
+            R = baseline.load().cnn_transformer
+            rl = torch.nn.ModuleList([R.Transformer_Encoder(cargs, hidden_dim=E) for _ in range(NL)]).to(dev).eval()
+            rl.load_state_dict(layers.state_dict(), strict=True)
+            for tag, a in (("fp32", False), ("bf16_autocast", True)):
+                def ref_fwd():
+                    f = feat
+                    with torch.autocast("cuda", torch.bfloat16, enabled=a):
+                        for m in rl:
+                            f = m(f, pos)
+                    return f
+                yr = ref_fwd()
+                ref_fwd()
+                ref[tag] = {"ms_per_step": timed(ref_fwd, max(2, args.steps // 2))}
+                ref[tag]["images_per_s"] = F / (ref[tag]["ms_per_step"] / 1e3)
+                ref[tag]["speedup"] = ref[tag]["ms_per_step"] / ms
+                if a == amp:
+                    ref["max_abs_diff_vs_reference_same_precision"] = (y.float() - yr.float()).abs().max().item()
+    # host cores: the reference's layers, one frame per step (bounded sample)
+    cpu = None
+    import baseline
+    if baseline.available():
+        R = baseline.load().cnn_transformer
+        cl = torch.nn.ModuleList([R.Transformer_Encoder(cargs, hidden_dim=E) for _ in range(NL)]).eval()
+        torch.set_num_threads(os.cpu_count() or 1)
+        with torch.no_grad():
+            f1, p1 = feat_h[:1].clone(), pos_h[:1].clone()
+            def cpu_one():
+                f = f1
+                for m in cl:
+                    f = m(f, p1)
+                return f
+            cpu_one()
+            t0 = time.perf_counter()
+            nrep = 3
+            for _ in range(nrep):
+                cpu_one()
+            cpu_s = (time.perf_counter() - t0) / nrep
+        cpu = {"value": 1.0 / cpu_s, "unit": "images/s", "cores": os.cpu_count(), "kind": "reference",
+               "sample": f"{nrep} x 1 frame through the reference's {NL} Transformer_Encoder layers, fp32"}
+    fl_attn = 4.0 * N * N * E
+    fl_gemm = 2.0 * N * E * 3 * E + 2.0 * N * E * E + 4.0 * N * E * FF
+    pk = BL.peaks()
+    tf = (fl_attn + fl_gemm) * NL * F / (ms / 1e3) / 1e12
+    attn_ms = fam.get("b200swin_mha_fwd", 0.0)
+    print(json.dumps({
+        "metric": "inference images/sec, cnn_transformer encoder layers (global MHA), VOID-shaped 480x640",
+        "value": F / (ms / 1e3), "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if amp else "f32(split-bf16 x3 GEMMs, fp32 CUDA-core attention)", "data": "synthetic",
+        "config": {"workload": f"{name}: {NL} x Transformer_Encoder(hidden {E}, {nH} heads x {E // nH}, ff {FF}) on {F} frames x "
+                               f"{N} tokens ({w['img'][0]}x{w['img'][1]} / 16), inference",
+                   "execution": "cuda_graph_replay" if graph else "eager",
+                   "l2": "256 MB flush write between timed iterations"},
+        "e2e": {"value": F / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": 2 * feat_h.numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},
+        "gpu_launches": launches,
+        "kernel_ms_per_step": {k: round(v, 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])},
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": tf / pk["tf_sustained"], "traffic": None,
+                     "kernel": "whole layer stack (tcgen05 GEMMs + warp-MMA global attention)", "peak_source": pk["source"]},
+        "roofline_attn": {"fwd": {"ms_per_step": attn_ms, "tflops": (fl_attn * NL * F / (attn_ms / 1e3) / 1e12) if attn_ms else None,
+                                  "kernel": "gattn_fwd_mma_kernel<64> (mma.sync m16n8k16; legacy tensor pipe ~550 TF/s)"}},
+        "reference_cuda_eager": ref, "cpu_baseline": cpu, "clocks": BL.clocks_summary(clk_path, local)}))
+
+
 if __name__ == "__main__":
     a = parse()
     wl = BL.WORKLOADS[a.workload]
@@ -837,5 +985,7 @@ if __name__ == "__main__":
         run_infer(a, wl, a.workload)
     elif wl["kind"] == "micro":
         run_micro(a, a.workload)
+    elif wl["kind"] == "mha":
+        run_mha(a, wl, a.workload)
     else:
         run_silog(a, wl, a.workload)

@@ -43,6 +43,10 @@ WORKLOADS = {
     "c5_micro": dict(kind="micro"),
     # BASELINE config 3 (VOID 480 x 640, cnn_transformer path): the path contains no window attention -- only SiLog applies
     "c3_void_silog": dict(kind="silog", img=(480, 640), frames=64, max_depth=10.0, invalid=0.30),
+    # ... and, with the global-attention kernels, its transformer encoder: 6 layers of global MHA + ReLU FFN
+    # over the 30 x 40 = 1200 stride-16 tokens of a 480 x 640 frame, hidden 512 = 8 heads x 64 (models/model.py:73-95,
+    # models/cnn_transformer.py:176-262), feed-forward 4096 (configs/config.yaml:63); batched inference
+    "c3_void_encoder": dict(kind="mha", img=(480, 640), frames=32, hidden=512, heads=8, ff=4096, layers=6),
 }
 
 

@@ -56,6 +56,7 @@ def _mha_ref64(q, k, v, nH, cot):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize("B,Nq,Nk,nH,hd", [(2, 1200, 1200, 8, 64),        # config 3: 30 x 40 tokens, hidden 512
+                                           (5, 1000, 333, 8, 64),        # enough CTAs for the 128-row forward; ragged both ways
                                            (1, 77, 77, 4, 64),           # ragged tail inside the first block
                                            (2, 130, 67, 2, 64),          # cross attention, Nq != Nk
                                            (1, 64, 128, 3, 32),          # head_dim 32, exact block multiples
