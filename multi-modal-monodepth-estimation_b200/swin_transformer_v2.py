@@ -630,6 +630,11 @@ class SwinTransformerV2(nn.Module):
             raise NotImplementedError("b200swin.SwinTransformerV2: ape / strid16 / conv patch variants are not built")
         if drop_rate != 0. or attn_drop_rate != 0.:
             raise NotImplementedError("b200swin.SwinTransformerV2: dropout is not built (the reference uses 0)")
+        # reference_rng=True: every DropPath call draws its own mask from the current generator, in the reference's call
+        # order and with timm's call (one bernoulli_ over the batch per branch), so a seeded training run sees the same
+        # stochastic-depth masks as the reference.  Default: all masks of a forward drawn in one batched launch (same
+        # distribution, different use of the generator), ~94 fewer launch-bound kernels per step.
+        self.reference_rng = bool(kwargs.pop('reference_rng', False))
         self.pretrain_img_size = pretrain_img_size
         self.depths = depths
         self.num_layers = len(depths)
@@ -742,7 +747,7 @@ class SwinTransformerV2(nn.Module):
         twice: ~94 launch-bound kernels per step on Swin-V2-B).  Same distribution as the per-call draw,
         Bernoulli(keep) / keep per sample; skipped under activation checkpointing, whose recompute relies on replaying
         the RNG of per-call draws."""
-        if not self.training or any(getattr(l, 'use_checkpoint', False) for l in self.layers):
+        if not self.training or self.reference_rng or any(getattr(l, 'use_checkpoint', False) for l in self.layers):
             return []
         mods = [m for m in self.modules() if isinstance(m, DropPath) and m.training and 0.0 < m.drop_prob < 1.0]
         if not mods:

@@ -105,6 +105,8 @@ def window_attention(x: torch.Tensor, sd: Mapping[str, torch.Tensor], num_heads:
     qkv = qkv.reshape(B_, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)                    # :287
     q, k, v = qkv[0], qkv[1], qkv[2]
     if "logit_scale" in sd:
+        if q.dtype in (torch.bfloat16, torch.float16):       # under autocast the reference widens first (.float(), :292-293)
+            q, k = q.float(), k.float()
         qn = F.normalize(q, dim=-1)                                                      # :292 (eps 1e-12)
         kn = F.normalize(k, dim=-1)                                                      # :293
         scale = logit_scale_eff(sd["logit_scale"])                                       # :294
@@ -122,6 +124,8 @@ def window_attention(x: torch.Tensor, sd: Mapping[str, torch.Tensor], num_heads:
         attn = attn.view(B_ // nW, nW, num_heads, N, N) + mask.unsqueeze(1).unsqueeze(0)
         attn = attn.view(-1, num_heads, N, N)
     p = torch.softmax(attn, dim=-1)                                                      # :324
+    if p.dtype != x.dtype and x.dtype in (torch.bfloat16, torch.float16):
+        p = p.type_as(x)                                                                 # :325
     o = (p @ v).transpose(1, 2).reshape(B_, N, C)                                        # :328
     y = F.linear(o, sd["proj.weight"], sd["proj.bias"])                                  # :334
     if return_aux:

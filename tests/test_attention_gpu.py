@@ -100,27 +100,44 @@ def test_basic_layer_fp32_vs_reference_golden(name):
 
 @pytest.mark.parametrize("name", ["layer_post_c64_ws4_pad", "layer_post_c128_ws12_pad"])
 def test_basic_layer_bf16_autocast(name):
+    """bf16 bar: 2e-2 on outputs and on every gradient.  A tensor may exceed it only as far as torch's OWN bf16 autocast
+    run of the same layer does on this GPU (the oracle's restatement executed under torch.autocast -- measured here, bar =
+    max(2e-2, 1.5 x that)): logit_scale / rpe_mlp gradients are sums over every window of dS terms that cancel row by row,
+    and the bf16 rounding of the GEMM operands does not average out of them in any implementation."""
     g = load_golden(name)
     layer, (H, W, down) = _build_layer(g)
+    dim, nH, ws, pre, _, _, B, depth, _, post, shift, _, _ = g["meta.cfg"].tolist()
     x = torch.from_numpy(g["in.x"]).cuda().requires_grad_(True)
+    cot, cot2 = torch.from_numpy(g["in.cot"]).cuda(), torch.from_numpy(g["in.cot2"]).cuda()
     with torch.autocast("cuda", torch.bfloat16):
         x_out, _, _, x_down, _, _ = layer(x, H, W)
     assert x_out.dtype == torch.bfloat16
     assert _relerr(x_out, g["out.x"]) < 2e-2
     assert _relerr(x_down, g["out.x_down"]) < 2e-2
-    total = (x_out.float() * torch.from_numpy(g["in.cot2"]).cuda()).sum()
+    total = (x_out.float() * cot2).sum()
     if down:
-        total = total + (x_down.float() * torch.from_numpy(g["in.cot"]).cuda()).sum()
+        total = total + (x_down.float() * cot).sum()
     total.backward()
-    assert _relerr(x.grad, g["grad.x"]) < 3e-2
+    # yardstick: the same layer through torch under the same autocast
+    sd = {k: (v.cuda().requires_grad_(True) if v.is_floating_point() and "relative_coords_table" not in k else v.cuda())
+          for k, v in swin_ref.npz_to_sd(g).items()}
+    x2 = x.detach().clone().requires_grad_(True)
+    with torch.autocast("cuda", torch.bfloat16):
+        y_out, _, _, y_down, _, _ = swin_ref.basic_layer(x2, sd, H, W, depth, nH, ws, bool(shift), bool(down), bool(post))
+    t2 = (y_out.float() * cot2).sum()
+    if down:
+        t2 = t2 + (y_down.float() * cot).sum()
+    t2.backward()
+    yard = {n: _relerr(sd[n].grad, g["grad.sd." + n]) for n, _ in layer.named_parameters()
+            if np.abs(g["grad.sd." + n]).max() > 0 and sd[n].grad is not None}
+    assert _relerr(x.grad, g["grad.x"]) < max(2e-2, 1.5 * _relerr(x2.grad, g["grad.x"]))
     bad = []
     for n, p in layer.named_parameters():
         ref = g["grad.sd." + n]
         if np.abs(ref).max() > 0:
             e = _relerr(p.grad, ref)
-            # logit_scale's gradient is a heavily cancelling sum (dS*cos over every window): looser in bf16
-            if e > (1.5e-1 if n.endswith("logit_scale") else 5e-2):
-                bad.append((n, e))
+            if e > max(2e-2, 1.5 * yard.get(n, 0.0)):
+                bad.append((n, e, yard.get(n)))
     assert not bad, bad
 
 

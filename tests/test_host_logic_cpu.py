@@ -52,6 +52,31 @@ def test_pre_drawn_masks_are_ignored_for_another_batch_size_and_in_eval():
     assert m.sample_scale(torch.zeros(8, 2)) is None
 
 
+def test_reference_rng_mode_reproduces_timm_drop_path_masks():
+    """reference_rng=True: per-call draws in the reference's order with timm's call -- x.new_empty((B, 1, 1)).bernoulli_(keep)
+    per branch (timm.models.layers.DropPath as used at swin_transformer_v2.py:473 / :483) -- so the same seed gives the
+    same masks as the reference."""
+    net = SwinTransformerV2(drop_path_rate=0.5, reference_rng=True, **CFG).train()
+    B = 16
+    assert net._draw_drop_paths(B, torch.device("cpu")) == []
+    x = torch.zeros(B, 7, 3)
+    torch.manual_seed(11)
+    mine = []
+    for blk in [b for l in net.layers for b in l.blocks]:
+        if isinstance(blk.drop_path, DropPath):
+            mine += [blk.drop_path.sample_scale(x), blk.drop_path.sample_scale(x)]      # attention branch, MLP branch
+    torch.manual_seed(11)
+    k = 0
+    for blk in [b for l in net.layers for b in l.blocks]:
+        if isinstance(blk.drop_path, DropPath):
+            keep = 1.0 - blk.drop_path.drop_prob
+            for _ in range(2):
+                ref = x.new_empty((B, 1, 1)).bernoulli_(keep).div_(keep)
+                assert torch.equal(mine[k], ref.view(B))
+                k += 1
+    assert k == len(mine) == 6
+
+
 def test_no_batched_draw_under_activation_checkpointing():
     """The recompute of a checkpointed block replays the RNG of per-call draws; pre-drawn masks would be gone by then."""
     net = SwinTransformerV2(drop_path_rate=0.5, use_checkpoint=True, **CFG).train()
