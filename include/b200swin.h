@@ -36,6 +36,8 @@ extern "C" {
 #define B200SWIN_EPI_QKV 2      /* Swin-V2 qkv: + (q_bias,0,v_bias), L2-normalise q,k per head */
 #define B200SWIN_EPI_DGELU 3    /* out = acc * aux_in   (aux_in = the gelu' saved by EPI_GELU) */
 #define B200SWIN_EPI_ADD 4      /* out = acc + aux_in   (dgrad + the gradient of the residual branch) */
+#define B200SWIN_EPI_RELU 5     /* out = max(acc + bias, 0); aux (optional) = 1 where positive, else 0 (ffn1 of
+                                   Transformer_Encoder, models/cnn_transformer.py:193-194; backward through EPI_DGELU) */
 
 int b200swin_version(void);
 const char* b200swin_last_error(void);
@@ -227,7 +229,8 @@ int b200swin_mha_avg_weights(const void* q, const void* k, int64_t ldq, int64_t 
  *  - a_lo / b_lo (both or neither): low bf16 halves from b200swin_split_bf16; the kernel then
  *    accumulates hi.hi + hi.lo + lo.hi, which reproduces an fp32 GEMM to ~1e-5 relative.
  *  - epilogue (B200SWIN_EPI_*): NONE: + bias[N] (nullable).  GELU: + bias, out = erf-GELU, aux_out (nullable)
- *    receives gelu'(pre-activation).  DGELU: out = acc * aux_in (that saved derivative).  QKV: N = 3C; adds bias
+ *    receives gelu'(pre-activation).  RELU: the same with max(., 0) and its 0/1 derivative.  DGELU: out = acc * aux_in
+ *    (that saved derivative).  QKV: N = 3C; adds bias
  *    (= q_bias[C]) to the q columns, nothing to k, bias2 (= v_bias[C]) to v; L2-normalises every
  *    32-wide head slice of q and k in fp32 (F.normalize, eps 1e-12, :292-293) and writes
  *    inv_norm[M,2,nH] = 1/max(|q|,eps), 1/max(|k|,eps) (nullable).

@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libb200swin.so")
 
 F32, BF16 = 0, 1
-EPI_NONE, EPI_GELU, EPI_QKV, EPI_DGELU, EPI_ADD = 0, 1, 2, 3, 4
+EPI_NONE, EPI_GELU, EPI_QKV, EPI_DGELU, EPI_ADD, EPI_RELU = 0, 1, 2, 3, 4, 5
 
 _lock = threading.Lock()
 _lib = None

@@ -115,6 +115,6 @@ class Transformer_Encoder(nn.Module):
         v = img_feat
         x, _ = self.self_attn(q, k, v, need_weights=False)       # the reference computes the weights and drops them
         x = ops.layer_norm_residual((v + x).float(), self.norm1.weight, self.norm1.bias, self.norm1.eps)
-        x2 = torch.relu(ops.linear(x, self.ffn1[0].weight, self.ffn1[0].bias))
-        x2 = ops.linear(x2, self.ffn2[0].weight, self.ffn2[0].bias)
+        # Linear -> ReLU -> Linear as two GEMMs, the ReLU (and its 0/1 derivative for the backward) in the first epilogue
+        x2 = ops.mlp(x, self.ffn1[0].weight, self.ffn1[0].bias, self.ffn2[0].weight, self.ffn2[0].bias, relu=True)
         return ops.layer_norm_residual((x + x2).float(), self.norm2.weight, self.norm2.bias, self.norm2.eps)

@@ -233,6 +233,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, Stager& st, 
     }
     if (p.aux_out) store_chunk<OutT>(st, &p.tmAux, g, col0, row0, p.N);
     store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
+  } else if constexpr (EPI == B200SWIN_EPI_RELU) {
+    if (p.bias) add_bias32(v, p.bias + col0, nvalid);
+    if (p.aux_out) {
+      float g[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) g[c] = v[c] > 0.f ? 1.f : 0.f;
+      store_chunk<OutT>(st, &p.tmAux, g, col0, row0, p.N);
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+    store_chunk<OutT>(st, &p.tmOut, v, col0, row0, p.N);
   } else if constexpr (EPI == B200SWIN_EPI_DGELU || EPI == B200SWIN_EPI_ADD) {
     constexpr bool MUL = EPI == B200SWIN_EPI_DGELU;
     if constexpr (sizeof(OutT) == 2) {
@@ -645,7 +656,7 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   BSW_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "gemm: dimension exceeds 2^31");
   BSW_REQUIRE((a_lo == nullptr) == (b_lo == nullptr), "gemm: a_lo and b_lo must be given together");
   BSW_REQUIRE(out_dtype == B200SWIN_F32 || out_dtype == B200SWIN_BF16, "gemm: bad out dtype %d", out_dtype);
-  BSW_REQUIRE(epilogue >= B200SWIN_EPI_NONE && epilogue <= B200SWIN_EPI_ADD, "gemm: bad epilogue %d", epilogue);
+  BSW_REQUIRE(epilogue >= B200SWIN_EPI_NONE && epilogue <= B200SWIN_EPI_RELU, "gemm: bad epilogue %d", epilogue);
   BSW_REQUIRE(N % 8 == 0, "gemm: N must be a multiple of 8 (16-byte rows for the TMA stores)");
   BSW_REQUIRE((a_mn_major ? M : K) % 8 == 0 && (b_mn_major ? N : K) % 8 == 0,
               "gemm: contiguous operand dimension must be a multiple of 8 (16-byte TMA rows)");
@@ -739,6 +750,9 @@ extern "C" int b200swin_gemm_bf16(const void* a_hi, const void* a_lo, int a_mn_m
   } else if (epilogue == B200SWIN_EPI_GELU) {
     BSW_REQUIRE(!a_mn_major && !b_mn_major, "gemm: the GELU epilogue is built for K-major operands only");
     LAUNCH_BN(false, false, B200SWIN_EPI_GELU);
+  } else if (epilogue == B200SWIN_EPI_RELU) {
+    BSW_REQUIRE(!a_mn_major && !b_mn_major, "gemm: the RELU epilogue is built for K-major operands only");
+    LAUNCH_BN(false, false, B200SWIN_EPI_RELU);
   } else if (epilogue == B200SWIN_EPI_QKV) {
     BSW_REQUIRE(!a_mn_major && !b_mn_major, "gemm: the QKV epilogue is built for K-major operands only");
     LAUNCH_BN(false, false, B200SWIN_EPI_QKV);

@@ -492,10 +492,11 @@ def linear(x, weight, bias=None):
 class _Mlp(torch.autograd.Function):
     """fc2(GELU(fc1(x))) with the GELU fused into fc1's epilogue -- which also emits gelu'(pre-activation) for the
     backward -- and the multiplication by that derivative fused into fc2's dgrad epilogue
-    (reference: Mlp.forward, swin_transformer_v2.py:76-89; exact-erf GELU)."""
+    (reference: Mlp.forward, swin_transformer_v2.py:76-89; exact-erf GELU).  relu=True: the ReLU feed-forward of
+    Transformer_Encoder (models/cnn_transformer.py:193-195, :205-207) through the same two GEMMs."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, passthrough=False):
+    def forward(ctx, x, w1, b1, w2, b2, passthrough=False, relu=False, will_backward=True):
         # passthrough: also return x itself (as a view).  The caller routes its residual branch through that alias, so
         # the gradient of the residual arrives HERE and is added in the epilogue of the last dgrad GEMM instead of in
         # a separate elementwise pass by the autograd engine.
@@ -509,8 +510,10 @@ class _Mlp(torch.autograd.Function):
         if cd == torch.bfloat16 and x2.dtype != torch.bfloat16:
             x2 = x2.to(torch.bfloat16)
         xo = stage_operand(x2, exact)
-        z = torch.empty((M, Hd), dtype=cd, device=x.device)
-        h = gemm(xo, stage_weight(w1, exact), M, Hd, C, epilogue=L.EPI_GELU, bias=_f32(b1), aux_out=z, out_dtype=cd)
+        # the activation's derivative is written only when a backward will read it
+        z = torch.empty((M, Hd), dtype=cd, device=x.device) if (will_backward and any(ctx.needs_input_grad)) else None
+        h = gemm(xo, stage_weight(w1, exact), M, Hd, C, epilogue=L.EPI_RELU if relu else L.EPI_GELU, bias=_f32(b1),
+                 aux_out=z, out_dtype=cd)
         ho = stage_operand(h, exact)
         y = gemm(ho, stage_weight(w2, exact), M, Co, Hd, bias=_f32(b2), out_dtype=cd)
         ctx.save_for_backward(xo.hi, xo.lo, z, ho.hi, ho.lo, w1, w2)
@@ -524,7 +527,7 @@ class _Mlp(torch.autograd.Function):
     def backward(ctx, dy, dres=None):
         xhi, xlo, z, hhi, hlo, w1, w2 = ctx.saved_tensors
         if dy is None:                                   # only the alias was used downstream
-            return dres, None, None, None, None, None
+            return dres, None, None, None, None, None, None, None
         exact = ctx.cd == torch.float32
         Hd, C = w1.shape
         Co = w2.shape[0]
@@ -545,11 +548,12 @@ class _Mlp(torch.autograd.Function):
             dx = _dgrad_plus(dzo, stage_weight(w1, exact), M, C, Hd, ctx.cd, dres).view(ctx.xshape)
             if dx.dtype != ctx.xdtype:
                 dx = dx.to(ctx.xdtype)
-        return dx, dw1, db1, dw2, db2, None
+        return dx, dw1, db1, dw2, db2, None, None, None
 
 
-def mlp(x, w1, b1, w2, b2, passthrough=False):
-    return _Mlp.apply(x, w1, b1, w2, b2, passthrough)
+def mlp(x, w1, b1, w2, b2, passthrough=False, relu=False):
+    # grad mode is read HERE: inside Function.forward it is always off
+    return _Mlp.apply(x, w1, b1, w2, b2, passthrough, relu, torch.is_grad_enabled())
 
 
 class _QKV(torch.autograd.Function):
@@ -715,7 +719,7 @@ class _AttnCore(torch.autograd.Function):
     Reference: swin_transformer_v2.py:295-328 + :429-463 + :874-892."""
 
     @staticmethod
-    def forward(ctx, qkv, inv_norm, table16, scale, qpad, vpad, mask, geom):
+    def forward(ctx, qkv, inv_norm, table16, scale, qpad, vpad, mask, geom, will_backward=True):
         B, H, W, C, nH, ws, shift = geom
         L.require_cuda(qkv, inv_norm, table16, scale, qpad, vpad, mask)
         lib = L.load()
@@ -734,7 +738,7 @@ class _AttnCore(torch.autograd.Function):
         with torch.cuda.device_of(qkv):
             out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
             # bf16 residual of O for the backward's D = <dO, O> (tensor-core path, only when a backward will run)
-            need_lo = impl != 0 and any(ctx.needs_input_grad)
+            need_lo = impl != 0 and will_backward and any(ctx.needs_input_grad)
             out_lo = torch.empty_like(out) if need_lo else None
             lse = torch.empty((nwin, nH, ws * ws), dtype=torch.float32, device=qkv.device)
             L.check(lib.b200swin_attn_fwd(qkv.data_ptr(), out.data_ptr(), L.ptr(out_lo), lse.data_ptr(), t16.data_ptr(),
@@ -775,11 +779,12 @@ class _AttnCore(torch.autograd.Function):
             _stash_colsum(dqkv, dcs)
         tdt, sdt, vdt = ctx.dtypes
         return (dqkv, None, dt16.to(tdt), dsc.view(sc.shape).to(sdt), None,
-                dvp.to(vdt) if vdt is not None else None, None, None)
+                dvp.to(vdt) if vdt is not None else None, None, None, None)
 
 
 def attention_core(qkv, inv_norm, table16, scale, qpad, vpad, mask, B, H, W, C, nH, ws, shift):
-    return _AttnCore.apply(qkv, inv_norm, table16, scale, qpad, vpad, mask, (B, H, W, C, nH, ws, shift))
+    return _AttnCore.apply(qkv, inv_norm, table16, scale, qpad, vpad, mask, (B, H, W, C, nH, ws, shift),
+                           torch.is_grad_enabled())
 
 
 # ------------------------------------------------------------------------------ global multi-head attention

@@ -212,7 +212,7 @@ def block_post(x: torch.Tensor, sd: Mapping[str, torch.Tensor], H: int, W: int, 
     assert L == H * W
     shortcut = x
     xw = gather_windows(x, H, W, ws, shift)
-    mask = shift_mask(H, W, ws, shift, x.dtype) if shift > 0 else None              # :437-442
+    mask = shift_mask(H, W, ws, shift, x.dtype).to(x.device) if shift > 0 else None              # :437-442
     aw = window_attention(xw, _sub(sd, "attn"), num_heads, mask, rpe_output_type=rpe_output_type)
     a = scatter_windows(aw, B, H, W, ws, shift)
     a = layer_norm_fp32(a, sd["norm1.weight"], sd["norm1.bias"], eps)                # :472
@@ -234,7 +234,7 @@ def block_pre(x: torch.Tensor, sd: Mapping[str, torch.Tensor], H: int, W: int, n
     shortcut = x
     y = layer_norm_fp32(x, sd["norm1.weight"], sd["norm1.bias"], eps)                # :567
     xw = gather_windows(y, H, W, ws, shift)
-    mask = shift_mask(H, W, ws, shift, x.dtype) if shift > 0 else None
+    mask = shift_mask(H, W, ws, shift, x.dtype).to(x.device) if shift > 0 else None
     aw = window_attention(xw, _sub(sd, "attn"), num_heads, mask, rpe_output_type=rpe_output_type)
     a = scatter_windows(aw, B, H, W, ws, shift)
     g1 = sd.get("gamma_1", 1.0)
