@@ -13,6 +13,7 @@
 // Same math as the other attention kernels: models/swin_transformer_v2.py:295-328 with the pad / roll / partition /
 // reverse / crop of :429-463 and the shift mask of :874-892 as address math; backward per SURVEY.md appendix A.
 #include <stdlib.h>
+#include <string.h>
 #include <type_traits>
 #include "common.cuh"
 #include "wingeom.cuh"
@@ -164,18 +165,24 @@ __device__ __forceinline__ int row_token(const WinGeom& g, const ItemPos& p, int
 
 // ------------------------------------------------------------------------------------------------------- forward
 // CTA = NT warps = one (window, head) item at a time, a contiguous head-major range of items per CTA; the q / k / v tiles
-// of the next two items are in flight (cp.async, three stages) while the warps work on the current one, one CTA barrier
-// per item.  Two CTAs per SM.
+// of the next two items are in flight (three stages) while the warps work on the current one, one CTA barrier per item.
+// Two CTAs per SM.
+// Staging of a window's tiles: a window that does not wrap around the map under the cyclic shift is a ws x ws x 32-column
+// BOX of the [B, H, W, 3C] qkv tensor: ONE elected thread issues three 4-D TMA loads (cp.async.bulk.tensor, SWIZZLE_64B =
+// the tile layout sw64() of the ldmatrix reads, completing on the stage's mbarrier); rows beyond H / W arrive as the
+// hardware's zero fill, which IS the k of a pad token, and the threads owning pad rows then write q = q_bias-hat and
+// v = v_bias over them.  Windows on the roll seam (last window row / column of a shifted block: up to four rectangles)
+// and the ragged window sizes keep the per-row 16-byte cp.async gather.
 constexpr int kFwdStages = 3;
 
 template <int WS>
 __global__ void __launch_bounds__(MCfg<WS>::THREADS, MCfg<WS>::FWD_CTAS)
-attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
+attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a, const __grid_constant__ CUtensorMap tmap, const int use_tma) {
   using Cf = MCfg<WS>;
   constexpr int N = Cf::N, NP = Cf::NP, TW = Cf::TW, CHN = Cf::CHN;
   constexpr uint32_t TILE = Cf::TILE, STAGE = 3 * TILE;
   extern __shared__ unsigned char smem_dyn[];
-  const uint32_t base_u32 = (ptx::smem_u32(smem_dyn) + 127u) & ~127u;
+  const uint32_t base_u32 = (ptx::smem_u32(smem_dyn) + 1023u) & ~1023u;  // 512-byte period of the TMA swizzle pattern
   unsigned char* sm = smem_dyn + (base_u32 - ptx::smem_u32(smem_dyn));
   unsigned char* tiles = sm;                                              // [stages][q | k | v]
   int* tokm = reinterpret_cast<int*>(tiles + kFwdStages * STAGE);         // [stages][NP] source token of a row
@@ -183,6 +190,7 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
   int* kofk = ridm + kFwdStages * NP;                                     // [NP] byte offset 4 (y TW + x) of a window row
   float* tab = reinterpret_cast<float*>(kofk + NP);                       // [NTAB] bias table of the head, log2 units, minus the softmax offset
   float* tred = tab + Cf::NTAB;                                           // [2 NT] per-warp max / min of the table
+  uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(tred + 2 * Cf::NT) + 7) & ~uintptr_t(7));   // [stages] "TMA tiles landed"
   const uint32_t tiles_s = base_u32;
 
   const WinGeom& g = a.g;
@@ -191,8 +199,19 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
   const int64_t it0 = (int64_t)blockIdx.x * per + min((int64_t)blockIdx.x, rem);
   const int nit = (int)(per + ((int64_t)blockIdx.x < rem ? 1 : 0));
   const int C3 = 3 * a.C;
+  const bool tma_on = !Cf::RAGGED && use_tma != 0;
+  // does the item's window lie in one piece on the map (no wrap under the roll)?  CTA-uniform
+  auto in_one_piece = [&](const ItemPos& q) { return tma_on && (g.shift == 0 || (q.wh < g.nWh - 1 && q.ww < g.nWw - 1)); };
 
   for (int r = tid; r < NP; r += Cf::THREADS) kofk[r] = r < N ? 4 * ((r / WS) * TW + (r % WS)) : 0;
+  if (tma_on) {
+    if (tid == 0) {
+      ptx::prefetch_tmap(&tmap);
+      for (int s_ = 0; s_ < kFwdStages; ++s_) ptx::mbar_init(&full[s_], 1);
+      ptx::fence_mbar_init();
+    }
+    __syncthreads();
+  }
 
   // a thread copies the same half row (32 bytes of q, k and v) of every item: row tid / 2, dims 16 (tid & 1) ...
   static_assert(NP * 2 == Cf::THREADS, "two threads per row");
@@ -209,22 +228,34 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
       tokm[stage * NP + prow] = t;
       ridm[stage * NP + prow] = region;
     }
-    if (t >= 0) {
-      const __nv_bfloat16* src = a.qkv + (int64_t)t * C3 + pp.h * HD + (tid & 1) * 16;
+    if (in_one_piece(pp)) {
+      if (tid == 0) {
+        ptx::fence_proxy_async_smem();            // the stage was last written / read through the generic proxy
+        ptx::mbar_arrive_expect_tx(&full[stage], 3u * TILE);
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        ptx::cp_async_16(q0_s + k * TILE + poff, src + k * a.C);
-        ptx::cp_async_16(q0_s + k * TILE + (poff ^ 16u), src + k * a.C + 8);
+        for (int k = 0; k < 3; ++k)
+          ptx::tma_load_4d(q0 + k * TILE, &tmap, &full[stage], k * a.C + pp.h * HD, pp.ww * WS + g.shift,
+                           pp.wh * WS + g.shift, pp.b);
       }
     } else {
-      const float* qp = (t == -1 && a.qpad) ? a.qpad + pp.h * HD + (tid & 1) * 16 : nullptr;
-      const float* vp = (t == -1 && a.vpad) ? a.vpad + pp.h * HD + (tid & 1) * 16 : nullptr;
-      put16(q0, q0_s, poff, nullptr, qp);
-      put16(q0, q0_s, poff ^ 16u, nullptr, qp ? qp + 8 : nullptr);
-      put16(q0 + TILE, q0_s + TILE, poff, nullptr, nullptr);
-      put16(q0 + TILE, q0_s + TILE, poff ^ 16u, nullptr, nullptr);
-      put16(q0 + 2 * TILE, q0_s + 2 * TILE, poff, nullptr, vp);
-      put16(q0 + 2 * TILE, q0_s + 2 * TILE, poff ^ 16u, nullptr, vp ? vp + 8 : nullptr);
+      if (tma_on && tid == 0) ptx::mbar_arrive(&full[stage]);      // a gathered item: the phase completes at once
+      if (t >= 0) {
+        const __nv_bfloat16* src = a.qkv + (int64_t)t * C3 + pp.h * HD + (tid & 1) * 16;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          ptx::cp_async_16(q0_s + k * TILE + poff, src + k * a.C);
+          ptx::cp_async_16(q0_s + k * TILE + (poff ^ 16u), src + k * a.C + 8);
+        }
+      } else {
+        const float* qp = (t == -1 && a.qpad) ? a.qpad + pp.h * HD + (tid & 1) * 16 : nullptr;
+        const float* vp = (t == -1 && a.vpad) ? a.vpad + pp.h * HD + (tid & 1) * 16 : nullptr;
+        put16(q0, q0_s, poff, nullptr, qp);
+        put16(q0, q0_s, poff ^ 16u, nullptr, qp ? qp + 8 : nullptr);
+        put16(q0 + TILE, q0_s + TILE, poff, nullptr, nullptr);
+        put16(q0 + TILE, q0_s + TILE, poff ^ 16u, nullptr, nullptr);
+        put16(q0 + 2 * TILE, q0_s + 2 * TILE, poff, nullptr, vp);
+        put16(q0 + 2 * TILE, q0_s + 2 * TILE, poff ^ 16u, nullptr, vp ? vp + 8 : nullptr);
+      }
     }
     item_next(a, pp);
   };
@@ -249,6 +280,25 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
   for (int i = 0; i < nit; ++i, item_next(a, p)) {
     const int stage = i % kFwdStages;
     ptx::cp_async_wait<1>();                      // this thread's copies of item i have landed
+    if (tma_on) {
+      // ... or the item's three TMA boxes.  Every use of a stage completes one phase of its mbarrier (gathered items by
+      // a plain arrive), so the parity is that of the use count
+      ptx::mbar_wait(&full[stage], (uint32_t)(i / kFwdStages) & 1u);
+      // pad tokens of a window that overhangs the map: the zero fill is their k; q and v are the bias rows
+      if (in_one_piece(p) && (p.wh * WS + g.shift + WS > g.H || p.ww * WS + g.shift + WS > g.W)) {
+        if (tokm[stage * NP + prow] == -1) {
+          unsigned char* q0 = tiles + (size_t)stage * STAGE;
+          const uint32_t q0_s = tiles_s + (uint32_t)stage * STAGE;
+          const float* qp = a.qpad ? a.qpad + p.h * HD + (tid & 1) * 16 : nullptr;
+          const float* vp = a.vpad ? a.vpad + p.h * HD + (tid & 1) * 16 : nullptr;
+          if (qp) { put16(q0, q0_s, poff, nullptr, qp); put16(q0, q0_s, poff ^ 16u, nullptr, qp + 8); }
+          if (vp) {
+            put16(q0 + 2 * TILE, q0_s + 2 * TILE, poff, nullptr, vp);
+            put16(q0 + 2 * TILE, q0_s + 2 * TILE, poff ^ 16u, nullptr, vp + 8);
+          }
+        }
+      }
+    }
     __syncthreads();                              // ... everybody's; and every warp is done with item i - 1
     if (i + 2 < nit) prefetch(i + 2);             // into the stage item i - 1 has just released
     ptx::cp_async_commit();
@@ -436,8 +486,8 @@ attn_mma_fwd_kernel(const __grid_constant__ MmaArgs a) {
 template <int WS>
 size_t mma_fwd_smem() {
   using Cf = MCfg<WS>;
-  return 128 + (size_t)kFwdStages * 3 * Cf::TILE + 2 * (size_t)kFwdStages * Cf::NP * 4 + (size_t)Cf::NTAB * 4 + (size_t)Cf::NP * 4 +
-         2 * (size_t)Cf::NT * 4 + 16;
+  return 1024 + (size_t)kFwdStages * 3 * Cf::TILE + 2 * (size_t)kFwdStages * Cf::NP * 4 + (size_t)Cf::NTAB * 4 + (size_t)Cf::NP * 4 +
+         2 * (size_t)Cf::NT * 4 + 16 + 8 * kFwdStages + 16;
 }
 
 // CTAs of a kernel that fit one SM: shared memory, threads and the per-sub-partition register file (warps of a CTA are
@@ -464,7 +514,16 @@ int launch_mma_fwd(const MmaArgs& a, cudaStream_t st) {
   const int occ = ctas_per_sm(attn_mma_fwd_kernel<WS>, Cf::THREADS, smem);
   int64_t grid = (int64_t)sm_count() * occ;
   if (grid > a.nitems) grid = a.nitems;
-  attn_mma_fwd_kernel<WS><<<(unsigned)grid, Cf::THREADS, smem, st>>>(a);
+  // window boxes of the qkv tensor viewed as [B][H][W][3C]: {32 columns (one head of q, k or v), ws, ws, 1}
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  int use_tma = 0;
+  if (!Cf::RAGGED) {
+    int rc = make_tmap_window_bf16(&tmap, a.qkv, a.g.B, a.g.H, a.g.W, 3 * a.C, WS);
+    if (rc) return rc;
+    use_tma = 1;
+  }
+  attn_mma_fwd_kernel<WS><<<(unsigned)grid, Cf::THREADS, smem, st>>>(a, tmap, use_tma);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
 }

@@ -578,6 +578,23 @@ int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t
   return B200SWIN_OK;
 }
 
+// ws x ws x 32-column boxes (one head of one window) of a bf16 [B][H][W][ld] tensor, written to shared memory as rows of
+// 64 bytes in window order with the 64-byte swizzle; elements beyond H / W are zero-filled
+int make_tmap_window_bf16(CUtensorMap* m, const void* base, int B, int H, int W, int ld, int ws) {
+  EncodeTiledFn enc = get_encode_tiled();
+  BSW_REQUIRE(enc, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  BSW_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && ld % 8 == 0, "TMA: window tensor must be 16-byte aligned");
+  cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {32, (cuuint32_t)ws, (cuuint32_t)ws, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BSW_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (window boxes) failed with CUresult %d", (int)r);
+  return B200SWIN_OK;
+}
+
 int make_tmap_2d(CUtensorMap* m, const void* base, int dtype, uint64_t inner, uint64_t outer,
                  uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode_tiled();

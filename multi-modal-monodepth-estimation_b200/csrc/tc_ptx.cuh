@@ -308,6 +308,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_tiled();
+int make_tmap_window_bf16(CUtensorMap* m, const void* base, int B, int H, int W, int ld, int ws);   // gemm_tc.cu
 
 // 2-D bf16 tensor [outer][inner] (inner contiguous), box [box_outer][box_inner], 128 B swizzle, zero OOB fill.
 int make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
