@@ -1001,21 +1001,26 @@ struct SCfg {
   static constexpr uint32_t OFF_DBS = OFF_BARS + 64;
   static constexpr uint32_t OFF_DVP = OFF_DBS + DBS * 2 * KTHREADS * 8;
   static constexpr uint32_t OFF_DVS = OFF_DVP + 8 * KTHREADS * 4;              // [8][KTHREADS] float: column sums of dV
-  static constexpr uint32_t SMEM = OFF_DVS + 8 * KTHREADS * 4 + 128;
+  static constexpr uint32_t SMEM = OFF_DVS + 8 * KTHREADS * 4 + 1024;        // + alignment of the base to 1 KB (TMA swizzle period)
   static_assert((Cf::NP / 2) * Cf::NP * 4 <= PANEL, "the flush staging lives in a panel");
   static_assert(Cf::NT % NH == 0, "tiles per helper warp");
 };
 
+// Operand staging as in the forward: a window in one piece on the map = four 4-D TMA boxes (q, k, v of the qkv tensor, dO
+// of the dout tensor) issued by one helper thread and completing on full[s] together with the helpers' arrivals; the zero
+// fill of rows beyond H / W is the k and the dO of a pad token, a pad QUERY contributes nothing (lse = +inf), and the v =
+// v_bias of pad KEYS is written by the key warp that owns those 16 rows (nobody else reads them) after the wait.
 template <int WS>
 __global__ void __launch_bounds__(SCfg<WS>::THREADS, 1)
-attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
+attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a, const __grid_constant__ CUtensorMap tm_qkv,
+                         const __grid_constant__ CUtensorMap tm_dout, const int use_tma) {
   using Cf = MCfg<WS>;
   using Sc = SCfg<WS>;
   constexpr int N = Cf::N, NP = Cf::NP, TW = Cf::TW, NT8 = Cf::NTILES8, NT = Cf::NT;
   constexpr int KTH = Sc::KTHREADS, HTH = Sc::HTHREADS;
   constexpr uint32_t TILE = Cf::TILE, PSTRIDE = Sc::PSTRIDE;
   extern __shared__ unsigned char smem_dyn[];
-  const uint32_t base_u32 = (ptx::smem_u32(smem_dyn) + 127u) & ~127u;
+  const uint32_t base_u32 = (ptx::smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sm = smem_dyn + (base_u32 - ptx::smem_u32(smem_dyn));
   float2* qmeta = reinterpret_cast<float2*>(sm + Sc::OFF_QMETA);
   float2* innorm = reinterpret_cast<float2*>(sm + Sc::OFF_INN);
@@ -1036,9 +1041,12 @@ attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
   const int64_t it0 = (int64_t)blockIdx.x * per + min((int64_t)blockIdx.x, rem);
   const int nit = (int)(per + ((int64_t)blockIdx.x < rem ? 1 : 0));
   const int C3 = 3 * a.C;
+  const bool tma_on = !Cf::RAGGED && use_tma != 0;
+  auto in_one_piece = [&](const ItemPos& q) { return tma_on && (g.shift == 0 || (q.wh < g.nWh - 1 && q.ww < g.nWw - 1)); };
 
   for (int r = tid; r < NP; r += Sc::THREADS) kofk[r] = r < N ? 4 * ((r / WS) * TW + (r % WS)) : 0;
   if (tid == 0) {
+    if (tma_on) { ptx::prefetch_tmap(&tm_qkv); ptx::prefetch_tmap(&tm_dout); }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&full[s], 2 * HTH);          // per helper thread: its cp.async have landed + its plain stores are released
       ptx::mbar_init(&pfull[s], NT);              // lane 0 of every key warp
@@ -1060,6 +1068,7 @@ attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
       const int stage = i & 1;
       unsigned char* q0 = sm + (size_t)stage * Sc::STAGE_TILES;
       const uint32_t q0_s = base_u32 + (uint32_t)stage * Sc::STAGE_TILES;
+      const bool one = in_one_piece(pp);
 #pragma unroll 1
       for (int k = 0; k < NT / Sc::NH; ++k) {     // a helper warp copies the tile 3 k + hw in round k
         const int task = k * HTH + hid, prow = task >> 1, half = task & 1;
@@ -1086,6 +1095,7 @@ attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
             *im = make_float2(0.f, 0.f);
           }
         }
+        if (one) continue;                        // the tiles come as TMA boxes (below)
         if (t >= 0) {
           const __nv_bfloat16* src = a.qkv + (int64_t)t * C3 + pp.h * HD + half * 16;
           const __nv_bfloat16* gsrc = a.dout + (int64_t)t * a.C + pp.h * HD + half * 16;
@@ -1111,7 +1121,16 @@ attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
         }
       }
       ptx::cp_async_mbar_arrive_noinc(&full[stage]);
-      ptx::mbar_arrive(&full[stage]);
+      if (one && hid == 0) {
+        ptx::fence_proxy_async_smem();            // the stage was last read / written through the generic proxy
+        ptx::mbar_arrive_expect_tx(&full[stage], 4u * TILE);
+        const int x0 = pp.ww * WS + g.shift, y0 = pp.wh * WS + g.shift;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) ptx::tma_load_4d(q0 + kk * TILE, &tm_qkv, &full[stage], kk * a.C + pp.h * HD, x0, y0, pp.b);
+        ptx::tma_load_4d(q0 + 3 * TILE, &tm_dout, &full[stage], pp.h * HD, x0, y0, pp.b);
+      } else {
+        ptx::mbar_arrive(&full[stage]);
+      }
       item_next(a, pp);
     };
     if (nit > 0) gather(0);
@@ -1351,6 +1370,18 @@ attn_mma_bwd_spec_kernel(const __grid_constant__ MmaArgs a) {
     const uint32_t tab_s = ptx::smem_u32(tab) + 4u * (uint32_t)((WS - 1) * (TW + 1));
     const uint32_t tabA = tab_s - (uint32_t)kofk[rA], tabB = tab_s - (uint32_t)kofk[rB];
     const int ridA = ridS[rA], ridB = ridS[rB];
+    if (in_one_piece(p) && (p.wh * WS + g.shift + WS > g.H || p.ww * WS + g.shift + WS > g.W)) {
+      // TMA-staged window that overhangs the map: this warp's pad keys get v = v_bias (their k is the zero fill)
+      const int row = warp * 16 + (lane >> 1);
+      if (a.vpad && tokS[row] == -1) {
+        unsigned char* vt = sm + (size_t)stage * Sc::STAGE_TILES + 2 * TILE;
+        const float* vp = a.vpad + p.h * HD + (lane & 1) * 16;
+        const uint32_t off = sw64(row, (lane & 1) * 2);
+        put16(vt, v_s, off, nullptr, vp);
+        put16(vt, v_s, off ^ 16u, nullptr, vp + 8);
+      }
+      __syncwarp();
+    }
     uint32_t ka[2][4], va[2][4];
     ldsm4(ka[0], k_s + la_off);
     ldsm4(ka[1], k_s + (la_off ^ 32u));
@@ -1505,7 +1536,11 @@ int launch_mma_bwd_spec(const MmaArgs& a, cudaStream_t st) {
   BSW_CUDA(cudaFuncSetAttribute(attn_mma_bwd_spec_kernel<WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = sm_count();
   if (grid > a.nitems) grid = a.nitems;
-  attn_mma_bwd_spec_kernel<WS><<<(unsigned)grid, Sc::THREADS, smem, st>>>(a);
+  CUtensorMap tm_qkv, tm_dout;                   // window boxes of qkv [B][H][W][3C] and dout [B][H][W][C]
+  int rc = make_tmap_window_bf16(&tm_qkv, a.qkv, a.g.B, a.g.H, a.g.W, 3 * a.C, WS);
+  if (rc == B200SWIN_OK) rc = make_tmap_window_bf16(&tm_dout, a.dout, a.g.B, a.g.H, a.g.W, a.C, WS);
+  if (rc) return rc;
+  attn_mma_bwd_spec_kernel<WS><<<(unsigned)grid, Sc::THREADS, smem, st>>>(a, tm_qkv, tm_dout, 1);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
 }
