@@ -517,12 +517,8 @@ int launch_mma_fwd(const MmaArgs& a, cudaStream_t st) {
   // window boxes of the qkv tensor viewed as [B][H][W][3C]: {32 columns (one head of q, k or v), ws, ws, 1}
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  int use_tma = 0;
-  if (!Cf::RAGGED) {
-    int rc = make_tmap_window_bf16(&tmap, a.qkv, a.g.B, a.g.H, a.g.W, 3 * a.C, WS);
-    if (rc) return rc;
-    use_tma = 1;
-  }
+  // (a shape the driver refuses to encode -- none known -- is served by the cp.async gather alone)
+  const int use_tma = !Cf::RAGGED && make_tmap_window_bf16(&tmap, a.qkv, a.g.B, a.g.H, a.g.W, 3 * a.C, WS) == B200SWIN_OK;
   attn_mma_fwd_kernel<WS><<<(unsigned)grid, Cf::THREADS, smem, st>>>(a, tmap, use_tma);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
@@ -1537,10 +1533,11 @@ int launch_mma_bwd_spec(const MmaArgs& a, cudaStream_t st) {
   int64_t grid = sm_count();
   if (grid > a.nitems) grid = a.nitems;
   CUtensorMap tm_qkv, tm_dout;                   // window boxes of qkv [B][H][W][3C] and dout [B][H][W][C]
-  int rc = make_tmap_window_bf16(&tm_qkv, a.qkv, a.g.B, a.g.H, a.g.W, 3 * a.C, WS);
-  if (rc == B200SWIN_OK) rc = make_tmap_window_bf16(&tm_dout, a.dout, a.g.B, a.g.H, a.g.W, a.C, WS);
-  if (rc) return rc;
-  attn_mma_bwd_spec_kernel<WS><<<(unsigned)grid, Sc::THREADS, smem, st>>>(a, tm_qkv, tm_dout, 1);
+  memset(&tm_qkv, 0, sizeof(tm_qkv));
+  memset(&tm_dout, 0, sizeof(tm_dout));
+  const int use_tma = make_tmap_window_bf16(&tm_qkv, a.qkv, a.g.B, a.g.H, a.g.W, 3 * a.C, WS) == B200SWIN_OK &&
+                      make_tmap_window_bf16(&tm_dout, a.dout, a.g.B, a.g.H, a.g.W, a.C, WS) == B200SWIN_OK;
+  attn_mma_bwd_spec_kernel<WS><<<(unsigned)grid, Sc::THREADS, smem, st>>>(a, tm_qkv, tm_dout, use_tma);
   BSW_LAUNCH_CHECK();
   return B200SWIN_OK;
 }

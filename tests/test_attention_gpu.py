@@ -328,7 +328,13 @@ def test_attention_large_temperature_takes_the_online_softmax_path(ws, H, shift)
     (2, 24, 24, 128, 4, 12, 6, torch.bfloat16, "ws"), (1, 30, 30, 64, 2, 12, 6, torch.bfloat16, "ws"),
     (1, 15, 15, 64, 2, 6, 3, torch.bfloat16, "ws"), (1, 21, 14, 64, 2, 7, 3, torch.bfloat16, "ws"),
     (2, 24, 24, 128, 4, 12, 6, torch.bfloat16, "mma"), (1, 30, 30, 64, 2, 12, 0, torch.bfloat16, "mma"),
-    (1, 21, 14, 64, 2, 7, 3, torch.bfloat16, "mma"), (2, 16, 20, 96, 3, 8, 4, torch.bfloat16, "mma")])
+    (1, 21, 14, 64, 2, 7, 3, torch.bfloat16, "mma"), (2, 16, 20, 96, 3, 8, 4, torch.bfloat16, "mma"),
+    # TMA window boxes at their edges: a map smaller than one window (the box overhangs on both sides, most rows are the
+    # hardware's zero fill + pad fix-ups), a one-window-wide map (every shifted window is on the roll seam -> gather path
+    # only), overhang in one direction only, several frames (box coordinate 3)
+    (3, 5, 7, 64, 2, 12, 0, torch.bfloat16, "tc"), (2, 5, 7, 64, 2, 12, 6, torch.bfloat16, "tc"),
+    (2, 12, 40, 64, 2, 12, 6, torch.bfloat16, "tc"), (4, 24, 29, 96, 3, 12, 6, torch.bfloat16, "tc"),
+    (3, 6, 17, 64, 2, 8, 0, torch.bfloat16, "tc"), (5, 3, 9, 32, 1, 4, 2, torch.bfloat16, "tc")])
 def test_attention_core_vs_oracle(B, H, W, C, nH, ws, shift, dtype, impl):
     """The core kernel alone (natural-order qkv in, natural-order out), forward and every gradient, against the
     oracle's gather -> dense attention -> scatter in float64.  Bars: fp32 1e-4 (2e-4 on the long parameter-gradient
