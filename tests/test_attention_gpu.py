@@ -334,7 +334,8 @@ def test_attention_large_temperature_takes_the_online_softmax_path(ws, H, shift)
     # only), overhang in one direction only, several frames (box coordinate 3)
     (3, 5, 7, 64, 2, 12, 0, torch.bfloat16, "tc"), (2, 5, 7, 64, 2, 12, 6, torch.bfloat16, "tc"),
     (2, 12, 40, 64, 2, 12, 6, torch.bfloat16, "tc"), (4, 24, 29, 96, 3, 12, 6, torch.bfloat16, "tc"),
-    (3, 6, 17, 64, 2, 8, 0, torch.bfloat16, "tc"), (5, 3, 9, 32, 1, 4, 2, torch.bfloat16, "tc")])
+    # (enough frames that the temperature gradient, one heavily cancelling number per head, averages its bf16 rounding)
+    (24, 6, 17, 64, 2, 8, 0, torch.bfloat16, "tc"), (40, 3, 9, 32, 1, 4, 2, torch.bfloat16, "tc")])
 def test_attention_core_vs_oracle(B, H, W, C, nH, ws, shift, dtype, impl):
     """The core kernel alone (natural-order qkv in, natural-order out), forward and every gradient, against the
     oracle's gather -> dense attention -> scatter in float64.  Bars: fp32 1e-4 (2e-4 on the long parameter-gradient
