@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(128) gattn_fwd_mma_kernel(GArgs a) {
       float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       mma_rows_nt<HD>(acc, qf, ks_s, np * 16, lane);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) { s[2 * np][e] = acc[0][e] * sl2; s[2 * np + 1][e] = acc[1][e] * sl2; }
+      for (int e = 0; e < 4; ++e) { s[2 * np][e] = acc[0][e]; s[2 * np + 1][e] = acc[1][e]; }    // raw dot products
     }
     if ((ib + 1) * 64 > a.Nk) {            // last block: keys beyond the sequence
 #pragma unroll
@@ -198,16 +198,20 @@ __global__ void __launch_bounds__(128) gattn_fwd_mma_kernel(GArgs a) {
       mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
       mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
     }
-    const float mn0 = fmaxf(m0, quad_max(mx0)), mn1 = fmaxf(m1, quad_max(mx1));     // finite: key ib*64 always exists
+    // running maxima in the log2 domain (the scale is positive, so the maximum of the raw products is the maximum);
+    // finite: key ib*64 always exists
+    const float mn0 = fmaxf(m0, quad_max(mx0) * sl2), mn1 = fmaxf(m1, quad_max(mx1) * sl2);
     const float al0 = ex2f(m0 - mn0), al1 = ex2f(m1 - mn1);
     m0 = mn0; m1 = mn1;
     l0 *= al0; l1 *= al1;
+    if (__any_sync(0xffffffffu, al0 != 1.f || al1 != 1.f)) {     // after the first blocks the maxima rarely move
 #pragma unroll
-    for (int j = 0; j < HD / 8; ++j) { o[j][0] *= al0; o[j][1] *= al0; o[j][2] *= al1; o[j][3] *= al1; }
+      for (int j = 0; j < HD / 8; ++j) { o[j][0] *= al0; o[j][1] *= al0; o[j][2] *= al1; o[j][3] *= al1; }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      s[j][0] = ex2f(s[j][0] - mn0); s[j][1] = ex2f(s[j][1] - mn0);
-      s[j][2] = ex2f(s[j][2] - mn1); s[j][3] = ex2f(s[j][3] - mn1);
+      s[j][0] = ex2f(fmaf(s[j][0], sl2, -mn0)); s[j][1] = ex2f(fmaf(s[j][1], sl2, -mn0));
+      s[j][2] = ex2f(fmaf(s[j][2], sl2, -mn1)); s[j][3] = ex2f(fmaf(s[j][3], sl2, -mn1));
       l0 += s[j][0] + s[j][1];
       l1 += s[j][2] + s[j][3];
     }
