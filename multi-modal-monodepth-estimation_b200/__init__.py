@@ -7,6 +7,7 @@ reference's module layout for the path it replaces:
 
     b200swin.swin_transformer_v2   <->  models/swin_transformer_v2.py
     b200swin.criterion             <->  utils/criterion.py
+    b200swin.cnn_transformer       <->  the global-attention encoder layer of models/cnn_transformer.py
 
 Everything executes through libb200swin.so (hand-written CUDA behind the C-ABI of
 include/b200swin.h); there is no CPU or eager-PyTorch fallback.

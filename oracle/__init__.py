@@ -18,6 +18,9 @@ What is here
   (``:648-678``), ``PatchEmbed`` (``:941-957``), ``BasicLayer.forward`` (``:866-908``)
   and ``SwinTransformerV2.forward`` (``:1251-1277``), driven by a reference
   ``state_dict``; plus the hand-derived backward of SURVEY appendix A.
+* ``mha_ref``     - ``torch.nn.MultiheadAttention`` (batch_first, no masks) and the reference's
+  ``Transformer_Encoder`` layer built on it (``models/cnn_transformer.py:176-216``); ``swin_ref`` also restates the
+  ``attn_type='normal'`` / learned-bias-table / ``ConvMlp`` branches of the Swin file (``:92-117, 241-244, 296-298``).
 * ``silog_ref``   - ``SiLogLoss`` (``utils/criterion.py:15-21``) with its closed-form
   gradient, and the ``eval_depth`` metrics (``utils/metrics.py:9-32``).
 
