@@ -118,6 +118,13 @@ int b200swin_ln_fwd(const void* x, const void* residual, const float* gamma, con
 int b200swin_ln_fwd_stream32(const void* x, const float* residual32, const float* gamma, const float* beta,
                              const float* row_scale, int64_t rows_per_scale, void* y, float* y32, float* mean,
                              float* rstd, int64_t rows, int C, float eps, void* stream);
+/* Post-norm transformer layer (Transformer_Encoder.forward, models/cnn_transformer.py:202-203, :208-209):
+ *   y = LN(x + xadd) * gamma + beta        x: the fp32 stream, xadd: the branch output (xadd_dtype: float32 or bfloat16)
+ * in ONE pass instead of an elementwise add, a LayerNorm and a cast: y float32, y16 (nullable) = bf16(y) for the next
+ * GEMM, xsum (nullable) = x + xadd in float32 -- the tensor b200swin_ln_bwd normalises (dtype 0); its dx is the gradient
+ * of x and of xadd alike.  C % 4 == 0, C <= 1024. */
+int b200swin_ln_fwd_sum(const float* x, const void* xadd, int xadd_dtype, const float* gamma, const float* beta, float* y,
+                        void* y16, float* xsum, float* mean, float* rstd, int64_t rows, int C, float eps, void* stream);
 size_t b200swin_ln_bwd_workspace_bytes(int64_t rows, int C);
 int b200swin_ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                     const float* row_scale, int64_t rows_per_scale, void* dx, float* dgamma, float* dbeta,

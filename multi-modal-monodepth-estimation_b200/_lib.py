@@ -42,6 +42,7 @@ SIGNATURES = {
     "b200swin_cpb_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, P, I, I, I, P]),
     "b200swin_ln_fwd": (I, [P, P, P, P, P, L, P, P, P, L, I, F, I, P]),
     "b200swin_ln_fwd_stream32": (I, [P, P, P, P, P, L, P, P, P, P, L, I, F, P]),
+    "b200swin_ln_fwd_sum": (I, [P, P, I, P, P, P, P, P, P, P, L, I, F, P]),
     "b200swin_ln_bwd_workspace_bytes": (Z, [L, I]),
     "b200swin_ln_bwd": (I, [P, P, P, P, P, P, L, P, P, P, P, L, I, I, P, Z, P]),
     "b200swin_attn_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P]),
@@ -92,7 +93,7 @@ class _Instrumented:
 # kernels launched per C-ABI call (for the bench's gpu_launches claim); split-K gemm adds its reduce
 KERNELS_PER_CALL = {
     "b200swin_silog_fwd": 2, "b200swin_silog_bwd": 1, "b200swin_window_gather": 1, "b200swin_window_scatter": 1,
-    "b200swin_shift_mask": 1, "b200swin_patch_merge": 1, "b200swin_patchify": 1, "b200swin_cpb_fwd": 1, "b200swin_cpb_bwd": 1, "b200swin_ln_fwd": 1, "b200swin_ln_fwd_stream32": 1, "b200swin_ln_bwd": 2, "b200swin_attn_fwd": 1,
+    "b200swin_shift_mask": 1, "b200swin_patch_merge": 1, "b200swin_patchify": 1, "b200swin_cpb_fwd": 1, "b200swin_cpb_bwd": 1, "b200swin_ln_fwd": 1, "b200swin_ln_fwd_stream32": 1, "b200swin_ln_fwd_sum": 1, "b200swin_ln_bwd": 2, "b200swin_attn_fwd": 1,
     "b200swin_attn_bwd": 2, "b200swin_gemm_bf16": 1, "b200swin_split_bf16": 1, "b200swin_colsum": 2,
     "b200swin_adamw_step": 1, "b200swin_mha_fwd": 1, "b200swin_mha_bwd": 3, "b200swin_mha_avg_weights": 1,
     "b200swin_dwconv3x3": 1, "b200swin_dwconv3x3_wgrad": 2,

@@ -51,6 +51,10 @@ class MultiheadAttention(nn.Module):
 
     def _proj(self, x, lo, hi):
         b = self.in_proj_bias[lo:hi] if self.in_proj_bias is not None else None
+        if x.dtype == torch.float32 and ops.compute_dtype(x) == torch.bfloat16:
+            t = ops.bf16_twin_of(x)                   # written by the previous layer's LayerNorm kernel: no cast pass
+            if t is not None:
+                x = t
         return ops.linear(x, self.in_proj_weight[lo:hi], b)
 
     def forward(self, query, key, value, key_padding_mask=None, need_weights=True, attn_mask=None,
@@ -114,7 +118,11 @@ class Transformer_Encoder(nn.Module):
         q = k = img_feat + img_pos
         v = img_feat
         x, _ = self.self_attn(q, k, v, need_weights=False)       # the reference computes the weights and drops them
-        x = ops.layer_norm_residual((v + x).float(), self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        # x = norm1(v + x): add, LayerNorm and the bf16 copy for the next GEMM in one kernel; the stream stays fp32
+        amp = ops.compute_dtype(img_feat) == torch.bfloat16
+        x32, x16 = ops.layer_norm_sum(v, x, self.norm1.weight, self.norm1.bias, self.norm1.eps, want16=amp)
         # Linear -> ReLU -> Linear as two GEMMs, the ReLU (and its 0/1 derivative for the backward) in the first epilogue
-        x2 = ops.mlp(x, self.ffn1[0].weight, self.ffn1[0].bias, self.ffn2[0].weight, self.ffn2[0].bias, relu=True)
-        return ops.layer_norm_residual((x + x2).float(), self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        x2 = ops.mlp(x16 if amp else x32, self.ffn1[0].weight, self.ffn1[0].bias, self.ffn2[0].weight, self.ffn2[0].bias,
+                     relu=True)
+        y32, _ = ops.layer_norm_sum(x32, x2, self.norm2.weight, self.norm2.bias, self.norm2.eps, want16=amp)
+        return y32                                               # carries its bf16 copy for the next layer's v projection

@@ -75,6 +75,76 @@ ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ residual, const flo
   }
 }
 
+// Post-norm transformer layer:  y = LN(x + xadd) * gamma + beta   (Transformer_Encoder.forward,
+// models/cnn_transformer.py:202-203 and :208-209: `x = v + attn(x); x = norm1(x)` / `x = x + ffn(x); x = norm2(x)`).
+// x is the fp32 stream, xadd the branch output (fp32 or bf16: the GEMM's output type under autocast).  One pass instead of
+// an elementwise add, a LayerNorm and the cast of the result for the next GEMM: y (fp32) and, optionally, y16 = bf16(y)
+// and xsum = x + xadd (what the backward normalises; written only when a backward will run).
+template <typename A, int NV, int R>
+__global__ void __launch_bounds__(kLnThreads)
+ln_fwd_sum_kernel(const float* __restrict__ x, const A* __restrict__ xadd, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float* __restrict__ y, __nv_bfloat16* __restrict__ y16,
+                  float* __restrict__ xsum, float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int C,
+                  float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kLnWarps;
+  const float inv_c = 1.0f / (float)C;
+  for (int64_t row0 = warp0 * R; row0 < rows; row0 += nwarps * R) {
+    float v[R][NV][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = lane * 4 + k * 128;
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[r][k][e] = 0.f;
+        if (row < rows && c < C) {
+          ld4(x + row * C + c, v[r][k]);
+          ld4(xadd + row * C + c, a);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[r][k][e] += a[e];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = row0 + r;
+      if (row >= rows) break;                       // warp-uniform
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) s += (v[r][k][0] + v[r][k][1]) + (v[r][k][2] + v[r][k][3]);
+      const float mean = warp_sum(s) * inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        if (lane * 4 + k * 128 < C) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float d = v[r][k][e] - mean; q = fmaf(d, d, q); }
+        }
+      }
+      const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = lane * 4 + k * 128;
+        if (c < C) {
+          float g[4], b[4], o[4];
+          ld4(gamma + c, g);
+          ld4(beta + c, b);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = (v[r][k][e] - mean) * rstd * g[e] + b[e];
+          st4(y + row * C + c, o);
+          if (y16) st4(y16 + row * C + c, o);
+          if (xsum) st4(xsum + row * C + c, v[r][k]);
+        }
+      }
+      if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    }
+  }
+}
+
 // Backward: dx per row, and per-block partial sums of dgamma/dbeta (reduced by ln_param_reduce_kernel).
 template <typename T, int NV, int R>
 __global__ void __launch_bounds__(kLnThreads)
@@ -766,6 +836,35 @@ extern "C" int b200swin_ln_fwd(const void* x, const void* residual, const float*
     return ln_fwd_launch<float>(x, residual, gamma, beta, row_scale, rows_per_scale, y, mean, rstd, rows, C, eps, st);
   return ln_fwd_launch<__nv_bfloat16>(x, residual, gamma, beta, row_scale, rows_per_scale, y, mean, rstd, rows, C,
                                       eps, st);
+}
+
+template <typename A>
+static int ln_fwd_sum_launch(const float* x, const void* xadd, const float* gamma, const float* beta, float* y, void* y16,
+                             float* xsum, float* mean, float* rstd, int64_t rows, int C, float eps, cudaStream_t st) {
+  const int grid = ln_grid(rows);
+#define LN_SUM(NV, R)                                                                                                  \
+  ln_fwd_sum_kernel<A, NV, R><<<grid, kLnThreads, 0, st>>>(x, (const A*)xadd, gamma, beta, y, (__nv_bfloat16*)y16, xsum, \
+                                                           mean, rstd, rows, C, eps)
+  if (C <= 128) LN_SUM(1, 4);
+  else if (C <= 256) LN_SUM(2, 2);
+  else if (C <= 512) LN_SUM(4, 2);
+  else LN_SUM(8, 1);
+#undef LN_SUM
+  BSW_LAUNCH_CHECK();
+  return B200SWIN_OK;
+}
+
+extern "C" int b200swin_ln_fwd_sum(const float* x, const void* xadd, int xadd_dtype, const float* gamma, const float* beta,
+                                   float* y, void* y16, float* xsum, float* mean, float* rstd, int64_t rows, int C, float eps,
+                                   void* stream) {
+  BSW_REQUIRE(x && xadd && gamma && beta && y && mean && rstd, "ln_fwd_sum: null pointer");
+  BSW_REQUIRE(rows >= 0 && C > 0 && C % 4 == 0 && C <= 1024, "ln_fwd_sum: C=%d must be a multiple of 4, <= 1024", C);
+  BSW_REQUIRE(xadd_dtype == B200SWIN_F32 || xadd_dtype == B200SWIN_BF16, "ln_fwd_sum: bad dtype %d", xadd_dtype);
+  if (rows == 0) return B200SWIN_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (xadd_dtype == B200SWIN_F32)
+    return ln_fwd_sum_launch<float>(x, xadd, gamma, beta, y, y16, xsum, mean, rstd, rows, C, eps, st);
+  return ln_fwd_sum_launch<__nv_bfloat16>(x, xadd, gamma, beta, y, y16, xsum, mean, rstd, rows, C, eps, st);
 }
 
 extern "C" int b200swin_ln_fwd_stream32(const void* x, const float* residual32, const float* gamma, const float* beta,

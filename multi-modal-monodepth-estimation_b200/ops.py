@@ -956,3 +956,78 @@ class _DwConv3x3(torch.autograd.Function):
 
 def dwconv3x3(x, weight):
     return _DwConv3x3.apply(x, weight)
+
+
+# ------------------------------------------------------------------------------ post-norm transformer layer: LN(x + branch)
+class _LayerNormSum(torch.autograd.Function):
+    """(y32, y16) = LN(x + xadd) * gamma + beta in one kernel (reference: `x = v + attn; x = norm1(x)` and
+    `x = x + ffn; x = norm2(x)`, models/cnn_transformer.py:202-203, :208-209).  x is the fp32 stream, xadd the branch output
+    (fp32, or bf16 under autocast); y16 = bf16(y32) is the operand of the next GEMM (None unless asked for).  The backward
+    normalises the saved sum; its dx is the gradient of x and of xadd alike."""
+
+    @staticmethod
+    def forward(ctx, x, xadd, gamma, beta, eps, want16, will_backward):
+        L.require_cuda(x, xadd, gamma, beta)
+        lib = L.load()
+        C = x.shape[-1]
+        xc = x.contiguous()
+        if xc.dtype != torch.float32:
+            xc = xc.float()
+        ac = xadd.contiguous()
+        rows = xc.numel() // C
+        g32 = gamma.contiguous().float()
+        b32 = beta.contiguous().float()
+        keep = will_backward and any(ctx.needs_input_grad)
+        with torch.cuda.device_of(xc):
+            y = torch.empty_like(xc)
+            y16 = torch.empty(xc.shape, dtype=torch.bfloat16, device=xc.device) if want16 else None
+            xsum = torch.empty_like(xc) if keep else None
+            stats = torch.empty((2, rows), dtype=torch.float32, device=xc.device)
+            L.check(lib.b200swin_ln_fwd_sum(xc.data_ptr(), ac.data_ptr(), L.dtype_code(ac), g32.data_ptr(), b32.data_ptr(),
+                                            y.data_ptr(), L.ptr(y16), L.ptr(xsum), stats[0].data_ptr(), stats[1].data_ptr(),
+                                            rows, C, float(eps), L.stream_of(xc)), "ln_fwd_sum")
+        ctx.save_for_backward(xsum, g32, stats)
+        ctx.dtypes = (x.dtype, xadd.dtype, gamma.dtype, beta.dtype)
+        ctx.set_materialize_grads(False)
+        return y.view(x.shape), (None if y16 is None else y16.view(x.shape))
+
+    @staticmethod
+    def backward(ctx, dy32, dy16=None):
+        xsum, g32, stats = ctx.saved_tensors
+        lib = L.load()
+        C = xsum.shape[-1]
+        rows = xsum.numel() // C
+        if dy32 is None and dy16 is None:
+            return None, None, None, None, None, None, None
+        dy = dy32.float() if dy32 is not None else None
+        if dy16 is not None:
+            dy = dy16.float() if dy is None else dy + dy16.float()
+        dyc = dy.contiguous()
+        with torch.cuda.device_of(xsum):
+            dx = torch.empty_like(xsum)
+            dgb = torch.empty((2, C), dtype=torch.float32, device=xsum.device)
+            ws_bytes = lib.b200swin_ln_bwd_workspace_bytes(rows, C)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xsum.device)
+            L.check(lib.b200swin_ln_bwd(dyc.data_ptr(), xsum.data_ptr(), g32.data_ptr(), stats[0].data_ptr(),
+                                        stats[1].data_ptr(), 0, 1, dx.data_ptr(), dgb[0].data_ptr(), dgb[1].data_ptr(), 0,
+                                        rows, C, L.F32, ws.data_ptr(), ws_bytes, L.stream_of(xsum)), "ln_bwd")
+        xd, ad, gd, bd = ctx.dtypes
+        return (dx if xd == torch.float32 else dx.to(xd), dx if ad == torch.float32 else dx.to(ad),
+                dgb[0].to(gd), dgb[1].to(bd), None, None, None)
+
+
+_TWIN16 = "_b200swin_bf16_twin"
+
+
+def layer_norm_sum(x, xadd, gamma, beta, eps, want16=False):
+    """(y32, y16 | None) = LN(x + xadd); y32 carries y16 as an attribute so that the next layer's GEMMs can read it."""
+    y32, y16 = _LayerNormSum.apply(x, xadd, gamma, beta, float(eps), bool(want16), torch.is_grad_enabled())
+    if y16 is not None:
+        setattr(y32, _TWIN16, y16)
+    return y32, y16
+
+
+def bf16_twin_of(x: torch.Tensor):
+    """The bf16 copy layer_norm_sum wrote beside an fp32 tensor (None when there is none or it does not match)."""
+    t = getattr(x, _TWIN16, None)
+    return t if (t is not None and t.shape == x.shape and t.device == x.device) else None
