@@ -131,3 +131,31 @@ def test_tiny_block_norm_gammas_survive_bf16_autocast():
     # below a bf16 ulp cannot pass through that operand; only its own blocks' contributions are preserved.
     assert errs[0] < 0.05, errs
     assert errs[1] < 0.6, errs
+
+
+@pytest.mark.parametrize("add_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,C", [(260, 256), (1201, 512), (7, 1024), (33, 128)])
+def test_layer_norm_sum_vs_float64(rows, C, add_dtype):
+    """y = LN(x + xadd) in one kernel (Transformer_Encoder's post-norm, models/cnn_transformer.py:202-203, :208-209): both
+    outputs and every gradient against float64; the bf16 copy is the rounding of the fp32 output."""
+    from b200swin import ops
+    g = torch.Generator().manual_seed(rows + C)
+    x = torch.randn(rows, C, generator=g).cuda().requires_grad_(True)
+    xa = torch.randn(rows, C, generator=g).cuda().to(add_dtype).requires_grad_(True)
+    gamma = (1 + 0.3 * torch.randn(C, generator=g)).cuda().requires_grad_(True)
+    beta = (0.2 * torch.randn(C, generator=g)).cuda().requires_grad_(True)
+    # (the cotangent of the bf16 output travels as bf16: keep it representable)
+    c32, c16 = torch.randn(rows, C, generator=g).cuda(), torch.randn(rows, C, generator=g).cuda().bfloat16().float()
+    y32, y16 = ops.layer_norm_sum(x, xa, gamma, beta, 1e-5, want16=True)
+    assert y32.dtype == torch.float32 and y16.dtype == torch.bfloat16 and torch.equal(y16, y32.detach().bfloat16())
+    assert ops.bf16_twin_of(y32) is y16
+    ((y32 * c32).sum() + (y16.float() * c16).sum()).backward()
+    x6, a6, g6, b6 = [t.detach().double().cpu().requires_grad_(True) for t in (x, xa, gamma, beta)]
+    y6 = torch.nn.functional.layer_norm(x6 + a6, (C,), g6, b6, 1e-5)
+    (y6 * (c32 + c16).double().cpu()).sum().backward()
+
+    def rel(a, r):
+        return ((a.detach().double().cpu() - r).norm() / r.norm()).item()
+    assert rel(y32, y6.detach()) < 1e-5
+    assert rel(x.grad, x6.grad) < 1e-4 and rel(gamma.grad, g6.grad) < 1e-4 and rel(beta.grad, b6.grad) < 1e-4
+    assert rel(xa.grad, a6.grad) < (1e-4 if add_dtype == torch.float32 else 5e-3)       # bf16 storage of the gradient
