@@ -64,6 +64,7 @@ struct FlArgs {
   float* dvpad;
   WinGeom g;
   int C, nH, N, ntiles, rpt, kb, nkb, ntab, nmeta;
+  int ntabc;                  // DQ: entries of a warp's COMPACT gradient table (see the kernel), <= ntab
   int64_t nwin, nunits;
 };
 
@@ -188,7 +189,13 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
   int* kof = tok + a.nmeta;                                        // [nmeta] byte offset 4 (y TW + x) into the bias table
   int* rid = kof + a.nmeta;                                        // [nmeta] shift-mask region id | beyond the window << 8
   float* tab = reinterpret_cast<float*>(rid + a.nmeta);            // [ntab] bias table of the head, log2 units
-  float* dtab = tab + a.ntab;                                      // DQ: [4 warps][ntab] private gradient sums
+  // DQ: [4 warps][ntabc] private gradient sums of the bias table.  A warp's 32 query rows span at most 31 / ws + 2 window
+  // rows, so it only ever touches ws - 1 + that many of the table's 2 ws - 1 rows (dy = y_query - y_key): the private
+  // tables hold just those rows, indexed from the warp's first window row.  That is 54 % of the full table at 24 / 30
+  // windows and makes room for one more CTA per SM (30x30: two instead of one).  The price: the units of a CTA run in
+  // (head, row tile, window) order -- a warp's rows stay put while the windows stream by -- and the tables are flushed
+  // when the (head, tile) pair changes.
+  float* dtab = tab + a.ntab;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t per = a.nunits / gridDim.x, rem = a.nunits % gridDim.x;
@@ -206,7 +213,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
     ptx::tmem_relinquish();
   }
   if (MODE == MODE_DQ)
-    for (int i = tid; i < 4 * a.ntab; i += kThreads) dtab[i] = 0.f;
+    for (int i = tid; i < 4 * a.ntabc; i += kThreads) dtab[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -220,19 +227,26 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
   const uint64_t desc_k = ptx::make_smem_desc(0, 16, 512, kSw64);          // K-major tile of 64 B rows
   const uint64_t desc_mn = ptx::make_smem_desc(0, 512, 512, kSw64);        // the same bytes read MN-major
 
-  int cur_h = -1;
+  int cur_h = -1, cur_tile = -1;
   int64_t cur_win = -1;
   float sc = 0.f, scale2 = 0.f, dsc = 0.f;
-  float* dtabw = dtab + warp * a.ntab;
+  float* dtabw = dtab + warp * a.ntabc;
   bool need_mask = false;
+  const bool compact = a.ntabc < a.ntab;
+  // first table row (dy index) a warp's compact table holds while the CTA works on row tile `tile`
+  auto first_dy = [&](int tile, int w) { return compact ? (tile * a.rpt + w * 32) / ws : 0; };
 
-  auto flush_head = [&](int h) {
-    // DQ: gradient sums of head h -> global (one atomic per table entry and CTA)
+  auto flush_head = [&](int h, int tile) {
+    // DQ: gradient sums of head h -> global (one atomic per touched table entry and warp)
     __syncthreads();
-    for (int r = tid; r < a.ntab; r += kThreads) {
-      const float v = (dtab[r] + dtab[a.ntab + r]) + (dtab[2 * a.ntab + r] + dtab[3 * a.ntab + r]);
-      dtab[r] = dtab[a.ntab + r] = dtab[2 * a.ntab + r] = dtab[3 * a.ntab + r] = 0.f;
-      if (v != 0.f) atomicAdd(a.dtable16 + (int64_t)r * a.nH + h, v);
+    for (int w = 0; w < 4; ++w) {
+      const int r0 = first_dy(tile, w) * TW;
+      float* tw_ = dtab + w * a.ntabc;
+      for (int r = tid; r < a.ntabc; r += kThreads) {
+        const float v = tw_[r];
+        tw_[r] = 0.f;
+        if (v != 0.f && r0 + r < a.ntab) atomicAdd(a.dtable16 + (int64_t)(r0 + r) * a.nH + h, v);
+      }
     }
     const float s = warp_sum(dsc);
     dsc = 0.f;
@@ -244,17 +258,26 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
 #pragma unroll 1
   for (int ui = 0; ui < nu; ++ui) {
     const int64_t u = u0 + ui;
-    const int tile = (int)(u % a.ntiles);
-    const int64_t iw = u / a.ntiles;
-    const int64_t win = iw % a.nwin;
-    const int h = (int)(iw / a.nwin);
+    int tile, h;
+    int64_t win;
+    if (MODE == MODE_DQ) {                           // (head, tile, window): see the compact gradient tables above
+      win = u % a.nwin;
+      const int64_t it = u / a.nwin;
+      tile = (int)(it % a.ntiles);
+      h = (int)(it / a.ntiles);
+    } else {                                         // (head, window, tile): the window's row tables serve all its tiles
+      tile = (int)(u % a.ntiles);
+      const int64_t iw = u / a.ntiles;
+      win = iw % a.nwin;
+      h = (int)(iw / a.nwin);
+    }
     const int b = (int)(win / nW);
     const int wrem = (int)(win - (int64_t)b * nW);
     const int wh = wrem / g.nWw, ww = wrem - wh * g.nWw;
 
     // ---- per-head / per-window tables (every thread has finished the previous unit: its last MMA wait is behind it)
-    if (h != cur_h || win != cur_win) {
-      if (MODE == MODE_DQ && cur_h >= 0 && h != cur_h) flush_head(cur_h);
+    if (h != cur_h || win != cur_win || (MODE == MODE_DQ && tile != cur_tile)) {
+      if (MODE == MODE_DQ && cur_h >= 0 && (h != cur_h || tile != cur_tile)) flush_head(cur_h, cur_tile);
       __syncthreads();
       if (h != cur_h) {
         for (int t = tid; t < a.ntab; t += kThreads) tab[t] = a.table16[(int64_t)t * a.nH + h] * kLog2e;
@@ -282,6 +305,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
       }
       cur_h = h;
       cur_win = win;
+      cur_tile = tile;
       __syncthreads();
     }
 
@@ -297,7 +321,11 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
     // entry; DKV: this row is the key, `tabq + kof[query]`.
     const int off_st = MODE == MODE_DKV ? 4 * (ws - 1) * (TW + 1) - kof_st : 4 * (ws - 1) * (TW + 1) + kof_st;
     const uint32_t tabq = ptx::smem_u32(tab) + (uint32_t)off_st;
-    const uint32_t dtabq = ptx::smem_u32(dtabw) + (uint32_t)off_st;   // DQ: the same entry of this warp's gradient sums
+    // DQ: the same entry of this warp's gradient sums, counted from the warp's first table row; a row beyond the window
+    // (short last tile) never stores, and reads as if it sat at the start of the warp's first window row
+    const int dy0 = first_dy(tile, warp);
+    const uint32_t dtabq = ptx::smem_u32(dtabw) +
+                           (uint32_t)(row_valid ? off_st - 4 * dy0 * TW : 4 * (ws - 1) * (TW + 1));
     float lse2_st = INFINITY, d_st = 0.f;                           // DQ: per-query constants
     if (MODE == MODE_DQ && row_valid) {
       lse2_st = a.lse[(win * a.nH + h) * N + r_st] * kLog2e;
@@ -581,7 +609,8 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
                   dsc = fmaf(dsv, cosv, dsc);
                   // gradient of the bias table: warp-private sums.  The 32 lanes of a step hit 32 distinct entries (one
                   // key, 32 different queries); consecutive steps of different lanes alias, hence the warp barrier.
-                  sts_f32(dtabq + (uint32_t)boff, lds_f32(dtabq + (uint32_t)boff) + dsv);
+                  const float cur = lds_f32(dtabq + (uint32_t)boff);
+                  if (row_valid) sts_f32(dtabq + (uint32_t)boff, cur + dsv);
                   __syncwarp();
                 }
               }
@@ -691,7 +720,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
     }
     __syncthreads();                                 // the stationary tiles / tables may be overwritten now
   }
-  if (MODE == MODE_DQ && cur_h >= 0) flush_head(cur_h);
+  if (MODE == MODE_DQ && cur_h >= 0) flush_head(cur_h, cur_tile);
 
   ptx::tc_fence_before();
   __syncthreads();
@@ -701,10 +730,10 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
   }
 }
 
-size_t flash_smem(int mode, int KB, int ntab, int nmeta) {
+size_t flash_smem(int mode, int KB, int ntab, int ntabc, int nmeta) {
   const size_t kStage = 2 * (size_t)KB * 64;
   size_t s = 1024 + 2 * (size_t)kXTile + (size_t)NSTAGE * kStage + 2 * (size_t)NSTAGE * KB * 4 + 3 * (size_t)nmeta * 4 +
-             (size_t)ntab * 4 + (mode == MODE_DQ ? 4 * (size_t)ntab * 4 : 0) + 16;
+             (size_t)ntab * 4 + (mode == MODE_DQ ? 4 * (size_t)ntabc * 4 : 0) + 16;
   // at most four CTAs per SM (128 TMEM columns each): never let a fifth fit by shared memory
   const size_t floor_bytes = 46 * 1024;
   return s < floor_bytes ? floor_bytes : s;
@@ -712,7 +741,7 @@ size_t flash_smem(int mode, int KB, int ntab, int nmeta) {
 
 template <int MODE, int KB>
 int launch_flash_kb(const FlArgs& a, cudaStream_t st) {
-  const size_t smem = flash_smem(MODE, KB, a.ntab, a.nmeta);
+  const size_t smem = flash_smem(MODE, KB, a.ntab, a.ntabc, a.nmeta);
   BSW_REQUIRE(smem <= 227 * 1024, "attn(flash): window %dx%d needs %zu bytes of shared memory", a.g.ws, a.g.ws, smem);
   BSW_CUDA(cudaFuncSetAttribute(attn_flash_kernel<MODE, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // whole unified L1 as shared memory: several CTAs per SM.  (The occupancy query answers for the carve-out of the
@@ -755,6 +784,11 @@ int fill_args(FlArgs* a, int B, int H, int W, int C, int nH, int ws, int shift) 
   a->ntiles = (a->N + 127) / 128;
   a->rpt = a->N < 128 ? a->N : 128;
   a->ntab = (2 * ws - 1) * (2 * ws - 1);
+  {
+    // rows of the bias table one warp (32 consecutive query rows of a tile) can touch: ws - 1 + the window rows it spans
+    const int rows = ws - 1 + (31 / ws + 2);
+    a->ntabc = rows < 2 * ws - 1 ? rows * (2 * ws - 1) : a->ntab;
+  }
   set_block(a, 64);
   a->nwin = (int64_t)B * a->g.nWh * a->g.nWw;
   a->nunits = a->nwin * nH * a->ntiles;
