@@ -826,8 +826,9 @@ int attn_bwd_flash(const void* qkv, const void* out, const void* out_lo, const v
   a.vpad = vpad; a.dqkv = (__nv_bfloat16*)dqkv; a.dtable16 = dtable16; a.dscale = dscale; a.dvpad = dvpad;
   rc = attn_bwd_prep(dout, out, out_lo, (float*)workspace, (int64_t)B * H * W * nH, st);
   if (rc) return rc;
-  // backward passes: 64-token blocks, 48 where that divides a small window exactly (12x12)
-  set_block(&a, (a.N % 48 == 0 && a.N % 64 != 0 && a.N <= 192) ? 48 : 64);
+  // backward passes: blocks of 64 streamed tokens, or of 48 where that pads the window less (12x12: 144 = 3 x 48 exactly;
+  // 30x30: 900 -> 912 instead of 960)
+  set_block(&a, (a.N + 47) / 48 * 48 < (a.N + 63) / 64 * 64 ? 48 : 64);
   rc = launch_flash<MODE_DQ>(a, st);
   if (rc) return rc;
   return launch_flash<MODE_DKV>(a, st);
