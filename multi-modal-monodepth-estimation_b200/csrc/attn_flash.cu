@@ -65,6 +65,7 @@ struct FlArgs {
   WinGeom g;
   int C, nH, N, ntiles, rpt, kb, nkb, ntab, nmeta;
   int ntabc;                  // DQ: entries of a warp's COMPACT gradient table (see the kernel), <= ntab
+  int ntabq;                  // DQ: entries of the CTA's compact copy of the bias table (rows a 128-row tile can touch), <= ntab
   int64_t nwin, nunits;
 };
 
@@ -187,15 +188,17 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
   float* blk_d = blk_lse + NSTAGE * KB;
   int* tok = reinterpret_cast<int*>(blk_d + NSTAGE * KB);          // [nmeta] flat token index, -1 pad, -2 beyond the window
   int* kof = tok + a.nmeta;                                        // [nmeta] byte offset 4 (y TW + x) into the bias table
-  int* rid = kof + a.nmeta;                                        // [nmeta] shift-mask region id | beyond the window << 8
-  float* tab = reinterpret_cast<float*>(rid + a.nmeta);            // [ntab] bias table of the head, log2 units
+  unsigned char* rid = reinterpret_cast<unsigned char*>(kof + a.nmeta);   // [nmeta] shift-mask region id | beyond the window << 7
+  // bias table of the head, log2 units: [ntab]; DQ: only the [ntabq] entries of the table rows the CTA's row tile can touch
+  float* tab = reinterpret_cast<float*>(rid + a.nmeta);
+  const int ntab_s = MODE == MODE_DQ ? a.ntabq : a.ntab;
   // DQ: [4 warps][ntabc] private gradient sums of the bias table.  A warp's 32 query rows span at most 31 / ws + 2 window
   // rows, so it only ever touches ws - 1 + that many of the table's 2 ws - 1 rows (dy = y_query - y_key): the private
   // tables hold just those rows, indexed from the warp's first window row.  That is 54 % of the full table at 24 / 30
   // windows and makes room for one more CTA per SM (30x30: two instead of one).  The price: the units of a CTA run in
   // (head, row tile, window) order -- a warp's rows stay put while the windows stream by -- and the tables are flushed
   // when the (head, tile) pair changes.
-  float* dtab = tab + a.ntab;
+  float* dtab = tab + ntab_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t per = a.nunits / gridDim.x, rem = a.nunits % gridDim.x;
@@ -235,6 +238,8 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
   const bool compact = a.ntabc < a.ntab;
   // first table row (dy index) a warp's compact table holds while the CTA works on row tile `tile`
   auto first_dy = [&](int tile, int w) { return compact ? (tile * a.rpt + w * 32) / ws : 0; };
+  const bool compact_q = MODE == MODE_DQ && a.ntabq < a.ntab;
+  auto first_dy_cta = [&](int tile) { return compact_q ? (tile * a.rpt) / ws : 0; };
 
   auto flush_head = [&](int h, int tile) {
     // DQ: gradient sums of head h -> global (one atomic per touched table entry and warp)
@@ -279,15 +284,17 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
     if (h != cur_h || win != cur_win || (MODE == MODE_DQ && tile != cur_tile)) {
       if (MODE == MODE_DQ && cur_h >= 0 && (h != cur_h || tile != cur_tile)) flush_head(cur_h, cur_tile);
       __syncthreads();
-      if (h != cur_h) {
-        for (int t = tid; t < a.ntab; t += kThreads) tab[t] = a.table16[(int64_t)t * a.nH + h] * kLog2e;
+      if (h != cur_h || (compact_q && tile != cur_tile)) {
+        const int t0 = first_dy_cta(tile) * TW;
+        for (int t = tid; t < ntab_s; t += kThreads)
+          tab[t] = t0 + t < a.ntab ? a.table16[(int64_t)(t0 + t) * a.nH + h] * kLog2e : 0.f;
         sc = a.scale[h];
         scale2 = sc * kLog2e;
       }
       if (win != cur_win) {
         need_mask = g.shift > 0 && (wh == g.nWh - 1 || ww == g.nWw - 1);
         for (int r = tid; r < a.nmeta; r += kThreads) {
-          int t = -2, ko = 0, rg = 1 << 8;
+          int t = -2, ko = 0, rg = 1 << 7;
           if (r < N) {
             const int y = r / ws, x = r - y * ws;
             const int si = wh * ws + y, sj = ww * ws + x;
@@ -300,7 +307,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
           }
           tok[r] = t;
           kof[r] = ko;
-          rid[r] = rg;
+          rid[r] = (unsigned char)rg;
         }
       }
       cur_h = h;
@@ -316,11 +323,14 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
     // a warp without a single row (short last tile) only keeps the barriers company
     const bool warp_live = warp * 32 < a.rpt && tile * a.rpt + warp * 32 < N;
     const int t_st = row_valid ? tok[r_st] : -2;
-    const int kof_st = kof[row_valid ? r_st : 0], rid_st = rid[row_valid ? r_st : 0] & 0xff;
+    const int kof_st = kof[row_valid ? r_st : 0], rid_st = rid[row_valid ? r_st : 0] & 0x7f;
     // bias index = koff(query) + (ws-1)(TW+1) - koff(key).  FWD / DQ: this row is the query, `tabq - kof[key]` is the
     // entry; DKV: this row is the key, `tabq + kof[query]`.
     const int off_st = MODE == MODE_DKV ? 4 * (ws - 1) * (TW + 1) - kof_st : 4 * (ws - 1) * (TW + 1) + kof_st;
-    const uint32_t tabq = ptx::smem_u32(tab) + (uint32_t)off_st;
+    // (DQ: the CTA's copy of the table starts at the first table row its tile can touch; a row beyond the window reads as
+    // if it sat at the start of that row)
+    const uint32_t tabq = ptx::smem_u32(tab) +
+                          (uint32_t)((!compact_q || row_valid) ? off_st - 4 * first_dy_cta(tile) * TW : 4 * (ws - 1) * (TW + 1));
     // DQ: the same entry of this warp's gradient sums, counted from the warp's first table row; a row beyond the window
     // (short last tile) never stores, and reads as if it sat at the start of the warp's first window row
     const int dy0 = first_dy(tile, warp);
@@ -429,7 +439,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
           const bool tail_blk = (kb + 1) * KB > N;
           const bool general = need_mask || tail_blk;
           const int4* kof4 = reinterpret_cast<const int4*>(kof + kb * KB);
-          const int4* rid4 = reinterpret_cast<const int4*>(rid + kb * KB);
+          const uint32_t* rid4 = reinterpret_cast<const uint32_t*>(rid + kb * KB);     // four keys per word
           uint32_t sv[KB];
 #pragma unroll
           for (int c = 0; c < KB / 16; ++c) tmem_ld16(t_row + sb + c * 16, &sv[c * 16]);
@@ -446,15 +456,15 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
               const int kj[4] = {kk.x, kk.y, kk.z, kk.w};
               int rj[4] = {0, 0, 0, 0};
               if (GEN) {
-                const int4 rr = rid4[j4];
-                rj[0] = rr.x; rj[1] = rr.y; rj[2] = rr.z; rj[3] = rr.w;
+                const uint32_t rr = rid4[j4];
+                rj[0] = rr & 0xff; rj[1] = (rr >> 8) & 0xff; rj[2] = (rr >> 16) & 0xff; rj[3] = rr >> 24;
               }
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 float s2 = fmaf(__uint_as_float(sv[j4 * 4 + k]), scale2, lds_f32(tabq - (uint32_t)kj[k]));
                 if (GEN) {
-                  if (need_mask && (rj[k] & 0xff) != rid_st) s2 += kMaskLog2;
-                  if (rj[k] >> 8) s2 = -INFINITY;
+                  if (need_mask && (rj[k] & 0x7f) != rid_st) s2 += kMaskLog2;
+                  if (rj[k] >> 7) s2 = -INFINITY;
                 }
                 mx = fmaxf(mx, s2);
                 sv[j4 * 4 + k] = __float_as_uint(s2);
@@ -554,7 +564,7 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
       const bool tail_blk = (kb + 1) * KB > N;       // keys / queries beyond the window in this block
       const bool general = need_mask || tail_blk;    // CTA-uniform: most blocks take the copy without mask / tail tests
       const int4* kof4 = reinterpret_cast<const int4*>(kof + kb * KB);
-      const int4* rid4 = reinterpret_cast<const int4*>(rid + kb * KB);
+      const uint2* rid8 = reinterpret_cast<const uint2*>(rid + kb * KB);            // eight keys per pair of words
       ptx::mbar_wait(&bar_mma, ph);
       ph ^= 1;
       ptx::tc_fence_after();
@@ -578,8 +588,9 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
               kj[0] = m0.x; kj[1] = m0.y; kj[2] = m0.z; kj[3] = m0.w; kj[4] = m1.x; kj[5] = m1.y; kj[6] = m1.z; kj[7] = m1.w;
             }
             if (GEN) {
-              const int4 m0 = rid4[cc * 2], m1 = rid4[cc * 2 + 1];
-              rj[0] = m0.x; rj[1] = m0.y; rj[2] = m0.z; rj[3] = m0.w; rj[4] = m1.x; rj[5] = m1.y; rj[6] = m1.z; rj[7] = m1.w;
+              const uint2 m = rid8[cc];
+              rj[0] = m.x & 0xff; rj[1] = (m.x >> 8) & 0xff; rj[2] = (m.x >> 16) & 0xff; rj[3] = m.x >> 24;
+              rj[4] = m.y & 0xff; rj[5] = (m.y >> 8) & 0xff; rj[6] = (m.y >> 16) & 0xff; rj[7] = m.y >> 24;
             }
             float lsev[8], dvv[8];
             if (MODE == MODE_DKV) {
@@ -599,9 +610,9 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
                 const int boff = MODE == MODE_DQ ? -kj[e] : kj[e];
                 const float cosv = __uint_as_float(sv[e]);
                 float s2 = fmaf(cosv, scale2, lds_f32(tabq + (uint32_t)boff));
-                if (GEN && need_mask && (rj[e] & 0xff) != rid_st) s2 += kMaskLog2;
+                if (GEN && need_mask && (rj[e] & 0x7f) != rid_st) s2 += kMaskLog2;
                 float p = ex2(s2 - (MODE == MODE_DQ ? lse2_st : lsev[e]));
-                if (GEN && MODE == MODE_DQ && (rj[e] >> 8)) p = 0.f;              // key beyond the window
+                if (GEN && MODE == MODE_DQ && (rj[e] >> 7)) p = 0.f;              // key beyond the window
                 const float dsv = p * (__uint_as_float(dv[e]) - (MODE == MODE_DQ ? d_st : dvv[e]));
                 pl[e1] = p;
                 dl[e1] = dsv;
@@ -730,10 +741,10 @@ attn_flash_kernel(const __grid_constant__ FlArgs a) {
   }
 }
 
-size_t flash_smem(int mode, int KB, int ntab, int ntabc, int nmeta) {
+size_t flash_smem(int mode, int KB, int ntab, int ntabc, int ntabq, int nmeta) {
   const size_t kStage = 2 * (size_t)KB * 64;
-  size_t s = 1024 + 2 * (size_t)kXTile + (size_t)NSTAGE * kStage + 2 * (size_t)NSTAGE * KB * 4 + 3 * (size_t)nmeta * 4 +
-             (size_t)ntab * 4 + (mode == MODE_DQ ? 4 * (size_t)ntabc * 4 : 0) + 16;
+  size_t s = 1024 + 2 * (size_t)kXTile + (size_t)NSTAGE * kStage + 2 * (size_t)NSTAGE * KB * 4 + 2 * (size_t)nmeta * 4 +
+             (size_t)nmeta + (mode == MODE_DQ ? (size_t)ntabq * 4 + 4 * (size_t)ntabc * 4 : (size_t)ntab * 4) + 16;
   // at most four CTAs per SM (128 TMEM columns each): never let a fifth fit by shared memory
   const size_t floor_bytes = 46 * 1024;
   return s < floor_bytes ? floor_bytes : s;
@@ -741,7 +752,7 @@ size_t flash_smem(int mode, int KB, int ntab, int ntabc, int nmeta) {
 
 template <int MODE, int KB>
 int launch_flash_kb(const FlArgs& a, cudaStream_t st) {
-  const size_t smem = flash_smem(MODE, KB, a.ntab, a.ntabc, a.nmeta);
+  const size_t smem = flash_smem(MODE, KB, a.ntab, a.ntabc, a.ntabq, a.nmeta);
   BSW_REQUIRE(smem <= 227 * 1024, "attn(flash): window %dx%d needs %zu bytes of shared memory", a.g.ws, a.g.ws, smem);
   BSW_CUDA(cudaFuncSetAttribute(attn_flash_kernel<MODE, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // whole unified L1 as shared memory: several CTAs per SM.  (The occupancy query answers for the carve-out of the
@@ -785,9 +796,22 @@ int fill_args(FlArgs* a, int B, int H, int W, int C, int nH, int ws, int shift) 
   a->rpt = a->N < 128 ? a->N : 128;
   a->ntab = (2 * ws - 1) * (2 * ws - 1);
   {
-    // rows of the bias table one warp (32 consecutive query rows of a tile) can touch: ws - 1 + the window rows it spans
-    const int rows = ws - 1 + (31 / ws + 2);
-    a->ntabc = rows < 2 * ws - 1 ? rows * (2 * ws - 1) : a->ntab;
+    // rows of the bias table a warp (32 consecutive query rows of a tile) / a CTA (the whole tile) can touch: ws - 1 + the
+    // window rows it spans, maximised over the tiles and warps that exist
+    int span_w = 1, span_c = 1;
+    for (int t = 0; t < a->ntiles; ++t) {
+      const int r0 = t * a->rpt, rows_t = a->N - r0 < a->rpt ? a->N - r0 : a->rpt;
+      const int sc_ = (r0 % ws + rows_t - 1) / ws + 1;
+      if (sc_ > span_c) span_c = sc_;
+      for (int w = 0; w * 32 < rows_t; ++w) {
+        const int rw = r0 + w * 32, n_w = rows_t - w * 32 < 32 ? rows_t - w * 32 : 32;
+        const int sw = (rw % ws + n_w - 1) / ws + 1;
+        if (sw > span_w) span_w = sw;
+      }
+    }
+    const int TW_ = 2 * ws - 1;
+    a->ntabc = ws - 1 + span_w < TW_ ? (ws - 1 + span_w) * TW_ : a->ntab;
+    a->ntabq = ws - 1 + span_c < TW_ ? (ws - 1 + span_c) * TW_ : a->ntab;
   }
   set_block(a, 64);
   a->nwin = (int64_t)B * a->g.nWh * a->g.nWw;
